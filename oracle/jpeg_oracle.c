@@ -1,0 +1,512 @@
+/* oracle/jpeg_oracle.c -- TEST INFRASTRUCTURE ONLY: a CPU restatement of the reference's
+ * baseline-JPEG decode path (harutel/hls-jpeg-decoder).  It is the checker for the CUDA
+ * path, never the thing measured or shipped: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg may build, link or call it.
+ *
+ * PARITY PINNED: the reference publishes no golden vectors, so this port is
+ * pinned against the reference ITSELF, compiled from its own sources by oracle/build_ref.sh
+ * (oracle/_ref/libhjdref_*.so): tests/test_oracle.py checks coefficients, planes and RGB
+ * bit-for-bit on the reference's Lenna.jpg and on seeded PIL-generated files, and the
+ * committed tests/golden/ vectors were produced by that reference build.
+ *
+ * Every function cites the reference lines it restates.  Deliberate differences, all
+ * outside what the unmodified reference can decode:
+ *   - restart intervals are counted in MCUs (the reference mis-parses DRI, openjpg.cpp:441-446,
+ *     and sniffs bytes, loadjpg.cpp:535-550); identical to harness route B;
+ *   - grayscale (Nf = 1) decodes component 1 with Cb = Cr = 128 (reference: unsupported);
+ *   - components are addressed by position in SOF, not by id-as-index (openjpg.cpp:343);
+ *   - cosf() is evaluated once per (position, frequency) instead of 8192 times per block:
+ *     the table holds the very same float values, and the 64-term sum is formed in the
+ *     reference's order, so results are bit-identical (verified against oracle/_ref).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define HJDO_OK              0
+#define HJDO_ERR_NOT_JPEG   -1
+#define HJDO_ERR_TRUNCATED  -2
+#define HJDO_ERR_UNSUPPORTED -3
+#define HJDO_ERR_HUFFMAN    -4
+#define HJDO_ERR_RESTART    -5
+
+/* loadjpg.cpp:56-66 -- ZigZagArray[natural index] = position in the zig-zag sequence. */
+static const int kZigZag[64] = {
+    0,  1,  5,  6,  14, 15, 27, 28,
+    2,  4,  7,  13, 16, 26, 29, 42,
+    3,  8,  12, 17, 25, 30, 41, 43,
+    9,  11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54,
+    20, 22, 33, 38, 46, 51, 55, 60,
+    21, 34, 37, 47, 50, 56, 59, 61,
+    35, 36, 48, 49, 57, 58, 62, 63,
+};
+
+typedef struct {
+    /* canonical code list, openjpg.cpp:48-98 (GenHuffCodes / BuildHuffmanTable) */
+    int n;
+    int length[256];
+    int code[256];
+    int value[256];
+    /* per-length index for the search of loadjpg.cpp:335-392 */
+    int first[18];   /* index of the first code of length k */
+    int count[18];
+} huff_t;
+
+typedef struct {
+    unsigned width, height;
+    int ncomp;
+    int hf[4], vf[4], tq[4], cid[4];
+    int td[4], ta[4];
+    float q[4][64];         /* zig-zag order, as floats: openjpg.cpp:102-116 */
+    int q_present[4];
+    huff_t dc[4], ac[4];
+    int restart_interval;
+    const uint8_t* scan;    /* entropy-coded segment */
+    size_t scan_len;
+} frame_t;
+
+typedef struct {
+    const uint8_t* s;
+    size_t len, pos;
+    uint32_t reservoir;
+    unsigned nbits;
+} bits_t;
+
+/* ------------------------------------------------------------------ header ----------- */
+
+static void build_huffman(huff_t* h, const uint8_t* bits /*[16]*/, const uint8_t* vals)
+{
+    /* openjpg.cpp:73-98 + 48-66: one entry per symbol, lengths ascending; code = counter,
+       shifted left each time the length increases. */
+    int c = 0, k, j;
+    memset(h, 0, sizeof *h);
+    for (k = 1; k <= 16; k++) {
+        h->first[k] = c;
+        h->count[k] = bits[k - 1];
+        for (j = 0; j < bits[k - 1] && c < 256; j++) h->length[c++] = k;
+    }
+    h->n = c;
+    {
+        int counter = 0, len = 1, i;
+        for (i = 0; i < c; i++) {
+            while (h->length[i] > len) { counter <<= 1; len++; }
+            h->code[i] = counter & 0xFFFF;      /* stBlock.code is unsigned short, loadjpg.h:101 */
+            h->value[i] = vals[i];
+            counter++;
+        }
+    }
+}
+
+static int parse_header(const uint8_t* p, size_t size, frame_t* f)
+{
+    /* openjpg.cpp:371-496 (ParseJFIF / JpegParseHeader), 120-155 (DQT), 310-367 (SOF),
+       234-305 (DHT), 160-229 (SOS). */
+    size_t i = 2;
+    int have_sof = 0;
+    memset(f, 0, sizeof *f);
+    if (size < 4 || p[0] != 0xFF || p[1] != 0xD8) return HJDO_ERR_NOT_JPEG;   /* 481 */
+    for (;;) {
+        int m;
+        size_t len;
+        if (i + 4 > size) return HJDO_ERR_TRUNCATED;
+        if (p[i] != 0xFF) return HJDO_ERR_NOT_JPEG;                              /* 383-386 */
+        while (i < size && p[i] == 0xFF) i++;                                    /* 389-392 */
+        if (i >= size) return HJDO_ERR_TRUNCATED;
+        m = p[i++];
+        if (m == 0xD8 || m == 0xD9) continue;                                    /* 433-438 */
+        if (i + 2 > size) return HJDO_ERR_TRUNCATED;
+        len = ((size_t)p[i] << 8) | p[i + 1];
+        if (len < 2 || i + len > size) return HJDO_ERR_TRUNCATED;
+        if (m == 0xDB) {                                                         /* DQT */
+            size_t k = i + 2, end = i + len;
+            while (k < end) {
+                int pq = p[k] >> 4, tq = p[k] & 15, c;
+                k++;
+                if (pq != 0 || tq >= 4) return HJDO_ERR_UNSUPPORTED;             /* 136-148 */
+                if (k + 64 > end) return HJDO_ERR_TRUNCATED;
+                for (c = 0; c < 64; c++) f->q[tq][c] = (float)p[k + c];          /* 102-116 */
+                f->q_present[tq] = 1;
+                k += 64;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {                                     /* SOF0 (+ Huffman-extended 8-bit) */
+            int c;
+            if (len < 8 || p[i + 2] != 8) return HJDO_ERR_UNSUPPORTED;
+            f->height = (p[i + 3] << 8) | p[i + 4];
+            f->width  = (p[i + 5] << 8) | p[i + 6];
+            f->ncomp  = p[i + 7];
+            if ((f->ncomp != 1 && f->ncomp != 3) || len < 8u + 3u * f->ncomp) return HJDO_ERR_UNSUPPORTED;
+            for (c = 0; c < f->ncomp; c++) {
+                f->cid[c] = p[i + 8 + 3 * c];
+                f->hf[c]  = p[i + 9 + 3 * c] >> 4;                               /* 344-345 */
+                f->vf[c]  = p[i + 9 + 3 * c] & 15;
+                f->tq[c]  = p[i + 10 + 3 * c];
+                if (f->tq[c] >= 4) return HJDO_ERR_UNSUPPORTED;
+            }
+            have_sof = 1;
+        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return HJDO_ERR_UNSUPPORTED;                                         /* progressive etc. */
+        } else if (m == 0xC4) {                                                  /* DHT */
+            size_t k = i + 2, end = i + len;
+            while (k < end) {
+                int tc = p[k] >> 4, th = p[k] & 15, cnt = 0, b;
+                if (k + 17 > end) return HJDO_ERR_TRUNCATED;
+                for (b = 0; b < 16; b++) cnt += p[k + 1 + b];                    /* 263-267 */
+                if (cnt > 256 || th >= 4 || tc > 1) return HJDO_ERR_UNSUPPORTED; /* 269-276 */
+                if (k + 17 + cnt > end) return HJDO_ERR_TRUNCATED;
+                build_huffman(tc ? &f->ac[th] : &f->dc[th], p + k + 1, p + k + 17);
+                k += 17 + cnt;
+            }
+        } else if (m == 0xDD) {                                                  /* DRI: Ri, not Lr */
+            if (len < 4) return HJDO_ERR_TRUNCATED;
+            f->restart_interval = (p[i + 2] << 8) | p[i + 3];
+        } else if (m == 0xDA) {                                                  /* SOS */
+            int ns, c;
+            if (!have_sof) return HJDO_ERR_UNSUPPORTED;
+            ns = p[i + 2];
+            if (ns != f->ncomp || len < 6u + 2u * ns) return HJDO_ERR_UNSUPPORTED;   /* single scan */
+            for (c = 0; c < ns; c++) {
+                int cs = p[i + 3 + 2 * c], t = p[i + 4 + 2 * c], j, found = -1;
+                for (j = 0; j < f->ncomp; j++) if (f->cid[j] == cs) found = j;
+                if (found < 0 || (t >> 4) >= 4 || (t & 15) >= 4) return HJDO_ERR_UNSUPPORTED;
+                f->td[found] = t >> 4;                                           /* 212-213 */
+                f->ta[found] = t & 15;
+            }
+            f->scan = p + i + len;
+            f->scan_len = size - (i + len);
+            break;
+        }
+        i += len;                                                                /* 461 */
+    }
+    if (f->width == 0 || f->height == 0) return HJDO_ERR_UNSUPPORTED;
+    if (f->ncomp == 3) {
+        /* The reference assumes chroma 1x1 and luma 1 or 2 (loadjpg.cpp:945-997, 884-932). */
+        if (f->hf[1] != 1 || f->vf[1] != 1 || f->hf[2] != 1 || f->vf[2] != 1) return HJDO_ERR_UNSUPPORTED;
+        if (f->hf[0] < 1 || f->hf[0] > 2 || f->vf[0] < 1 || f->vf[0] > 2) return HJDO_ERR_UNSUPPORTED;
+    }
+    return HJDO_OK;
+}
+
+/* ------------------------------------------------------------------ entropy ---------- */
+
+static unsigned stream_byte(const bits_t* b, size_t at) { return at < b->len ? b->s[at] : 0; }
+
+static void fill_nbits(bits_t* b, unsigned limit)
+{
+    /* loadjpg.cpp:446-484, live branch 468-482: at most two bytes per call, each only while
+       nbits < limit; FF 00 -> FF; FF xx (xx != 0) is inserted as data. */
+    int byte_cnt;
+    for (byte_cnt = 0; byte_cnt < 2; byte_cnt++) {
+        if (b->nbits < limit) {
+            unsigned c = stream_byte(b, b->pos);
+            b->pos++;
+            b->reservoir <<= 8;
+            if (c == 0xFF && stream_byte(b, b->pos) == 0x00) b->pos++;
+            b->reservoir |= c;
+            b->nbits += 8;
+        }
+    }
+}
+
+static int is_in_huffman_codes(const huff_t* h, int code, int k, int* out)
+{
+    /* loadjpg.cpp:335-392: match iff code == and length == k.  Canonical codes of one length
+       are consecutive, so the linear scan reduces to a range test. */
+    int n = h->count[k], first = h->first[k];
+    if (n > 0) {
+        int c0 = h->code[first];
+        if (code >= c0 && code < c0 + n) { *out = h->value[first + (code - c0)]; return 1; }
+    }
+    return 0;
+}
+
+static int determine_sign(int val, int nbits)
+{
+    /* loadjpg.cpp:396-409 */
+    if (val < (1 << (nbits - 1))) val = val + (int)(0xFFFFFFFFu << nbits) + 1;
+    return val;
+}
+
+static unsigned take_bits(bits_t* b, unsigned n)
+{
+    /* loadjpg.cpp:647-652 / 793-798 */
+    unsigned v;
+    fill_nbits(b, n);
+    v = b->reservoir >> (b->nbits - n);
+    b->nbits -= n;
+    b->reservoir &= ((1u << b->nbits) - 1u);
+    return v;
+}
+
+static int process_huffman_block(int16_t dct[64], int16_t* prev_dc, const huff_t* htdc,
+                                 const huff_t* htac, bits_t* b)
+{
+    /* loadjpg.cpp:497-863 with restart sniffing removed (m_restart_interval == 0). */
+    int k, found = 0, value = 0, nr = 1, eob = 0, err = 0;
+    memset(dct, 0, 128);                                                         /* 523-527 */
+    for (k = 1; k < 16; k++) {                                                   /* 562: DC, k = 1..15 */
+        int code;
+        fill_nbits(b, k);
+        code = (int)(b->reservoir >> (b->nbits - k));                            /* 584 */
+        if (is_in_huffman_codes(htdc, code, k, &value)) {
+            fill_nbits(b, k);                                                    /* 607-609 */
+            b->nbits -= k;
+            b->reservoir &= ((1u << b->nbits) - 1u);
+            found = 1;
+            if (value == 0) {
+                dct[0] = *prev_dc;                                               /* 619-627 */
+            } else {
+                int16_t data = (int16_t)take_bits(b, (unsigned)value);
+                data = (int16_t)determine_sign(data, value);                     /* 656 */
+                dct[0] = (int16_t)(data + *prev_dc);                             /* 664-665 */
+                *prev_dc = dct[0];
+            }
+            break;
+        }
+    }
+    if (!found) err = HJDO_ERR_HUFFMAN;                                          /* 680-685: printf only */
+    while (nr <= 63 && !eob) {                                                   /* 700 */
+        int matched = 0;
+        for (k = 1; k <= 16; k++) {                                              /* 713 */
+            int code;
+            fill_nbits(b, k);
+            code = (int)(b->reservoir >> (b->nbits - k));                        /* 732 */
+            if (is_in_huffman_codes(htac, code, k, &value)) {
+                unsigned size_val, count_0;
+                fill_nbits(b, k);
+                b->nbits -= k;                                                   /* 758-759 */
+                b->reservoir &= ((1u << b->nbits) - 1u);
+                size_val = value & 0xF;                                          /* 768-769 */
+                count_0 = value >> 4;
+                if (size_val == 0) {
+                    if (count_0 == 0) eob = 1;                                   /* 773 */
+                    else if (count_0 == 0xF) nr += 16;                           /* 774 */
+                } else {
+                    int16_t data;
+                    nr += count_0;                                               /* 778 */
+                    data = (int16_t)take_bits(b, size_val);
+                    data = (int16_t)determine_sign(data, size_val);              /* 802 */
+                    if (nr <= 63) dct[nr] = data;                                /* 806; reference writes OOB */
+                    else err = HJDO_ERR_HUFFMAN;
+                    nr++;
+                }
+                matched = 1;
+                break;
+            }
+        }
+        if (!matched) { err = HJDO_ERR_HUFFMAN; break; }   /* reference would spin forever (700-829) */
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------ IDCT ------------- */
+
+static float g_cos[8][8];     /* g_cos[p][k] = cosf(((2p+1) * k * PI) / 16), PI = 3.14f (loadjpg.cpp:108,120) */
+static float g_cc[8][8];      /* C(u) * C(v), loadjpg.cpp:96-102,120 */
+static int g_tables_ready = 0;
+
+static float c_of(int u) { return u == 0 ? (1.0f / sqrtf(2)) : 1.0f; }           /* 96-102 */
+
+static void init_tables(void)
+{
+    const float PI = 3.14f;
+    int p, k;
+    if (g_tables_ready) return;
+    for (p = 0; p < 8; p++)
+        for (k = 0; k < 8; k++) {
+            g_cos[p][k] = cosf(((2 * p + 1) * k * PI) / 16);
+            g_cc[p][k] = c_of(p) * c_of(k);
+        }
+    g_tables_ready = 1;
+}
+
+/* Exposed so that the product can be checked against the very constants used here. */
+void hjdo_idct_tables(float cos_out[64], float cc_out[64])
+{
+    init_tables();
+    memcpy(cos_out, g_cos, sizeof g_cos);
+    memcpy(cc_out, g_cc, sizeof g_cc);
+}
+
+static uint8_t clamp_u8(int i) { return i < 0 ? 0 : (i > 255 ? 255 : (uint8_t)i); }  /* 83-91 */
+
+/* loadjpg.cpp:184-228 DecodeSingleBlock: dequantise (144-152), de-zig-zag (156-163),
+   transpose (167-180), direct-form IDCT (105-140), +128, clamp, store rows. */
+void hjdo_decode_single_block(const int16_t coef[64], const float q[64], uint8_t* out, int stride)
+{
+    int16_t data[64], block[64], arr[8][8];
+    int c, i, x, y, u, v;
+    init_tables();
+    for (c = 0; c < 64; c++) data[c] = (int16_t)(int)(coef[c] * q[c]);           /* 150 */
+    for (i = 0; i < 64; i++) block[i] = data[kZigZag[i]];                        /* 161 */
+    for (y = 0, c = 0; y < 8; y++)
+        for (x = 0; x < 8; x++) arr[x][y] = block[c++];                          /* 176 */
+    for (y = 0; y < 8; y++) {
+        for (x = 0; x < 8; x++) {
+            float sum = 0;
+            int16_t val;
+            for (u = 0; u < 8; u++)
+                for (v = 0; v < 8; v++)
+                    sum += g_cc[u][v] * arr[u][v] * g_cos[x][u] * g_cos[y][v];   /* 120 */
+            val = (int16_t)(int)(0.25 * sum);                                    /* 123, 136 */
+            val = (int16_t)(val + 128);                                          /* 137 */
+            out[y * stride + x] = clamp_u8(val);                                 /* 219 */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ colour ----------- */
+
+/* loadjpg.cpp:867-880, called as (yc, cr, cb) at 918: names swapped, maths as below. */
+void hjdo_ycc_to_rgb(int yc, int cb, int cr, uint8_t* rgb)
+{
+    float red, green, blue;
+    red   = yc + 1.402f * (cr - 128);
+    green = yc - 0.34414f * (cb - 128) - 0.71414f * (cr - 128);
+    blue  = yc + 1.772f * (cb - 128);
+    rgb[0] = clamp_u8((int)red);
+    rgb[1] = clamp_u8((int)green);
+    rgb[2] = clamp_u8((int)blue);
+}
+
+/* ------------------------------------------------------------------ top -------------- */
+
+int hjdo_get_image_size(const uint8_t* jpg, size_t size, unsigned* w, unsigned* h, int* ncomp,
+                        int* hf, int* vf, int* ri)
+{
+    frame_t* f = (frame_t*)malloc(sizeof *f);
+    int rc;
+    if (!f) return HJDO_ERR_TRUNCATED;
+    rc = parse_header(jpg, size, f);
+    if (rc == HJDO_OK) {
+        if (w) *w = f->width;
+        if (h) *h = f->height;
+        if (ncomp) *ncomp = f->ncomp;
+        if (hf) *hf = f->ncomp == 3 ? f->hf[0] : 1;
+        if (vf) *vf = f->ncomp == 3 ? f->vf[0] : 1;
+        if (ri) *ri = f->restart_interval;
+    }
+    free(f);
+    return rc;
+}
+
+/* Same contract as hjdref_decode(mode 1) in oracle/ref_harness.cpp.
+   stages: bit 0 = entropy only (skip IDCT + colour; planes/rgb untouched). */
+int hjdo_decode(const uint8_t* jpg, size_t size, int stages, int16_t* coef, uint8_t* planes,
+                uint8_t* rgb, unsigned* out_w, unsigned* out_h)
+{
+    frame_t* f = (frame_t*)malloc(sizeof *f);
+    bits_t b;
+    int rc, err = 0, c;
+    int16_t prev_dc[4] = {0, 0, 0, 0};                                           /* 1159-1162 */
+    int16_t dct[64];
+    uint8_t tY[256], tCb[64], tCr[64];
+    unsigned hF, vF, xs, ys, mcus_x, mcus_y, x, y, mx, my, mcu = 0;
+    size_t ypw, yph, cpw, cph;
+    uint8_t *pY, *pCb, *pCr;
+    const int entropy_only = stages & 1;
+    if (!f) return HJDO_ERR_TRUNCATED;
+    rc = parse_header(jpg, size, f);
+    if (rc != HJDO_OK) { free(f); return rc; }
+    if (out_w) *out_w = f->width;
+    if (out_h) *out_h = f->height;
+    init_tables();
+    hF = f->ncomp == 3 ? f->hf[0] : 1;
+    vF = f->ncomp == 3 ? f->vf[0] : 1;
+    xs = 8 * hF; ys = 8 * vF;                                                    /* 1164-1165 */
+    mcus_x = (f->width + xs - 1) / xs; mcus_y = (f->height + ys - 1) / ys;
+    ypw = (size_t)mcus_x * xs; yph = (size_t)mcus_y * ys; cpw = (size_t)mcus_x * 8; cph = (size_t)mcus_y * 8;
+    pY = planes; pCb = planes ? planes + ypw * yph : 0; pCr = planes ? pCb + cpw * cph : 0;
+    memset(&b, 0, sizeof b);                                                     /* 1148-1149 */
+    b.s = f->scan; b.len = f->scan_len;
+    memset(tCb, 128, 64); memset(tCr, 128, 64);
+
+    for (y = 0, my = 0; y < f->height; y += ys, my++) {                          /* 1170 */
+        for (x = 0, mx = 0; x < f->width; x += xs, mx++, mcu++) {                /* 1174 */
+            unsigned bx, by, px, py;
+            if (f->restart_interval && mcu && mcu % (unsigned)f->restart_interval == 0) {
+                if (stream_byte(&b, b.pos) != 0xFF || (stream_byte(&b, b.pos + 1) & 0xF8) != 0xD0) err = HJDO_ERR_RESTART;
+                else b.pos += 2;
+                b.reservoir = 0; b.nbits = 0;
+                for (c = 0; c < 4; c++) prev_dc[c] = 0;
+            }
+            /* DecodeMCU, loadjpg.cpp:945-997 */
+            for (by = 0; by < vF; by++)
+                for (bx = 0; bx < hF; bx++) {
+                    int e = process_huffman_block(dct, &prev_dc[0], &f->dc[f->td[0]], &f->ac[f->ta[0]], &b);
+                    if (e && !err) err = e;
+                    if (coef) { memcpy(coef, dct, 128); coef += 64; }
+                    if (!entropy_only)
+                        hjdo_decode_single_block(dct, f->q[f->tq[0]], &tY[bx * 8 + by * 64 * hF], (int)(hF * 8)); /* 958-970 */
+                }
+            if (f->ncomp == 3) {
+                int e = process_huffman_block(dct, &prev_dc[1], &f->dc[f->td[1]], &f->ac[f->ta[1]], &b);
+                if (e && !err) err = e;
+                if (coef) { memcpy(coef, dct, 128); coef += 64; }
+                if (!entropy_only) hjdo_decode_single_block(dct, f->q[f->tq[2]], tCb, 8);   /* 984: Cr's q-table (sic) */
+                e = process_huffman_block(dct, &prev_dc[2], &f->dc[f->td[2]], &f->ac[f->ta[2]], &b);
+                if (e && !err) err = e;
+                if (coef) { memcpy(coef, dct, 128); coef += 64; }
+                if (!entropy_only) hjdo_decode_single_block(dct, f->q[f->tq[2]], tCr, 8);   /* 996 */
+            }
+            if (entropy_only) continue;
+            if (planes) {
+                unsigned r;
+                for (r = 0; r < ys; r++) memcpy(pY + ((size_t)my * ys + r) * ypw + (size_t)mx * xs, tY + r * xs, xs);
+                for (r = 0; r < 8; r++) {
+                    memcpy(pCb + ((size_t)my * 8 + r) * cpw + (size_t)mx * 8, tCb + r * 8, 8);
+                    memcpy(pCr + ((size_t)my * 8 + r) * cpw + (size_t)mx * 8, tCr + r * 8, 8);
+                }
+            }
+            if (rgb) {
+                /* YCrCB_to_RGB24_Block8x8, loadjpg.cpp:884-932 */
+                for (py = 0; py < ys; py++)
+                    for (px = 0; px < xs; px++) {
+                        int yoff, coff;
+                        if (px + x >= f->width) continue;                        /* 907 */
+                        if (py + y >= f->height) continue;                       /* 908 */
+                        yoff = (int)(px + py * xs);                              /* 911 */
+                        coff = (int)(px * (1.0f / hF)) + (int)(py * (1.0f / vF)) * 8;   /* 912 */
+                        hjdo_ycc_to_rgb(tY[yoff], tCb[coff], tCr[coff],
+                                        rgb + ((size_t)(y + py) * f->width + (x + px)) * 3);   /* 921-925 */
+                    }
+            }
+        }
+    }
+    free(f);
+    return err;
+}
+
+/* WriteBMP24, openjpg.cpp:504-570: 54-byte header, bottom-up rows, B,G,R on disk, rows padded to 4. */
+size_t hjdo_bmp24_size(unsigned w, unsigned h)
+{
+    unsigned pad = (4 - (w * 3) % 4) % 4;                                        /* 534-535 */
+    return (size_t)w * h * 3 + (size_t)h * pad + 54;                             /* 541 */
+}
+
+void hjdo_bmp24_encode(unsigned w, unsigned h, const uint8_t* rgb, uint8_t* out)
+{
+    unsigned pad = (4 - (w * 3) % 4) % 4;
+    uint32_t file_size = (uint32_t)hjdo_bmp24_size(w, h);
+    uint8_t* o = out;
+    int y;
+    unsigned x, k;
+    memset(o, 0, 54);
+    o[0] = 'B'; o[1] = 'M';
+    o[2] = file_size & 255; o[3] = (file_size >> 8) & 255; o[4] = (file_size >> 16) & 255; o[5] = file_size >> 24;
+    o[10] = 54;                                                                  /* iOffsetBits */
+    o[14] = 40;                                                                  /* iSizeHeader */
+    o[18] = w & 255; o[19] = (w >> 8) & 255; o[20] = (w >> 16) & 255; o[21] = w >> 24;
+    o[22] = h & 255; o[23] = (h >> 8) & 255; o[24] = (h >> 16) & 255; o[25] = h >> 24;
+    o[26] = 1;                                                                   /* iPlanes */
+    o[28] = 24;                                                                  /* iBitCount */
+    o += 54;
+    for (y = (int)h - 1; y >= 0; y--) {                                          /* 555 */
+        for (x = 0; x < w; x++) {
+            const uint8_t* p = rgb + ((size_t)x + (size_t)w * y) * 3;
+            *o++ = p[2]; *o++ = p[1]; *o++ = p[0];                               /* 559-561 */
+        }
+        for (k = 0; k < pad; k++) *o++ = 0;                                      /* 563-567 */
+    }
+}
