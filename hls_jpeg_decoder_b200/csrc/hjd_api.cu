@@ -1,0 +1,685 @@
+// csrc/hjd_api.cu -- the C ABI of include/hjd.h: batch handle, HBM slabs, launches.
+//
+// Host-side counterpart of the reference's ConvertJpgFile / JpegDecodeHW call sequence
+// (openjpg.cpp:593-684): load -> parse -> decode -> (write BMP).  Here "decode" is a set of
+// kernel launches over flat HBM slabs holding N images, and nothing is decoded on the CPU.
+#include "../../include/hjd.h"
+#include "hjd_types.h"
+#include "jpeg_parse.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* what, const char* detail = nullptr)
+{
+    g_err = what;
+    if (detail) { g_err += ": "; g_err += detail; }
+    return code;
+}
+
+#define CU(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) return fail(HJD_ERR_CUDA, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// grow-only buffers
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 16 + 4096;      // slack so that slowly growing batches do not reallocate
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------------------------------
+// batch
+// ------------------------------------------------------------------------------------------
+struct FileRef { const uint8_t* ptr; int64_t size; uint64_t dev_off; };
+
+struct hjd_batch {
+    int device = 0;
+    unsigned flags = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t mark[4] = {nullptr, nullptr, nullptr, nullptr};   // hjd_batch_mark
+
+    // host metadata of the uploaded batch
+    std::vector<HjdImageDesc> imgs;
+    std::vector<int32_t> parse_status;
+    std::vector<HjdTableSet> tsets;
+    std::vector<HjdQuantSet> qsets;
+    std::vector<HjdEntropyWork> work;
+    std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
+    std::vector<uint8_t> host_restart_warn;     // HJD_FLAG_HOST_SCAN only
+    std::unordered_map<uint64_t, uint32_t> tset_of, qset_of;
+    uint64_t total_blocks = 0, rgb_bytes = 0, plane_bytes = 0, scan_bytes = 0, pixels = 0, arena_bytes = 0;
+    uint32_t total_intervals = 0, max_blocks = 0, max_w = 0, max_h = 0;
+    bool any_parse_error = false;
+    bool uploaded = false, decoded = false;
+    int launches = 0;
+
+    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_istart, d_coef, d_planes, d_rgb, d_status;
+    PinBuf h_meta;
+};
+
+static void compute_idct_constants(float cos_tab[64], float* cc0, float* cc00)
+{
+    // The very expressions of the reference, evaluated by the host libm (loadjpg.cpp:96-102,108,120).
+    const float PI = 3.14f;
+    for (int p = 0; p < 8; p++)
+        for (int k = 0; k < 8; k++) cos_tab[p * 8 + k] = cosf(((2 * p + 1) * k * PI) / 16);
+    volatile float c0 = 1.0f / sqrtf(2);
+    *cc0 = c0 * 1.0f;
+    *cc00 = c0 * c0;
+}
+
+extern "C" void hjd_get_idct_tables(float cos_tab[64], float cc[64])
+{
+    float c0, c00;
+    compute_idct_constants(cos_tab, &c0, &c00);
+    for (int u = 0; u < 8; u++)
+        for (int v = 0; v < 8; v++) cc[u * 8 + v] = (u == 0 && v == 0) ? c00 : ((u == 0 || v == 0) ? c0 : 1.0f);
+}
+
+extern "C" int hjd_version(void) { return HJD_VERSION; }
+extern "C" const char* hjd_last_error(void) { return g_err.c_str(); }
+
+extern "C" int hjd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
+{
+    int n = hjd_device_count();
+    if (n <= 0) { fail(HJD_ERR_CUDA, "hjd_batch_create", "no CUDA device available (this library has no CPU fallback)"); return nullptr; }
+    if (device < 0 || device >= n) { fail(HJD_ERR_ARG, "hjd_batch_create", "bad device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(HJD_ERR_CUDA, "cudaSetDevice"); return nullptr; }
+    hjd_batch* b = new hjd_batch();
+    b->device = device;
+    b->flags = flags;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    b->own_stream = true;
+    for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev[i]);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&b->mark[i]);
+    if (e == cudaSuccess) {
+        float cos_tab[64], c0, c00;
+        compute_idct_constants(cos_tab, &c0, &c00);
+        e = hjd_set_idct_constants(cos_tab, c0, c00);
+    }
+    if (e != cudaSuccess) {
+        fail(HJD_ERR_CUDA, "hjd_batch_create", cudaGetErrorString(e));
+        hjd_batch_destroy(b);
+        return nullptr;
+    }
+    return b;
+}
+
+extern "C" void hjd_batch_destroy(hjd_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release();
+    b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
+    b->h_meta.release();
+    for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    for (int i = 0; i < 4; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+extern "C" int hjd_batch_set_stream(hjd_batch* b, void* cuda_stream)
+{
+    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_set_stream", "null batch");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    b->stream = (cudaStream_t)cuda_stream;
+    b->own_stream = false;
+    return HJD_OK;
+}
+
+// Parse + lay out + upload.  files[i].dev_off must already hold the arena offset of file i.
+static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_t* contiguous_src,
+                         uint64_t contiguous_bytes)
+{
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));     // staging buffers of the previous batch are free again
+    const int n = (int)files.size();
+    b->imgs.assign(n, HjdImageDesc());
+    b->parse_status.assign(n, 0);
+    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear();
+    b->host_istart.clear();
+    b->host_restart_warn.assign(n, 0);
+    b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
+    b->total_intervals = b->max_blocks = b->max_w = b->max_h = 0;
+    b->any_parse_error = false;
+    b->uploaded = b->decoded = false;
+
+    HjdParsed ps;
+    for (int i = 0; i < n; i++) {
+        HjdImageDesc& d = b->imgs[i];
+        memset(&d, 0, sizeof d);
+        d.interval_base = b->total_intervals;
+        d.block_base = b->total_blocks;
+        d.rgb_off = b->rgb_bytes;
+        d.y_off = d.cb_off = d.cr_off = b->plane_bytes;
+        int st = (files[i].ptr && files[i].size > 0) ? hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &ps)
+                                                     : HJD_IMG_ERR_NOT_JPEG;
+        if (st == HJD_IMG_OK && ps.scan_len > 0xFFFFFF00ull) st = HJD_IMG_ERR_UNSUPPORTED;
+        uint32_t tset = 0, qset = 0;
+        if (st == HJD_IMG_OK) {
+            const uint64_t tk = hjd_table_key(ps);
+            auto it = b->tset_of.find(tk);
+            if (it != b->tset_of.end()) tset = it->second;
+            else {
+                HjdTableSet ts;
+                st = hjd_build_table_set(ps, &ts);
+                if (st == HJD_IMG_OK) { tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_of[tk] = tset; }
+            }
+        }
+        if (st == HJD_IMG_OK) {
+            const uint64_t qk = hjd_quant_key(ps);
+            auto it = b->qset_of.find(qk);
+            if (it != b->qset_of.end()) qset = it->second;
+            else {
+                HjdQuantSet qs;
+                hjd_build_quant_set(ps, &qs);
+                qset = (uint32_t)b->qsets.size(); b->qsets.push_back(qs); b->qset_of[qk] = qset;
+            }
+        }
+        b->parse_status[i] = st;
+        if (st != HJD_IMG_OK) { b->any_parse_error = true; continue; }   // n_intervals = n_blocks = 0: skipped
+
+        d.width = ps.width; d.height = ps.height;
+        d.ncomp = (uint8_t)ps.ncomp; d.hf = (uint8_t)ps.hf; d.vf = (uint8_t)ps.vf;
+        d.blocks_per_mcu = (uint8_t)(ps.ncomp == 3 ? ps.hf * ps.vf + 2 : 1);
+        d.mcus_x = (ps.width + 8 * ps.hf - 1) / (8 * ps.hf);            // loadjpg.cpp:1170-1174
+        d.mcus_y = (ps.height + 8 * ps.vf - 1) / (8 * ps.vf);
+        d.n_mcus = d.mcus_x * d.mcus_y;
+        d.restart_interval = ps.restart_interval;
+        d.n_intervals = ps.restart_interval ? (d.n_mcus + ps.restart_interval - 1) / ps.restart_interval : 1;
+        d.scan_len = (uint32_t)ps.scan_len;
+        d.scan_off = files[i].dev_off + ps.scan_off;
+        d.table_set = tset; d.quant_set = qset;
+        d.n_blocks = (uint64_t)d.n_mcus * d.blocks_per_mcu;
+        d.y_pitch = d.mcus_x * 8 * ps.hf;
+        d.c_pitch = d.mcus_x * 8;
+        const uint64_t ysz = (uint64_t)d.y_pitch * d.mcus_y * 8 * ps.vf;
+        const uint64_t csz = ps.ncomp == 3 ? (uint64_t)d.c_pitch * d.mcus_y * 8 : 0;
+        d.y_off = b->plane_bytes;
+        d.cb_off = d.y_off + align_up(ysz, 256);
+        d.cr_off = d.cb_off + align_up(csz, 256);
+        b->plane_bytes = d.cr_off + align_up(csz, 256);
+        b->rgb_bytes += align_up((uint64_t)ps.width * ps.height * 3, 256);
+        b->total_intervals += d.n_intervals;
+        b->total_blocks += d.n_blocks;
+        b->scan_bytes += ps.scan_len;
+        b->pixels += (uint64_t)ps.width * ps.height;
+        if (d.n_blocks > b->max_blocks) b->max_blocks = (uint32_t)d.n_blocks;
+        if (ps.width > b->max_w) b->max_w = ps.width;
+        if (ps.height > b->max_h) b->max_h = ps.height;
+
+        if (b->flags & HJD_FLAG_HOST_SCAN) {
+            const size_t at = b->host_istart.size();
+            b->host_istart.resize(at + d.n_intervals, (uint32_t)ps.scan_len);
+            const uint32_t found = hjd_host_find_intervals(files[i].ptr + ps.scan_off, ps.scan_len,
+                                                           b->host_istart.data() + at, d.n_intervals);
+            if (ps.restart_interval && found != d.n_intervals) b->host_restart_warn[i] = 1;
+        }
+    }
+    if (b->total_blocks >= 0xFFFFFFFFull) return fail(HJD_ERR_ARG, "hjd_batch_upload", "batch exceeds 2^32 blocks");
+
+    // entropy work list: runs of <= HJD_ENT_THREADS consecutive intervals sharing one table set
+    {
+        uint32_t cur_first = 0, cur_n = 0, cur_img = 0, cur_ts = 0;
+        for (int i = 0; i < n; i++) {
+            const HjdImageDesc& d = b->imgs[i];
+            uint32_t left = d.n_intervals, g = d.interval_base;
+            while (left) {
+                if (cur_n && (cur_ts != d.table_set || cur_n == HJD_ENT_THREADS)) {
+                    b->work.push_back(HjdEntropyWork{cur_first, cur_n, cur_img, cur_ts});
+                    cur_n = 0;
+                }
+                if (!cur_n) { cur_first = g; cur_img = (uint32_t)i; cur_ts = d.table_set; }
+                const uint32_t take = left < (HJD_ENT_THREADS - cur_n) ? left : (HJD_ENT_THREADS - cur_n);
+                cur_n += take; g += take; left -= take;
+            }
+        }
+        if (cur_n) b->work.push_back(HjdEntropyWork{cur_first, cur_n, cur_img, cur_ts});
+    }
+
+    // device slabs
+    CU(b->d_arena.ensure(b->arena_bytes + 64));
+    CU(b->d_imgs.ensure(sizeof(HjdImageDesc) * (size_t)(n + 1)));
+    CU(b->d_tsets.ensure(sizeof(HjdTableSet) * (b->tsets.size() + 1)));
+    CU(b->d_qsets.ensure(sizeof(HjdQuantSet) * (b->qsets.size() + 1)));
+    CU(b->d_work.ensure(sizeof(HjdEntropyWork) * (b->work.size() + 1)));
+    CU(b->d_istart.ensure(sizeof(uint32_t) * ((size_t)b->total_intervals + 2)));
+    CU(b->d_coef.ensure(b->total_blocks * 128 + 256));
+    CU(b->d_rgb.ensure(b->rgb_bytes + 256));
+    CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
+    if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
+
+    // metadata: one pinned staging block, then async copies
+    const size_t sz_imgs = sizeof(HjdImageDesc) * (size_t)n;
+    const size_t sz_ts = sizeof(HjdTableSet) * b->tsets.size();
+    const size_t sz_qs = sizeof(HjdQuantSet) * b->qsets.size();
+    const size_t sz_wk = sizeof(HjdEntropyWork) * b->work.size();
+    const size_t sz_is = sizeof(uint32_t) * b->host_istart.size();
+    size_t o_imgs = 0, o_ts = align_up(o_imgs + sz_imgs, 256), o_qs = align_up(o_ts + sz_ts, 256),
+           o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256), tot = o_is + sz_is;
+    CU(b->h_meta.ensure(tot + 256));
+    uint8_t* hm = (uint8_t*)b->h_meta.p;
+    memcpy(hm + o_imgs, b->imgs.data(), sz_imgs);
+    if (sz_ts) memcpy(hm + o_ts, b->tsets.data(), sz_ts);
+    if (sz_qs) memcpy(hm + o_qs, b->qsets.data(), sz_qs);
+    if (sz_wk) memcpy(hm + o_wk, b->work.data(), sz_wk);
+    if (sz_is) memcpy(hm + o_is, b->host_istart.data(), sz_is);
+    if (sz_imgs) CU(cudaMemcpyAsync(b->d_imgs.p, hm + o_imgs, sz_imgs, cudaMemcpyHostToDevice, b->stream));
+    if (sz_ts) CU(cudaMemcpyAsync(b->d_tsets.p, hm + o_ts, sz_ts, cudaMemcpyHostToDevice, b->stream));
+    if (sz_qs) CU(cudaMemcpyAsync(b->d_qsets.p, hm + o_qs, sz_qs, cudaMemcpyHostToDevice, b->stream));
+    if (sz_wk) CU(cudaMemcpyAsync(b->d_work.p, hm + o_wk, sz_wk, cudaMemcpyHostToDevice, b->stream));
+    if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemsetAsync(b->d_status.p, 0, sizeof(int32_t) * (size_t)(n + 1), b->stream));
+
+    // the files themselves
+    if (contiguous_src) {
+        CU(cudaMemcpyAsync(b->d_arena.p, contiguous_src, contiguous_bytes, cudaMemcpyHostToDevice, b->stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            if (files[i].ptr && files[i].size > 0)
+                CU(cudaMemcpyAsync((uint8_t*)b->d_arena.p + files[i].dev_off, files[i].ptr, (size_t)files[i].size,
+                                   cudaMemcpyHostToDevice, b->stream));
+    }
+    b->uploaded = true;
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_upload(hjd_batch* b, const uint8_t* const* bufs, const int64_t* sizes, int n)
+{
+    if (!b || !bufs || !sizes || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload", "bad arguments");
+    std::vector<FileRef> files((size_t)n);
+    uint64_t off = 0;
+    for (int i = 0; i < n; i++) {
+        files[i] = FileRef{bufs[i], sizes[i], off};
+        off += align_up(sizes[i] > 0 ? (uint64_t)sizes[i] : 0, 16);
+    }
+    b->arena_bytes = off;
+    return upload_common(b, files, nullptr, 0);
+}
+
+extern "C" int hjd_batch_upload_arena(hjd_batch* b, const uint8_t* arena, const int64_t* offsets,
+                                      const int64_t* sizes, int n)
+{
+    if (!b || !arena || !offsets || !sizes || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload_arena", "bad arguments");
+    std::vector<FileRef> files((size_t)n);
+    int64_t lo = n ? offsets[0] : 0, hi = 0;
+    for (int i = 0; i < n; i++) {
+        if (offsets[i] < 0 || sizes[i] < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload_arena", "negative offset/size");
+        if (offsets[i] < lo) lo = offsets[i];
+        if (offsets[i] + sizes[i] > hi) hi = offsets[i] + sizes[i];
+    }
+    const int64_t lo_al = lo & ~(int64_t)15;      // keep the 16-byte phase of every file
+    for (int i = 0; i < n; i++) files[i] = FileRef{arena + offsets[i], sizes[i], (uint64_t)(offsets[i] - lo_al)};
+    b->arena_bytes = n ? (uint64_t)(hi - lo_al) : 0;
+    return upload_common(b, files, n ? arena + lo_al : nullptr, b->arena_bytes);
+}
+
+extern "C" int hjd_batch_decode(hjd_batch* b)
+{
+    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_decode", "null batch");
+    if (!b->uploaded) return fail(HJD_ERR_STATE, "hjd_batch_decode", "nothing uploaded");
+    CU(cudaSetDevice(b->device));
+    const int n = (int)b->imgs.size();
+    cudaStream_t st = b->stream;
+    const uint8_t* arena = (const uint8_t*)b->d_arena.p;
+    const HjdImageDesc* imgs = (const HjdImageDesc*)b->d_imgs.p;
+    int32_t* status = (int32_t*)b->d_status.p;
+    b->launches = 0;
+
+    if (b->any_parse_error) CU(cudaMemsetAsync(b->d_rgb.p, 0, b->rgb_bytes, st));
+    CU(cudaEventRecord(b->ev[0], st));
+    if (!(b->flags & HJD_FLAG_HOST_SCAN) && n > 0) {
+        CU(hjd_launch_marker_scan(arena, imgs, (uint32_t*)b->d_istart.p, status, n, st));
+        b->launches += 1;
+    }
+    CU(cudaEventRecord(b->ev[1], st));
+    if (!b->work.empty()) {
+        CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
+                                      (const HjdEntropyWork*)b->d_work.p, (int)b->work.size(),
+                                      (int16_t*)b->d_coef.p, status, st));
+        b->launches += 1;
+    }
+    CU(cudaEventRecord(b->ev[2], st));
+    if (b->total_blocks) {
+        CU(b->d_planes.ensure(b->plane_bytes + 256));
+        CU(hjd_launch_idct_planes((const int16_t*)b->d_coef.p, imgs, (const HjdQuantSet*)b->d_qsets.p,
+                                  (uint8_t*)b->d_planes.p, n, b->max_blocks, st));
+        b->launches += (n + 65534) / 65535;
+    }
+    CU(cudaEventRecord(b->ev[3], st));
+    if (b->total_blocks) {
+        CU(hjd_launch_color((const uint8_t*)b->d_planes.p, imgs, (uint8_t*)b->d_rgb.p, n, b->max_w, b->max_h, st));
+        b->launches += (n + 65534) / 65535;
+    }
+    CU(cudaEventRecord(b->ev[4], st));
+    b->decoded = true;
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_sync(hjd_batch* b)
+{
+    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_sync", "null batch");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_num_images(const hjd_batch* b) { return b ? (int)b->imgs.size() : 0; }
+
+extern "C" int hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* o)
+{
+    if (!b || !o || i < 0 || i >= (int)b->imgs.size()) return fail(HJD_ERR_ARG, "hjd_batch_get_info", "bad arguments");
+    const HjdImageDesc& d = b->imgs[i];
+    memset(o, 0, sizeof *o);
+    o->width = d.width; o->height = d.height; o->ncomp = d.ncomp; o->hf = d.hf; o->vf = d.vf;
+    o->blocks_per_mcu = d.blocks_per_mcu; o->mcus_x = d.mcus_x; o->mcus_y = d.mcus_y;
+    o->restart_interval = d.restart_interval; o->n_intervals = d.n_intervals; o->scan_bytes = d.scan_len;
+    o->block_base = d.block_base; o->n_blocks = d.n_blocks; o->rgb_offset = d.rgb_off;
+    o->y_offset = d.y_off; o->cb_offset = d.cb_off; o->cr_offset = d.cr_off;
+    o->y_pitch = d.y_pitch; o->c_pitch = d.c_pitch; o->status = b->parse_status[i];
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_get_status(hjd_batch* b, int32_t* status)
+{
+    if (!b || !status) return fail(HJD_ERR_ARG, "hjd_batch_get_status", "bad arguments");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->imgs.size();
+    if (n == 0) return HJD_OK;
+    CU(cudaMemcpyAsync(status, b->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    for (size_t i = 0; i < n; i++) {
+        if (b->parse_status[i] != 0) status[i] = b->parse_status[i];
+        else if (b->host_restart_warn[i]) status[i] |= HJD_IMG_WARN_RESTART;
+    }
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_get_timings(hjd_batch* b, hjd_timings* t)
+{
+    if (!b || !t) return fail(HJD_ERR_ARG, "hjd_batch_get_timings", "bad arguments");
+    if (!b->decoded) return fail(HJD_ERR_STATE, "hjd_batch_get_timings", "no decode yet");
+    CU(cudaSetDevice(b->device));
+    CU(cudaEventSynchronize(b->ev[4]));
+    CU(cudaEventElapsedTime(&t->scan_ms, b->ev[0], b->ev[1]));
+    CU(cudaEventElapsedTime(&t->entropy_ms, b->ev[1], b->ev[2]));
+    CU(cudaEventElapsedTime(&t->idct_ms, b->ev[2], b->ev[3]));
+    CU(cudaEventElapsedTime(&t->color_ms, b->ev[3], b->ev[4]));
+    CU(cudaEventElapsedTime(&t->total_ms, b->ev[0], b->ev[4]));
+    t->launches = b->launches;
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_mark(hjd_batch* b, int slot)
+{
+    if (!b || slot < 0 || slot >= 4) return fail(HJD_ERR_ARG, "hjd_batch_mark", "bad arguments");
+    CU(cudaSetDevice(b->device));
+    CU(cudaEventRecord(b->mark[slot], b->stream));
+    return HJD_OK;
+}
+
+extern "C" float hjd_batch_elapsed_ms(hjd_batch* b, int slot_a, int slot_b)
+{
+    if (!b || slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4) { fail(HJD_ERR_ARG, "hjd_batch_elapsed_ms", "bad arguments"); return -1.f; }
+    float ms = -1.f;
+    if (cudaSetDevice(b->device) != cudaSuccess || cudaEventSynchronize(b->mark[slot_b]) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, b->mark[slot_a], b->mark[slot_b]) != cudaSuccess) {
+        fail(HJD_ERR_CUDA, "hjd_batch_elapsed_ms", cudaGetErrorString(cudaGetLastError()));
+        return -1.f;
+    }
+    return ms;
+}
+
+extern "C" uint64_t hjd_batch_rgb_bytes(const hjd_batch* b)   { return b ? b->rgb_bytes : 0; }
+extern "C" uint64_t hjd_batch_coef_bytes(const hjd_batch* b)  { return b ? b->total_blocks * 128 : 0; }
+extern "C" uint64_t hjd_batch_plane_bytes(const hjd_batch* b) { return b ? b->plane_bytes : 0; }
+extern "C" uint64_t hjd_batch_scan_bytes(const hjd_batch* b)  { return b ? b->scan_bytes : 0; }
+extern "C" uint64_t hjd_batch_pixels(const hjd_batch* b)      { return b ? b->pixels : 0; }
+extern "C" void* hjd_batch_device_rgb(hjd_batch* b)    { return b ? b->d_rgb.p : nullptr; }
+extern "C" void* hjd_batch_device_coef(hjd_batch* b)   { return b ? b->d_coef.p : nullptr; }
+extern "C" void* hjd_batch_device_planes(hjd_batch* b) { return b ? b->d_planes.p : nullptr; }
+
+static int download(hjd_batch* b, void* dst, const void* src, uint64_t bytes, const char* who)
+{
+    if (!b || !dst) return fail(HJD_ERR_ARG, who, "bad arguments");
+    if (!b->decoded) return fail(HJD_ERR_STATE, who, "no decode yet");
+    CU(cudaSetDevice(b->device));
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_download_rgb(hjd_batch* b, uint8_t* dst)
+{ return download(b, dst, b ? b->d_rgb.p : nullptr, b ? b->rgb_bytes : 0, "hjd_batch_download_rgb"); }
+
+extern "C" int hjd_batch_download_image(hjd_batch* b, int i, uint8_t* dst)
+{
+    if (!b || i < 0 || i >= (int)b->imgs.size()) return fail(HJD_ERR_ARG, "hjd_batch_download_image", "bad arguments");
+    const HjdImageDesc& d = b->imgs[i];
+    return download(b, dst, (const uint8_t*)b->d_rgb.p + d.rgb_off, (uint64_t)d.width * d.height * 3,
+                    "hjd_batch_download_image");
+}
+
+extern "C" int hjd_batch_download_coef(hjd_batch* b, int16_t* dst)
+{ return download(b, dst, b ? b->d_coef.p : nullptr, b ? b->total_blocks * 128 : 0, "hjd_batch_download_coef"); }
+
+extern "C" int hjd_batch_download_planes(hjd_batch* b, uint8_t* dst)
+{
+    if (b && !b->d_planes.p) return fail(HJD_ERR_STATE, "hjd_batch_download_planes", "planes not kept");
+    return download(b, dst, b ? b->d_planes.p : nullptr, b ? b->plane_bytes : 0, "hjd_batch_download_planes");
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer end-to-end path
+// ------------------------------------------------------------------------------------------
+extern "C" uint64_t hjd_rgb_slab_bytes(const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n)
+{
+    uint64_t total = 0;
+    if (!arena || !offsets || !sizes) return 0;
+    HjdParsed ps;
+    for (int i = 0; i < n; i++)
+        if (hjd_parse_jpeg(arena + offsets[i], (size_t)sizes[i], &ps) == HJD_IMG_OK)
+            total += align_up((uint64_t)ps.width * ps.height * 3, 256);
+    return total;
+}
+
+extern "C" int hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes,
+                                     int n, uint8_t* rgb_out, uint64_t rgb_capacity, uint64_t* rgb_offsets_out,
+                                     int32_t* status_out, int chunk_images)
+{
+    if (!b || !arena || !offsets || !sizes || !rgb_out || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "bad arguments");
+    if (chunk_images <= 0) chunk_images = n;
+    uint64_t out_off = 0;
+    for (int first = 0; first < n; first += chunk_images) {
+        const int cnt = (n - first < chunk_images) ? n - first : chunk_images;
+        int rc = hjd_batch_upload_arena(b, arena, offsets + first, sizes + first, cnt);
+        if (rc) return rc;
+        if (out_off + b->rgb_bytes > rgb_capacity) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "rgb_out too small");
+        rc = hjd_batch_decode(b);
+        if (rc) return rc;
+        if (b->rgb_bytes) CU(cudaMemcpyAsync(rgb_out + out_off, b->d_rgb.p, b->rgb_bytes, cudaMemcpyDeviceToHost, b->stream));
+        if (rgb_offsets_out)
+            for (int i = 0; i < cnt; i++) rgb_offsets_out[first + i] = out_off + b->imgs[i].rgb_off;
+        if (status_out) { rc = hjd_batch_get_status(b, status_out + first); if (rc) return rc; }
+        out_off += b->rgb_bytes;
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return HJD_OK;
+}
+
+extern "C" void* hjd_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); fail(HJD_ERR_NOMEM, "cudaHostAlloc"); return nullptr; }
+    return p;
+}
+extern "C" void hjd_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------
+// reference-shaped single-image calls
+// ------------------------------------------------------------------------------------------
+struct DefaultBatch {
+    hjd_batch* b = nullptr;
+    ~DefaultBatch() { if (b) hjd_batch_destroy(b); }
+};
+static thread_local DefaultBatch g_default;
+
+static hjd_batch* default_batch()
+{
+    if (!g_default.b) g_default.b = hjd_batch_create(0, 0);
+    return g_default.b;
+}
+
+extern "C" void hjd_free(void* p) { free(p); }
+
+extern "C" int hjd_get_image_size(const uint8_t* buf, int size, unsigned* width, unsigned* height)
+{
+    HjdParsed ps;
+    if (!buf || size <= 0 || hjd_parse_jpeg(buf, (size_t)size, &ps) != HJD_IMG_OK) { fail(HJD_ERR_ARG, "hjd_get_image_size", "not a decodable baseline JPEG"); return 0; }
+    if (width) *width = ps.width;
+    if (height) *height = ps.height;
+    return 1;
+}
+
+extern "C" int hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsigned* width, unsigned* height)
+{
+    if (!buf || size <= 0 || !rgb) { fail(HJD_ERR_ARG, "hjd_decode_jpg_file_data", "bad arguments"); return 0; }
+    *rgb = nullptr;
+    hjd_batch* b = default_batch();
+    if (!b) return 0;
+    const uint8_t* bufs[1] = {buf};
+    const int64_t sizes[1] = {size};
+    if (hjd_batch_upload(b, bufs, sizes, 1) != HJD_OK) return 0;
+    if (b->parse_status[0] != HJD_IMG_OK) { fail(HJD_ERR_ARG, "hjd_decode_jpg_file_data", "unsupported or corrupt JPEG"); return 0; }
+    if (hjd_batch_decode(b) != HJD_OK) return 0;
+    const HjdImageDesc& d = b->imgs[0];
+    const size_t bytes = (size_t)d.width * d.height * 3;
+    uint8_t* out = (uint8_t*)malloc(bytes ? bytes : 1);
+    if (!out) { fail(HJD_ERR_NOMEM, "malloc"); return 0; }
+    if (hjd_batch_download_image(b, 0, out) != HJD_OK) { free(out); return 0; }
+    *rgb = out;
+    if (width) *width = d.width;
+    if (height) *height = d.height;
+    return 1;
+}
+
+extern "C" size_t hjd_encode_bmp24(unsigned width, unsigned height, const uint8_t* rgb, uint8_t* out)
+{
+    // openjpg.cpp:504-570: 14+40 byte header, bottom-up, B G R, each row padded to a multiple of 4.
+    const unsigned pad = (4 - (width * 3) % 4) % 4;
+    const size_t total = (size_t)width * height * 3 + (size_t)height * pad + 54;
+    if (!out) return total;
+    memset(out, 0, 54);
+    auto put32 = [&](int at, uint32_t v) { out[at] = v & 255; out[at + 1] = (v >> 8) & 255; out[at + 2] = (v >> 16) & 255; out[at + 3] = (v >> 24) & 255; };
+    out[0] = 'B'; out[1] = 'M';
+    put32(2, (uint32_t)total);
+    put32(10, 54);
+    put32(14, 40);
+    put32(18, width);
+    put32(22, height);
+    out[26] = 1;
+    out[28] = 24;
+    uint8_t* o = out + 54;
+    for (unsigned row = height; row-- > 0;) {
+        const uint8_t* src = rgb + (size_t)row * width * 3;
+        for (unsigned x = 0; x < width; x++) { o[0] = src[2]; o[1] = src[1]; o[2] = src[0]; o += 3; src += 3; }
+        for (unsigned k = 0; k < pad; k++) *o++ = 0;
+    }
+    return total;
+}
+
+extern "C" int hjd_write_bmp24(const char* path, unsigned width, unsigned height, const uint8_t* rgb)
+{
+    if (!path || !rgb) { fail(HJD_ERR_ARG, "hjd_write_bmp24", "bad arguments"); return 0; }
+    const size_t total = hjd_encode_bmp24(width, height, rgb, nullptr);
+    uint8_t* tmp = (uint8_t*)malloc(total);
+    if (!tmp) { fail(HJD_ERR_NOMEM, "malloc"); return 0; }
+    hjd_encode_bmp24(width, height, rgb, tmp);
+    FILE* fp = fopen(path, "wb");
+    if (!fp) { free(tmp); fail(HJD_ERR_IO, "fopen", path); return 0; }
+    const size_t w = fwrite(tmp, 1, total, fp);
+    fclose(fp);
+    free(tmp);
+    if (w != total) { fail(HJD_ERR_IO, "fwrite", path); return 0; }
+    return 1;
+}
+
+extern "C" int hjd_convert_jpg_file(const char* jpg_in, const char* bmp_out)
+{
+    // ConvertJpgFile, openjpg.cpp:593-684: returns 1 on success, 0 on failure.
+    if (!jpg_in || !bmp_out) { fail(HJD_ERR_ARG, "hjd_convert_jpg_file", "bad arguments"); return 0; }
+    FILE* fp = fopen(jpg_in, "rb");
+    if (!fp) { fail(HJD_ERR_IO, "fopen", jpg_in); return 0; }          // openjpg.cpp:603-608
+    fseek(fp, 0, SEEK_END);
+    const long len = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (len <= 0 || len > 0x7FFFFFFF) { fclose(fp); fail(HJD_ERR_IO, "empty or oversized file", jpg_in); return 0; }
+    uint8_t* buf = (uint8_t*)malloc((size_t)len);
+    if (!buf) { fclose(fp); fail(HJD_ERR_NOMEM, "malloc"); return 0; }
+    const size_t got = fread(buf, 1, (size_t)len, fp);
+    fclose(fp);
+    uint8_t* rgb = nullptr;
+    unsigned w = 0, h = 0;
+    int ok = (got == (size_t)len) && hjd_decode_jpg_file_data(buf, (int)len, &rgb, &w, &h);
+    free(buf);
+    if (!ok) return 0;
+    ok = hjd_write_bmp24(bmp_out, w, h, rgb);
+    hjd_free(rgb);
+    return ok;
+}

@@ -1,0 +1,73 @@
+// csrc/hjd_types.h -- descriptors shared by the host boundary code and the CUDA kernels.
+//
+// This replaces the reference's fixed-capacity carrier structs (stJpegData / stHuffmanData /
+// stComponent / stHuffmanTable, loadjpg.h:97-171): instead of one image with inline arrays,
+// a batch is a set of flat HBM slabs plus one small descriptor per image.
+#pragma once
+#include <stdint.h>
+
+#define HJD_LUT_BITS    10                    // first-level Huffman lookup width
+#define HJD_LUT_SIZE    (1 << HJD_LUT_BITS)
+#define HJD_MAX_TABLES  6                     // (DC, AC) x 3 components, de-duplicated per set
+
+// One flattened Huffman table (built on the host from BITS/HUFFVAL, i.e. the same canonical
+// codes GenHuffCodes produces, openjpg.cpp:48-66).
+//   lut[peek >> (16 - LUT_BITS)] = (length << 8) | symbol   for codes of length <= LUT_BITS, else 0
+//   longer codes: the first L in (LUT_BITS, 16] with peek16 < limit[L]; symbol = vals[(peek16 >> (16-L)) + delta[L]]
+struct HjdHuffTable {
+    uint16_t lut[HJD_LUT_SIZE];
+    uint32_t limit[17];      // exclusive upper bound of left-aligned codes of length <= L (0x10000 possible)
+    int32_t  delta[17];      // valptr[L] - mincode[L]
+    uint8_t  vals[256];
+    uint32_t pad[2];         // sizeof == 2448, a multiple of 16 (copied to shared memory as uint4)
+};
+
+// Huffman tables of one image (or of many images that share identical DHT segments).
+struct HjdTableSet {
+    HjdHuffTable tab[HJD_MAX_TABLES];
+    int32_t n_tabs;
+    uint8_t dc_of_comp[4];   // component -> index into tab[]
+    uint8_t ac_of_comp[4];
+    uint8_t pad[4];
+};
+
+// Quantisation tables of one image, per component, zig-zag order (as in the file, openjpg.cpp:102-116).
+// Component 1 (Cb) already carries Cr's table: the reference dequantises Cb with Cr's (loadjpg.cpp:984).
+struct HjdQuantSet {
+    uint16_t q[3][64];
+};
+
+struct HjdImageDesc {
+    uint32_t width, height;
+    uint32_t mcus_x, mcus_y;
+    uint32_t n_mcus;
+    uint32_t restart_interval;   // MCUs; 0 = whole scan is one interval
+    uint32_t n_intervals;
+    uint32_t interval_base;      // global index of this image's first restart interval
+    uint32_t scan_len;           // entropy-coded bytes
+    uint32_t table_set;          // index into the table-set pool
+    uint32_t quant_set;          // index into the quant-set pool
+    uint32_t y_pitch, c_pitch;   // plane pitches in bytes (MCU-padded widths)
+    uint8_t  ncomp, hf, vf, blocks_per_mcu;
+    uint64_t scan_off;           // byte offset of the entropy-coded segment in the file arena
+    uint64_t block_base;         // first 8x8 block of this image in the coefficient slab
+    uint64_t n_blocks;
+    uint64_t y_off, cb_off, cr_off;   // byte offsets in the plane slab
+    uint64_t rgb_off;            // byte offset in the RGB slab
+    uint32_t sub_base;           // self-sync path: global index of this image's first sub-sequence
+    uint32_t n_subs;             // self-sync path: sub-sequences in this image (0 = restart path)
+};
+
+// One CTA's worth of restart intervals for the entropy kernel; all share one table set.
+struct HjdEntropyWork {
+    uint32_t first_interval;     // global interval index
+    uint32_t n_intervals;        // <= threads per CTA
+    uint32_t first_image;        // image that owns first_interval
+    uint32_t table_set;
+};
+
+// Per-image status bits written by kernels (mirrors HJD_IMG_WARN_* in include/hjd.h).
+#define HJD_ST_BAD_CODE     1
+#define HJD_ST_COEF_RANGE   2
+#define HJD_ST_OVERRUN      4
+#define HJD_ST_RESTART      8

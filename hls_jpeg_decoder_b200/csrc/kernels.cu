@@ -1,0 +1,610 @@
+// csrc/kernels.cu -- hand-written sm_100a kernels of the baseline-JPEG decode path.
+//
+// Reference functions replaced (harutel/hls-jpeg-decoder, src/loadjpg.cpp):
+//   kernel 0  marker scan      : the byte sniffing of ProcessHuffmanBlock 535-550 (done once, in parallel)
+//   kernel 1  entropy decode   : FillNBits 446-484, IsInHuffmanCodes 335-392, DetermineSign 396-409,
+//                                ProcessHuffmanBlock 497-863, block order of DecodeMCU 945-997
+//   kernel 2  dequant+IDCT     : DequantizeBlock 144-152, DeZigZag 156-163, TransformArray 167-180,
+//                                IDCT_calc 105-124, PerformIDCT 126-140, Clamp 83-91, DecodeSingleBlock 184-228
+//   kernel 3  upsample+colour  : ConvertYCrCbtoRGB 867-880, YCrCB_to_RGB24_Block8x8 884-932
+// The MCU raster loop of JpegDecodeHW (1134-1190) becomes the grid: every restart interval,
+// 8x8 block and pixel run of every image of the batch is an independent unit of work.
+//
+// All of it is HBM-bound integer/byte work plus a small FP32 IDCT; no tensor cores on purpose.
+#include "kernels.cuh"
+#include <cuda_runtime.h>
+
+// ------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------
+__constant__ float c_cos[64];     // c_cos[p*8+k] = cosf(((2p+1)*k*3.14f)/16)  (host libm, loadjpg.cpp:120)
+__constant__ float c_cc0;         // C(0)*C(k>0) = 1/sqrtf(2)                    (loadjpg.cpp:96-102)
+__constant__ float c_cc00;        // C(0)*C(0) = fl(0.70710677^2) = 0.49999997
+
+cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_cos, cos_tab, 64 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_cc0, &cc0, sizeof(float));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_cc00, &cc00, sizeof(float));
+}
+
+// zig-zag position p -> natural (row-major) index n; inverse of the reference's ZigZagArray
+// (loadjpg.cpp:56-66).  A macro list so that every index is a compile-time constant and the
+// 64 coefficients of a block stay in registers.
+#define HJD_ZZ_LIST(X) \
+    X(0, 0)   X(1, 1)   X(2, 8)   X(3, 16)  X(4, 9)   X(5, 2)   X(6, 3)   X(7, 10)  \
+    X(8, 17)  X(9, 24)  X(10, 32) X(11, 25) X(12, 18) X(13, 11) X(14, 4)  X(15, 5)  \
+    X(16, 12) X(17, 19) X(18, 26) X(19, 33) X(20, 40) X(21, 48) X(22, 41) X(23, 34) \
+    X(24, 27) X(25, 20) X(26, 13) X(27, 6)  X(28, 7)  X(29, 14) X(30, 21) X(31, 28) \
+    X(32, 35) X(33, 42) X(34, 49) X(35, 56) X(36, 57) X(37, 50) X(38, 43) X(39, 36) \
+    X(40, 29) X(41, 22) X(42, 15) X(43, 23) X(44, 30) X(45, 37) X(46, 44) X(47, 51) \
+    X(48, 58) X(49, 59) X(50, 52) X(51, 45) X(52, 38) X(53, 31) X(54, 39) X(55, 46) \
+    X(56, 53) X(57, 60) X(58, 61) X(59, 54) X(60, 47) X(61, 55) X(62, 62) X(63, 63)
+
+// ------------------------------------------------------------------------------------------
+// kernel 0: restart-marker scan
+// ------------------------------------------------------------------------------------------
+// One CTA per image.  Every thread inspects 16 bytes per step; RSTn = FF D0..D7 (an FF inside
+// entropy data is always followed by 00, so the pair test is exact).  The marker ordinal comes
+// from a block-wide prefix sum; interval j+1 starts two bytes after marker j.
+__global__ void __launch_bounds__(256)
+hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
+                  uint32_t* __restrict__ interval_start, int32_t* __restrict__ status, int img_base)
+{
+    const int img = blockIdx.x + img_base;
+    const HjdImageDesc d = imgs[img];
+    uint32_t* out = interval_start + d.interval_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (d.n_intervals == 0) return;
+    if (tid == 0) out[0] = 0;
+    if (d.restart_interval == 0 || d.n_intervals <= 1) return;
+
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_running;
+    if (tid == 0) s_running = 0;
+    __syncthreads();
+
+    const uint8_t* s = arena + d.scan_off;
+    const uint32_t lead = (uint32_t)((uintptr_t)s & 15);
+    const uint8_t* a0 = s - lead;
+    const uint32_t total = d.scan_len + lead;
+
+    for (uint32_t chunk = 0; chunk < total; chunk += 256 * 16) {
+        const uint32_t off = chunk + tid * 16;
+        uint32_t mask = 0;
+        if (off < total) {
+            const uint4 v = __ldg((const uint4*)(a0 + off));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            // any FF byte in these 16?
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) any |= ((~w[k]) - 0x01010101u) & w[k] & 0x80808080u;
+            if (any) {
+                const uint32_t nb = (off + 16 < total) ? a0[off + 16] : 0u;
+#pragma unroll
+                for (int p = 0; p < 16; p++) {
+                    const uint32_t b  = (w[p >> 2] >> (8 * (p & 3))) & 255u;
+                    const uint32_t nx = (p == 15) ? nb : ((w[(p + 1) >> 2] >> (8 * ((p + 1) & 3))) & 255u);
+                    const bool hit = (b == 0xFFu) && ((nx & 0xF8u) == 0xD0u) && (off + p >= lead) && (off + p + 1 < total);
+                    mask |= hit ? (1u << p) : 0u;
+                }
+            }
+        }
+        const uint32_t cnt = __popc(mask);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = s_running;
+        uint32_t block_total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t c = s_warp[k];
+            if (k < warp) before += c;
+            block_total += c;
+        }
+        uint32_t ord = before + incl - cnt;
+        while (mask) {
+            const int p = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (ord + 1 < d.n_intervals) out[ord + 1] = off + p + 2 - lead;
+            ord++;
+        }
+        __syncthreads();
+        if (tid == 0) s_running += block_total;
+        __syncthreads();
+    }
+    const uint32_t found = s_running;
+    if (found != d.n_intervals - 1) {
+        if (tid == 0) atomicOr(&status[img], HJD_ST_RESTART);
+        // intervals with no marker become empty: the entropy kernel zero-fills them and flags overrun
+        for (uint32_t j = found + 1 + tid; j < d.n_intervals; j += 256) out[j] = d.scan_len;
+    }
+}
+
+cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* imgs, uint32_t* interval_start,
+                                   int32_t* status, int n_images, cudaStream_t st)
+{
+    if (n_images <= 0) return cudaSuccess;
+    hjd_k_marker_scan<<<n_images, 256, 0, st>>>(arena, imgs, interval_start, status, 0);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 1a: restart-interval-parallel entropy decode
+// ------------------------------------------------------------------------------------------
+// One thread per restart interval (the unit the bitstream makes independent: byte-aligned start,
+// DC predictors reset).  Lanes free-run one Huffman symbol per loop trip; a lane that completes a
+// block raises a flag and the whole warp flushes that block's 128 bytes from its shared-memory
+// slot to HBM as one coalesced store, so the coefficient slab is written exactly once, densely.
+//
+// Shared memory: the table set of this CTA's images (first-level LUTs + long-code tables) and one
+// 64 x int16 slot per thread, XOR-swizzled by lane so that scattered 2-byte coefficient stores and
+// the word-per-lane flush are both bank-conflict free.
+
+struct BitReader {
+    const uint8_t* base;   // entropy-coded segment of the image
+    uint32_t pos, end;     // byte cursor / end of this interval (relative to base)
+    uint64_t buf;          // MSB-aligned bit window
+    int nbits;             // valid bits in buf
+    int padbits;           // zero bits appended after `end`
+};
+
+__device__ __forceinline__ void br_refill(BitReader& r)
+{
+    // FillNBits (loadjpg.cpp:446-484): FF 00 -> FF; an FF followed by anything else is data.
+    if (r.nbits > 32) return;
+    if (r.pos + 4 <= r.end) {
+        const uintptr_t a = (uintptr_t)(r.base + r.pos);
+        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+        const uint32_t lo = __ldg(ap), hi = __ldg(ap + 1);
+        const uint32_t x = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
+        if ((((~x) - 0x01010101u) & x & 0x80808080u) == 0) {          // no FF byte: take all four
+            const uint32_t w = __byte_perm(x, 0, 0x0123);
+            r.buf |= (uint64_t)w << (32 - r.nbits);
+            r.nbits += 32;
+            r.pos += 4;
+            return;
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        uint32_t b = 0;
+        if (r.pos < r.end) {
+            b = r.base[r.pos++];
+            if (b == 0xFFu && r.pos < r.end && r.base[r.pos] == 0) r.pos++;
+        } else {
+            r.padbits += 8;
+        }
+        r.buf |= (uint64_t)b << (56 - r.nbits);
+        r.nbits += 8;
+    }
+}
+
+__global__ void __launch_bounds__(HJD_ENT_THREADS)
+hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
+                      const HjdTableSet* __restrict__ tsets, const uint32_t* __restrict__ interval_start,
+                      const HjdEntropyWork* __restrict__ work, int16_t* __restrict__ coef,
+                      int32_t* __restrict__ status)
+{
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    uint32_t* s_slots = (uint32_t*)s_raw;                                  // [threads][32 words]
+    HjdHuffTable* s_tab = (HjdHuffTable*)(s_raw + HJD_ENT_THREADS * 128);  // [n_tabs]
+
+    const HjdEntropyWork wk = work[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const HjdTableSet* ts = tsets + wk.table_set;
+    const int n_tabs = ts->n_tabs;
+    {
+        const uint4* src = (const uint4*)ts->tab;
+        uint4* dst = (uint4*)s_tab;
+        const int n16 = n_tabs * (int)(sizeof(HjdHuffTable) / 16);
+        for (int i = tid; i < n16; i += HJD_ENT_THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < HJD_ENT_THREADS * 32; i += HJD_ENT_THREADS) s_slots[i] = 0;
+    }
+    __syncthreads();
+
+    // ---- per-lane interval setup -----------------------------------------------------------
+    BitReader br;
+    br.base = arena; br.pos = br.end = 0; br.buf = 0; br.nbits = 0; br.padbits = 0;
+    uint32_t blocks_left = 0, gblk = 0;
+    int img = 0, bpm = 1, ny = 1;
+    int dcY = 0, acY = 0, dcB = 0, acB = 0, dcR = 0, acR = 0;
+    if ((uint32_t)tid < wk.n_intervals) {
+        const uint32_t g = wk.first_interval + tid;
+        img = (int)wk.first_image;
+        while (g >= imgs[img].interval_base + imgs[img].n_intervals) img++;
+        const HjdImageDesc* d = imgs + img;
+        const uint32_t j = g - d->interval_base;
+        const uint32_t ri = d->restart_interval;
+        const uint32_t first_mcu = ri ? j * ri : 0;
+        const uint32_t n_mcu = ri ? min(ri, d->n_mcus - first_mcu) : d->n_mcus;
+        bpm = d->blocks_per_mcu;
+        ny = d->ncomp == 3 ? d->hf * d->vf : 1;
+        br.base = arena + d->scan_off;
+        br.pos = interval_start[g];
+        br.end = (j + 1 < d->n_intervals) ? interval_start[g + 1] - 2 : d->scan_len;
+        if (br.end < br.pos || br.end > d->scan_len) br.end = br.pos;
+        blocks_left = n_mcu * (uint32_t)bpm;
+        gblk = (uint32_t)(d->block_base + (uint64_t)first_mcu * bpm);
+        dcY = ts->dc_of_comp[0]; acY = ts->ac_of_comp[0];
+        dcB = ts->dc_of_comp[1]; acB = ts->ac_of_comp[1];
+        dcR = ts->dc_of_comp[2]; acR = ts->ac_of_comp[2];
+    }
+
+    uint16_t* my_slot = (uint16_t*)(s_slots + tid * 32);
+    int k = 0, bi = 0;                 // zig-zag index inside the block, block index inside the MCU
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    const HjdHuffTable* tdc = s_tab + dcY;
+    const HjdHuffTable* tac = s_tab + acY;
+    int flags = 0;
+    bool dead = false;                 // undecodable code met: zero-fill the rest of the interval
+
+    // ---- symbol loop -----------------------------------------------------------------------
+    while (__any_sync(0xffffffffu, blocks_left > 0)) {
+        bool done_block = false;
+        uint32_t flush_blk = 0;
+        if (blocks_left > 0) {
+            if (dead) {
+                k = 64;
+            } else {
+                br_refill(br);
+                const HjdHuffTable* t = (k == 0) ? tdc : tac;
+                const uint32_t peek = (uint32_t)(br.buf >> 48);
+                const uint32_t e = t->lut[peek >> (16 - HJD_LUT_BITS)];
+                uint32_t len = e >> 8, sym = e & 255u;
+                if (len == 0) {                                       // code longer than the first level
+                    len = HJD_LUT_BITS + 1;
+                    while (len <= 16 && peek >= t->limit[len]) len++;
+                    if (len > 16) {
+                        dead = true; flags |= HJD_ST_BAD_CODE; len = 0; sym = 0; k = 64;
+                    } else {
+                        sym = t->vals[((peek >> (16 - len)) + (uint32_t)t->delta[len]) & 255u];
+                    }
+                }
+                if (!dead) {
+                    br.buf <<= len; br.nbits -= (int)len;
+                    const uint32_t size = sym & 15u;
+                    int val = 0;
+                    if (size) {                                       // DetermineSign, loadjpg.cpp:396-409
+                        const uint32_t v = (uint32_t)(br.buf >> (64 - size));
+                        br.buf <<= size; br.nbits -= (int)size;
+                        val = (v < (1u << (size - 1))) ? (int)v - (int)((1u << size) - 1u) : (int)v;
+                    }
+                    if (k == 0) {                                     // DC: loadjpg.cpp:616-667
+                        const int c = (bi < ny) ? 0 : (bi == ny ? 1 : 2);
+                        int p = (c == 0) ? pred0 : (c == 1 ? pred1 : pred2);
+                        p = (int)(short)(p + val);
+                        if (c == 0) pred0 = p; else if (c == 1) pred1 = p; else pred2 = p;
+                        my_slot[(0 ^ lane) * 2] = (uint16_t)p;
+                        k = 1;
+                    } else {                                          // AC: loadjpg.cpp:768-808
+                        const uint32_t run = sym >> 4;
+                        if (size == 0) {
+                            if (run == 0) k = 64;                     // EOB
+                            else if (run == 15) k += 16;              // ZRL
+                        } else {
+                            k += (int)run;
+                            if (k <= 63) my_slot[(((k >> 1) ^ lane) << 1) | (k & 1)] = (uint16_t)val;
+                            else flags |= HJD_ST_COEF_RANGE;
+                            k++;
+                        }
+                    }
+                }
+            }
+            if (k >= 64) {
+                done_block = true;
+                flush_blk = gblk++;
+                blocks_left--;
+                k = 0;
+                if (++bi == bpm) bi = 0;
+                const int c = (bi < ny) ? 0 : (bi == ny ? 1 : 2);
+                tdc = s_tab + ((c == 0) ? dcY : (c == 1 ? dcB : dcR));
+                tac = s_tab + ((c == 0) ? acY : (c == 1 ? acB : acR));
+                if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
+            }
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, done_block);
+        if (m) {
+            __syncwarp();
+            do {
+                const int owner = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t g = __shfl_sync(0xffffffffu, flush_blk, owner);
+                uint32_t* slot = s_slots + ((tid & ~31) + owner) * 32;
+                const uint32_t w = slot[lane ^ owner];
+                slot[lane ^ owner] = 0;
+                ((uint32_t*)coef)[(size_t)g * 32 + lane] = w;
+            } while (m);
+            __syncwarp();
+        }
+    }
+    if (flags) atomicOr(&status[img], flags);
+}
+
+cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
+                                       const uint32_t* interval_start, const HjdEntropyWork* work, int n_work,
+                                       int16_t* coef, int32_t* status, cudaStream_t st)
+{
+    if (n_work <= 0) return cudaSuccess;
+    const size_t smem = HJD_ENT_THREADS * 128 + HJD_MAX_TABLES * sizeof(HjdHuffTable);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    hjd_k_entropy_restart<<<n_work, HJD_ENT_THREADS, smem, st>>>(arena, imgs, tsets, interval_start, work, coef, status);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 2: dequantise + de-zig-zag + IDCT (+128, clamp) -> planes
+// ------------------------------------------------------------------------------------------
+// The reference evaluates, for every output sample, a 64-term float sum in a fixed order with
+// PI = 3.14f and truncates 0.25*sum toward zero (loadjpg.cpp:105-124).  Truncation is
+// discontinuous, so a faster summation order can differ by one level whenever 0.25*sum lands
+// next to an integer.  This kernel computes the separable form (16 FMA per sample) and proves,
+// per sample, that truncation cannot differ: with A = sum |C(u)C(v)*coef| the two evaluations
+// differ by at most (65+14) * 2^-24 * A (standard rounding-error bounds for a 64-term recursive
+// sum of doubly-rounded products, and for two 8-term FMA chains), i.e. < 20 * 2^-24 * A on the
+// 0.25*sum scale.  Samples closer than 24 * 2^-24 * A to a non-zero integer (well under 1 %) are
+// re-evaluated in the reference's exact order (u outer, v inner, products left to right, no FMA).
+// Blocks with only a DC term are exact in both forms (cos(0) = 1) and are never re-evaluated.
+// Result: planes identical to the reference's, not merely within 1.
+
+__device__ __forceinline__ int hjd_finish_sample(float sum)
+{
+    int iv = __float2int_rz(0.25f * sum);      // (int)(0.25*sum), loadjpg.cpp:123
+    iv = (int)(short)iv;                       // stored to short, loadjpg.cpp:136
+    iv = (int)(short)(iv + 128);               // loadjpg.cpp:137
+    return min(max(iv, 0), 255);               // Clamp, loadjpg.cpp:83-91
+}
+
+// Dequantise one block held as 8 x uint4 (zig-zag order) into bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)).
+// Returns A_ac = sum over AC terms of |bp| ; *a_dc = |bp[0]|.
+__device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4 q[8], float bp[64], float* a_dc)
+{
+    const float cc0 = c_cc0, cc00 = c_cc00;
+    const uint32_t* cw = (const uint32_t*)c;
+    const uint32_t* qw = (const uint32_t*)q;
+    float a_ac = 0.f;
+#define HJD_DQ(P, N)                                                                           \
+    {                                                                                          \
+        const int cv = (int)(short)((cw[(P) >> 1] >> (((P) & 1) * 16)) & 0xFFFFu);             \
+        const int qv = (int)((qw[(P) >> 1] >> (((P) & 1) * 16)) & 0xFFFFu);                    \
+        const float f = (float)(int)(short)(cv * qv);       /* loadjpg.cpp:150, product exact */ \
+        const float ccw = ((N) == 0) ? cc00 : ((((N) & 7) == 0 || ((N) >> 3) == 0) ? cc0 : 1.0f); \
+        const float b = __fmul_rn(ccw, f);                  /* (C(u)*C(v)) * block[u][v] */    \
+        bp[(N)] = b;                                                                           \
+        if ((N) == 0) *a_dc = fabsf(b); else a_ac += fabsf(b);                                 \
+    }
+    HJD_ZZ_LIST(HJD_DQ)
+#undef HJD_DQ
+    return a_ac;
+}
+
+// Exact re-evaluation of sample (x, y) in the reference's order.  tx/ty: rows of the cos table.
+__device__ __forceinline__ float hjd_exact_sum(const float bp[64], const float* tx, const float* ty)
+{
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const float cxu = tx[u];
+#pragma unroll
+        for (int v = 0; v < 8; v++)
+            sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(bp[8 * v + u], cxu), ty[v]));
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(HJD_IDCT_THREADS)
+hjd_k_idct_planes(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
+                  const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ planes, int img_base)
+{
+    __shared__ float s_cos[64];
+    if (threadIdx.x < 64) s_cos[threadIdx.x] = c_cos[threadIdx.x];
+    __syncthreads();
+
+    const HjdImageDesc* d = imgs + (blockIdx.y + img_base);
+    const uint64_t b = (uint64_t)blockIdx.x * HJD_IDCT_THREADS + threadIdx.x;
+    if (b >= d->n_blocks) return;
+    const uint32_t bpm = d->blocks_per_mcu;
+    const uint32_t mcu = (uint32_t)(b / bpm), bi = (uint32_t)(b - (uint64_t)mcu * bpm);
+    const uint32_t my = mcu / d->mcus_x, mx = mcu - my * d->mcus_x;
+    const uint32_t ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
+    int comp; uint32_t bx, by, pitch; uint64_t poff;
+    if (bi < ny) {                     // Y blocks, row-major inside the MCU (loadjpg.cpp:949-959)
+        comp = 0; pitch = d->y_pitch; poff = d->y_off;
+        bx = mx * d->hf + bi % d->hf; by = my * d->vf + bi / d->hf;
+    } else {
+        comp = (bi == ny) ? 1 : 2; pitch = d->c_pitch; poff = comp == 1 ? d->cb_off : d->cr_off;
+        bx = mx; by = my;
+    }
+
+    uint4 c[8], q[8];
+    const uint4* cp = (const uint4*)(coef + (d->block_base + b) * 64);
+    const uint4* qp = (const uint4*)(qsets[d->quant_set].q[comp]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i] = cp[i]; q[i] = __ldg(qp + i); }
+
+    float bp[64];
+    float a_dc;
+    const float a_ac = hjd_dequant_block(c, q, bp, &a_dc);
+    // re-evaluation window on the 0.25*sum scale: 24 * 2^-24 * A; DC-only blocks are exact
+    const float win = (a_ac == 0.f) ? -1.f : (a_ac + a_dc) * 1.430511474609375e-06f;
+
+    // pass 1 (horizontal frequency u -> position x): r[8v+x] = sum_u bp[8v+u] * cos[x][u]
+    float r[64];
+#pragma unroll
+    for (int v = 0; v < 8; v++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            float acc = bp[8 * v];                 // cos[x][0] == 1
+#pragma unroll
+            for (int u = 1; u < 8; u++) acc = fmaf(bp[8 * v + u], c_cos[x * 8 + u], acc);
+            r[8 * v + x] = acc;
+        }
+    // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples
+    uint32_t row_lo[8], row_hi[8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) { row_lo[y] = 0; row_hi[y] = 0; }
+    uint32_t near_lo = 0, near_hi = 0;             // bit (8y + x)
+#pragma unroll
+    for (int x = 0; x < 8; x++)
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+            float acc = r[x];                      // v = 0, cos[y][0] == 1
+#pragma unroll
+            for (int v = 1; v < 8; v++) acc = fmaf(r[8 * v + x], c_cos[y * 8 + v], acc);
+            const float h = 0.25f * acc;
+            const float n = rintf(h);
+            const bool nearint = (fabsf(h - n) <= win) && (n != 0.f);
+            const uint32_t pix = (uint32_t)hjd_finish_sample(acc);
+            if (x < 4) row_lo[y] |= pix << (8 * x); else row_hi[y] |= pix << (8 * (x - 4));
+            if (y < 4) near_lo |= nearint ? (1u << (8 * y + x)) : 0u;
+            else       near_hi |= nearint ? (1u << (8 * (y - 4) + x)) : 0u;
+        }
+
+    uint8_t* dst = planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8;
+#pragma unroll
+    for (int y = 0; y < 8; y++) *(uint2*)(dst + (uint64_t)y * pitch) = make_uint2(row_lo[y], row_hi[y]);
+
+    // exact re-evaluation of the flagged samples (same thread, later store wins)
+    while (near_lo | near_hi) {
+        int pos;
+        if (near_lo) { pos = __ffs(near_lo) - 1; near_lo &= near_lo - 1; }
+        else         { pos = 32 + __ffs(near_hi) - 1; near_hi &= near_hi - 1; }
+        const int y = pos >> 3, x = pos & 7;
+        const float sum = hjd_exact_sum(bp, s_cos + x * 8, s_cos + y * 8);
+        dst[(uint64_t)y * pitch + x] = (uint8_t)hjd_finish_sample(sum);
+    }
+}
+
+cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
+                                   uint8_t* planes, int n_images, uint32_t max_blocks, cudaStream_t st)
+{
+    if (n_images <= 0 || max_blocks == 0) return cudaSuccess;
+    const unsigned gx = (max_blocks + HJD_IDCT_THREADS - 1) / HJD_IDCT_THREADS;
+    for (int base = 0; base < n_images; base += 65535) {
+        const int n = min(65535, n_images - base);
+        hjd_k_idct_planes<<<dim3(gx, n), HJD_IDCT_THREADS, 0, st>>>(coef, imgs, qsets, planes, base);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 3: chroma upsample + YCbCr -> RGB + clamp
+// ------------------------------------------------------------------------------------------
+// One thread = 16 pixels of one row = 48 output bytes = three 128-bit stores.  Float arithmetic
+// is the reference's, operation for operation (no FMA contraction, truncation toward zero):
+//   R = Y + 1.402f*(Cr-128);  G = (Y - 0.34414f*(Cb-128)) - 0.71414f*(Cr-128);  B = Y + 1.772f*(Cb-128)
+// (loadjpg.cpp:873-879 with the swapped argument names of the call at 918 resolved).
+// Chroma is replicated, nearest neighbour (loadjpg.cpp:911-912).
+
+__device__ __forceinline__ uint32_t hjd_clamp255(int v) { return (uint32_t)min(max(v, 0), 255); }
+
+__device__ __forceinline__ void hjd_ycc_pixel(int yv, float rr, float g1, float g2, float bb,
+                                              uint32_t& R, uint32_t& G, uint32_t& B)
+{
+    const float fy = (float)yv;
+    R = hjd_clamp255(__float2int_rz(__fadd_rn(fy, rr)));
+    G = hjd_clamp255(__float2int_rz(__fsub_rn(__fsub_rn(fy, g1), g2)));
+    B = hjd_clamp255(__float2int_rz(__fadd_rn(fy, bb)));
+}
+
+// 16 pixels -> 48 packed bytes.  HS = log2(horizontal luma factor): chroma sample i >> HS.
+template <int HS>
+__device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_t cbw[4], const uint32_t crw[4],
+                                             uint32_t out[12])
+{
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[i] = 0;
+    float rr = 0.f, g1 = 0.f, g2 = 0.f, bb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (HS == 0 || (i & 1) == 0) {
+            const int ci = i >> HS;
+            const int cb = (int)((cbw[ci >> 2] >> (8 * (ci & 3))) & 255u) - 128;
+            const int cr = (int)((crw[ci >> 2] >> (8 * (ci & 3))) & 255u) - 128;
+            rr = __fmul_rn(1.402f, (float)cr);
+            g1 = __fmul_rn(0.34414f, (float)cb);
+            g2 = __fmul_rn(0.71414f, (float)cr);
+            bb = __fmul_rn(1.772f, (float)cb);
+        }
+        const int yv = (int)((yw[i >> 2] >> (8 * (i & 3))) & 255u);
+        uint32_t R, G, B;
+        hjd_ycc_pixel(yv, rr, g1, g2, bb, R, G, B);
+        out[(3 * i) >> 2]     |= R << (8 * ((3 * i) & 3));
+        out[(3 * i + 1) >> 2] |= G << (8 * ((3 * i + 1) & 3));
+        out[(3 * i + 2) >> 2] |= B << (8 * ((3 * i + 2) & 3));
+    }
+}
+
+__global__ void __launch_bounds__(HJD_COLOR_THREADS)
+hjd_k_color(const uint8_t* __restrict__ planes, const HjdImageDesc* __restrict__ imgs,
+            uint8_t* __restrict__ rgb, int img_base)
+{
+    const HjdImageDesc* d = imgs + (blockIdx.y + img_base);
+    const uint32_t W = d->width, H = d->height;
+    const uint32_t segs = (W + 15) >> 4;
+    const uint64_t t = (uint64_t)blockIdx.x * HJD_COLOR_THREADS + threadIdx.x;
+    if (t >= (uint64_t)segs * H) return;
+    const uint32_t row = (uint32_t)(t / segs), seg = (uint32_t)(t - (uint64_t)row * segs);
+    const uint32_t x0 = seg * 16;
+    const int hs = d->hf - 1, vs = d->vf - 1;      // shifts (factors are 1 or 2)
+    const bool gray = d->ncomp == 1;
+
+    const uint8_t* yp = planes + d->y_off + (uint64_t)row * d->y_pitch + x0;
+    uint32_t yw[4];
+    { const uint2 a = *(const uint2*)yp, b = *(const uint2*)(yp + 8); yw[0] = a.x; yw[1] = a.y; yw[2] = b.x; yw[3] = b.y; }
+    uint32_t cbw[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+    uint32_t crw[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+    if (!gray) {
+        const uint64_t coff = (uint64_t)(row >> vs) * d->c_pitch + (x0 >> hs);
+        const uint8_t* bp = planes + d->cb_off + coff;
+        const uint8_t* rp = planes + d->cr_off + coff;
+        { const uint2 a = *(const uint2*)bp; cbw[0] = a.x; cbw[1] = a.y; }
+        { const uint2 a = *(const uint2*)rp; crw[0] = a.x; crw[1] = a.y; }
+        if (hs == 0) {
+            { const uint2 a = *(const uint2*)(bp + 8); cbw[2] = a.x; cbw[3] = a.y; }
+            { const uint2 a = *(const uint2*)(rp + 8); crw[2] = a.x; crw[3] = a.y; }
+        }
+    }
+
+    uint32_t out[12];
+    if (hs) hjd_color_16<1>(yw, cbw, crw, out); else hjd_color_16<0>(yw, cbw, crw, out);
+
+    uint8_t* dst = rgb + d->rgb_off + ((uint64_t)row * W + x0) * 3;    // loadjpg.cpp:921-925
+    const uint32_t npix = min(16u, W - x0);
+    if (npix == 16 && (((uintptr_t)dst) & 15) == 0) {
+        uint4* o = (uint4*)dst;
+        o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        o[2] = make_uint4(out[8], out[9], out[10], out[11]);
+    } else {
+        const uint32_t nbytes = npix * 3;
+#pragma unroll
+        for (int i = 0; i < 48; i++)
+            if ((uint32_t)i < nbytes) dst[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
+cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, uint8_t* rgb, int n_images,
+                             uint32_t max_width, uint32_t max_height, cudaStream_t st)
+{
+    if (n_images <= 0 || max_width == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)((max_width + 15) >> 4) * max_height;
+    const unsigned gx = (unsigned)((threads + HJD_COLOR_THREADS - 1) / HJD_COLOR_THREADS);
+    for (int base = 0; base < n_images; base += 65535) {
+        const int n = min(65535, n_images - base);
+        hjd_k_color<<<dim3(gx, n), HJD_COLOR_THREADS, 0, st>>>(planes, imgs, rgb, base);
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,29 @@
+// csrc/kernels.cuh -- launch wrappers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hjd_types.h"
+
+#define HJD_ENT_THREADS   128   // entropy kernel: one restart interval per thread
+#define HJD_IDCT_THREADS  128   // unfused IDCT kernel: one 8x8 block per thread
+#define HJD_COLOR_THREADS 128   // unfused colour kernel: 16 pixels of one row per thread
+
+// Upload the IDCT constants (host libm values, loadjpg.cpp:96-102,120).
+cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00);
+
+// Kernel 0: RSTn marker scan -> interval_start[] (one CTA per image).
+cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* imgs, uint32_t* interval_start,
+                                   int32_t* status, int n_images, cudaStream_t st);
+
+// Kernel 1a: restart-interval-parallel Huffman decode -> int16 coefficients (zig-zag order).
+cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
+                                       const uint32_t* interval_start, const HjdEntropyWork* work, int n_work,
+                                       int16_t* coef, int32_t* status, cudaStream_t st);
+
+// Kernel 2: dequantise + de-zig-zag + IDCT -> u8 planes (bit-exact with the reference's direct form).
+cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
+                                   uint8_t* planes, int n_images, uint32_t max_blocks, cudaStream_t st);
+
+// Kernel 3: chroma upsample + YCbCr->RGB + clamp -> packed RGB24.
+cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, uint8_t* rgb, int n_images,
+                             uint32_t max_width, uint32_t max_height, cudaStream_t st);

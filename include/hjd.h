@@ -1,0 +1,175 @@
+/* include/hjd.h -- C ABI of the B200-native baseline-JPEG decode path.
+ *
+ * Drop-in boundary for the hot path of harutel/hls-jpeg-decoder.  The
+ * reference has plain C++ linkage and no FFI; these are the entry points a binding (cgo,
+ * JNI, ctypes, ...) or the reference's own main.cpp would bind instead of its CPU decode:
+ *
+ *   reference interface (file:line)                           -> replacement
+ *   ---------------------------------------------------------------------------------------
+ *   int  ConvertJpgFile(char*, char*)        openjpg.h:23, openjpg.cpp:593  -> hjd_convert_jpg_file
+ *   int  DecodeJpgFileData(buf,size,&rgb,&w,&h)  loadjpg.h:186 (declared only) -> hjd_decode_jpg_file_data
+ *   void JpegGetImageSize(..., &w, &h)       loadjpg.h:183 (declared only)  -> hjd_get_image_size
+ *   void WriteBMP24(name, w, h, rgb)         openjpg.cpp:504                -> hjd_write_bmp24
+ *   int  JpegDecodeHW(stJpegData*, h, w, hF, vF) loadjpg.h:180, loadjpg.cpp:1134
+ *        (the HLS top: parsed tables + entropy segment in, RGB out)         -> hjd_batch_* (N images per call)
+ *
+ * csrc/ref_shim.cpp additionally defines the reference's exact C++ names on top of this ABI
+ * so that the reference's src/main.cpp links unchanged.
+ *
+ * Conventions: plain pointers and sizes only; no global mutable state besides a lazily
+ * created per-thread default batch used by the single-image calls; one hjd_batch per GPU,
+ * used from one host thread at a time.  All hot-path work runs in hand-written sm_100a CUDA
+ * kernels; there is no CPU fallback: without a usable GPU every decode call fails with
+ * HJD_ERR_CUDA and hjd_last_error() says why.
+ *
+ * Output contract (loadjpg.cpp:921-925): RGB24, top-down, tightly packed, stride 3*width, R first.
+ * BMP contract (openjpg.cpp:504-570): 54-byte header, bottom-up rows, B,G,R, rows padded to 4 bytes.
+ */
+#ifndef HJD_H
+#define HJD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HJD_VERSION 100
+
+/* Return codes of the batch API (single-image reference-style calls return 1/0, see below). */
+#define HJD_OK                 0
+#define HJD_ERR_ARG           -1
+#define HJD_ERR_CUDA          -2   /* no device / CUDA runtime failure; see hjd_last_error() */
+#define HJD_ERR_NOMEM         -3
+#define HJD_ERR_IO            -4
+#define HJD_ERR_STATE         -5   /* call order (e.g. decode before upload) */
+
+/* Per-image status (hjd_batch_get_status).  0 = decoded; parse errors are negative and the
+ * image is skipped (its RGB slab is left zero-filled); decode warnings are positive bit flags
+ * and the image is still produced (the reference itself only printf()s on such input). */
+#define HJD_IMG_OK                 0
+#define HJD_IMG_ERR_NOT_JPEG      -1   /* openjpg.cpp:481-486 */
+#define HJD_IMG_ERR_TRUNCATED     -2
+#define HJD_IMG_ERR_UNSUPPORTED   -3   /* progressive, 12-bit, 16-bit DQT, CMYK, chroma sampling != 1x1 ... */
+#define HJD_IMG_ERR_BAD_TABLE     -4   /* DHT over-subscribed / missing table */
+#define HJD_IMG_WARN_BAD_CODE      1   /* undecodable Huffman code; rest of that restart interval zero-filled */
+#define HJD_IMG_WARN_COEF_RANGE    2   /* run past coefficient 63 (loadjpg.cpp:780-783) */
+#define HJD_IMG_WARN_OVERRUN       4   /* entropy data ended before the interval did */
+#define HJD_IMG_WARN_RESTART       8   /* RSTn count differs from ceil(MCUs/Ri)-1 */
+
+/* hjd_batch_create flags */
+#define HJD_FLAG_KEEP_PLANES   1u   /* run the unfused IDCT -> planes -> colour kernels (parity taps) */
+#define HJD_FLAG_HOST_SCAN     2u   /* find RSTn markers on the host instead of the GPU pre-pass */
+
+typedef struct hjd_batch hjd_batch;
+
+typedef struct hjd_image_info {
+    uint32_t width, height;
+    uint8_t  ncomp;            /* 1 or 3 */
+    uint8_t  hf, vf;           /* luma sampling factors (1 or 2); chroma is 1x1 */
+    uint8_t  blocks_per_mcu;
+    uint32_t mcus_x, mcus_y;
+    uint32_t restart_interval; /* MCUs, 0 = none */
+    uint32_t n_intervals;
+    uint32_t scan_bytes;       /* entropy-coded segment length */
+    uint64_t block_base;       /* first block of this image in the coefficient buffer */
+    uint64_t n_blocks;
+    uint64_t rgb_offset;       /* byte offset of this image in the RGB slab */
+    uint64_t y_offset, cb_offset, cr_offset;   /* byte offsets in the plane slab */
+    uint32_t y_pitch, c_pitch;
+    int32_t  status;
+} hjd_image_info;
+
+/* Stage timings of the last hjd_batch_decode (CUDA events on the batch stream), milliseconds. */
+typedef struct hjd_timings {
+    float scan_ms;      /* kernel 0: RSTn marker scan -> interval table */
+    float entropy_ms;   /* kernel 1: Huffman decode -> int16 coefficients (+ self-sync passes) */
+    float idct_ms;      /* kernel 2 (or fused 2+3) */
+    float color_ms;     /* kernel 3 (0 when fused) */
+    float total_ms;
+    int   launches;     /* kernels launched by the last decode */
+} hjd_timings;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int         hjd_version(void);
+const char* hjd_last_error(void);          /* thread-local, never NULL */
+int         hjd_device_count(void);        /* 0 when no CUDA device is usable */
+
+/* ---- reference-shaped single-image entry points (return 1 = success, 0 = failure) -------- */
+/* openjpg.cpp:593 ConvertJpgFile: load .jpg, decode on the GPU, write 24-bit .bmp. */
+int  hjd_convert_jpg_file(const char* jpg_in, const char* bmp_out);
+/* loadjpg.h:186 DecodeJpgFileData: *rgb is allocated by the library (release with hjd_free). */
+int  hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsigned* width, unsigned* height);
+void hjd_free(void* p);
+/* loadjpg.h:183 JpegGetImageSize, from the file bytes (header parse only, no GPU). */
+int  hjd_get_image_size(const uint8_t* buf, int size, unsigned* width, unsigned* height);
+/* openjpg.cpp:504 WriteBMP24. */
+int  hjd_write_bmp24(const char* path, unsigned width, unsigned height, const uint8_t* rgb);
+/* Same bytes as hjd_write_bmp24 into memory; returns the BMP size (call with out = NULL to size it). */
+size_t hjd_encode_bmp24(unsigned width, unsigned height, const uint8_t* rgb, uint8_t* out);
+
+/* ---- batch API: the JpegDecodeHW replacement, N independent images per call -------------- */
+hjd_batch* hjd_batch_create(int device, unsigned flags);
+void       hjd_batch_destroy(hjd_batch* b);
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the batch's own. */
+int  hjd_batch_set_stream(hjd_batch* b, void* cuda_stream);
+
+/* Parse headers, build Huffman/quant tables and descriptors, copy the files to HBM.
+ * bufs[i]/sizes[i]: whole .jpg files in host memory (pinned memory makes the copy asynchronous). */
+int  hjd_batch_upload(hjd_batch* b, const uint8_t* const* bufs, const int64_t* sizes, int n);
+/* Same, for files packed in one host arena: file i = arena[offsets[i] .. offsets[i]+sizes[i]).
+ * One host->device copy of [offsets[0], offsets[n-1]+sizes[n-1]). */
+int  hjd_batch_upload_arena(hjd_batch* b, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n);
+
+/* Launch the decode of everything uploaded (asynchronous on the batch stream):
+ * marker scan -> entropy decode -> dequant/IDCT -> upsample/colour.  Results stay in HBM. */
+int  hjd_batch_decode(hjd_batch* b);
+int  hjd_batch_sync(hjd_batch* b);
+
+int  hjd_batch_num_images(const hjd_batch* b);
+int  hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* out);
+int  hjd_batch_get_status(hjd_batch* b, int32_t* status /* n */);   /* syncs */
+int  hjd_batch_get_timings(hjd_batch* b, hjd_timings* out);          /* syncs */
+/* CUDA-event stopwatch on the batch stream: record event `slot` (0..3); milliseconds between two
+ * recorded slots (waits for slot_b).  This is how bench.py times K steps on the launching stream. */
+int   hjd_batch_mark(hjd_batch* b, int slot);
+float hjd_batch_elapsed_ms(hjd_batch* b, int slot_a, int slot_b);
+uint64_t hjd_batch_rgb_bytes(const hjd_batch* b);     /* size of the RGB slab */
+uint64_t hjd_batch_coef_bytes(const hjd_batch* b);
+uint64_t hjd_batch_plane_bytes(const hjd_batch* b);
+uint64_t hjd_batch_scan_bytes(const hjd_batch* b);    /* sum of entropy-coded bytes */
+uint64_t hjd_batch_pixels(const hjd_batch* b);        /* sum of width*height */
+
+/* Device pointers of the result slabs (valid until the next upload / destroy). */
+void* hjd_batch_device_rgb(hjd_batch* b);
+void* hjd_batch_device_coef(hjd_batch* b);
+void* hjd_batch_device_planes(hjd_batch* b);
+
+/* Device -> host copies (synchronous with respect to the batch stream). */
+int  hjd_batch_download_rgb(hjd_batch* b, uint8_t* dst /* hjd_batch_rgb_bytes */);
+int  hjd_batch_download_image(hjd_batch* b, int i, uint8_t* dst /* w*h*3 */);
+int  hjd_batch_download_coef(hjd_batch* b, int16_t* dst /* hjd_batch_coef_bytes */);
+int  hjd_batch_download_planes(hjd_batch* b, uint8_t* dst /* hjd_batch_plane_bytes */);
+
+/* End to end with host buffers: upload, decode and download in overlapped chunks
+ * (copy engines and SMs busy at the same time).  rgb_out receives image i at
+ * rgb_offsets_out[i] (tightly packed, 256-byte aligned starts); capacity in bytes. */
+int  hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes,
+                           int n, uint8_t* rgb_out, uint64_t rgb_capacity, uint64_t* rgb_offsets_out,
+                           int32_t* status_out, int chunk_images);
+/* Bytes hjd_batch_decode_host needs in rgb_out for these files (header parse only). */
+uint64_t hjd_rgb_slab_bytes(const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA binding. */
+void* hjd_host_alloc(size_t bytes);
+void  hjd_host_free(void* p);
+
+/* The float constants the kernels use (computed on the host with the libm expressions of
+ * loadjpg.cpp:96-102,120): cos_tab[p*8+k] = cosf(((2p+1)*k*3.14f)/16), cc[u*8+v] = C(u)*C(v). */
+void hjd_get_idct_tables(float cos_tab[64], float cc[64]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HJD_H */

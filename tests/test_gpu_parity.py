@@ -1,0 +1,220 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libhjd.so via ctypes); the oracle is only the checker.
+
+Bars (BASELINE.json north_star): entropy-decoded coefficients bit-exact; RGB max |diff| <= 1 per
+channel.  This implementation aims higher -- planes and RGB identical -- and the tests assert
+that, reporting mismatch counts when it does not hold.
+"""
+import glob
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
+GOLDEN = json.load(open(os.path.join(GOLDEN_DIR, "golden.json")))["cases"]
+RGB_TOLERANCE = 1      # north_star: max |diff| <= 1 per channel versus the reference's float IDCT
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def golden_files():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.jpg")))
+
+
+@pytest.fixture(scope="module")
+def dec(hjd):
+    d = hjd.BatchDecoder(0, hjd.FLAG_KEEP_PLANES)
+    yield d
+    d.close()
+
+
+def compare_image(dec, i, oracle, all_coef, slab, name):
+    inf = dec.info(i)
+    coef = dec.image_coefficients(i, all_coef)
+    assert coef.shape == oracle["coef"].shape, name
+    bad_blocks = int((coef != oracle["coef"]).any(axis=1).sum())
+    assert bad_blocks == 0, f"{name}: {bad_blocks} of {coef.shape[0]} coefficient blocks differ"
+    planes = dec.planes(i, slab)
+    for pname, a, b in zip("Y Cb Cr".split(), planes, oracle["planes"]):
+        if a is None:
+            continue
+        diff = int((a != b).sum())
+        assert diff == 0, f"{name}: plane {pname}: {diff} of {a.size} samples differ"
+    rgb = dec.rgb(i)
+    assert rgb.shape == oracle["rgb"].shape
+    d = np.abs(rgb.astype(np.int16) - oracle["rgb"].astype(np.int16))
+    mism = int((d != 0).sum())
+    assert d.max(initial=0) <= RGB_TOLERANCE, f"{name}: max RGB diff {d.max()} ({mism} samples differ)"
+    assert mism == 0, f"{name}: {mism} RGB samples differ (max {d.max()})"
+    return inf
+
+
+def test_golden_batch(dec, port):
+    """All committed fixtures in ONE batch (mixed geometry, sampling, tables, restart intervals)."""
+    names = golden_files()
+    files = [open(os.path.join(GOLDEN_DIR, n + ".jpg"), "rb").read() for n in names]
+    dec.upload(files)
+    dec.decode()
+    st = dec.status()
+    assert (st == 0).all(), dict(zip(names, st.tolist()))
+    all_coef, slab = dec.coefficients(), dec.plane_slab()
+    for i, (n, f) in enumerate(zip(names, files)):
+        g = GOLDEN[n]
+        coef = dec.image_coefficients(i, all_coef)
+        assert sha(coef) == g["coef_sha256"], n        # golden made by the real reference
+        assert sha(dec.rgb(i)) == g["rgb_sha256"], n
+        compare_image(dec, i, port.decode(f), all_coef, slab, n)
+
+
+def test_lenna_config1(hjd, dec, port, tmp_path):
+    """Config 1: data/Lenna.jpg -> BMP, coefficient sha256 from SURVEY.md section 4."""
+    from oracle import refbind
+    path = refbind.lenna_path()
+    if not path:
+        pytest.skip("oracle/_ref/data/Lenna.jpg not present")
+    jpg = open(path, "rb").read()
+    dec.upload([jpg])
+    dec.decode()
+    assert dec.status()[0] == 0
+    coef = dec.coefficients()
+    assert sha(coef) == "46c20f75d72e2525a21b3a0559c4fe098143cd9aed7468ac8c5ca78ec653a418"
+    o = port.decode(jpg)
+    compare_image(dec, 0, o, coef, dec.plane_slab(), "lenna")
+    assert sha(dec.rgb(0)) == GOLDEN["__lenna__"]["rgb_sha256"]
+    # the drop-in entry points
+    out = str(tmp_path / "out.bmp")
+    assert hjd.ConvertJpgFile(path, out) == 1
+    bmp = open(out, "rb").read()
+    assert len(bmp) == 786486
+    assert bmp == port.bmp24_bytes(o["rgb"])
+    rgb, w, h = hjd.DecodeJpgFileData(jpg)
+    assert (w, h) == (512, 512) and np.array_equal(rgb, o["rgb"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_images(dec, port, seed):
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    rng = np.random.default_rng(2000 + seed)
+    files, names = [], []
+    for k in range(6):
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+        sub = ["4:4:4", "4:2:2", "4:2:0"][int(rng.integers(0, 3))]
+        q = int(rng.integers(5, 101))
+        ri = int(rng.choice([0, 0, 1, 2, 7, 8, 64]))
+        gray = bool(rng.integers(0, 5) == 0)
+        opt = bool(rng.integers(0, 2))
+        sigma = float(rng.choice([0, 2, 6, 25]))
+        files.append(encode_jpeg(synth_rgb(w, h, 100 * seed + k, noise_sigma=sigma), q, sub, ri, gray=gray, optimize=opt))
+        names.append(f"s{seed}k{k}_{w}x{h}_{sub}_q{q}_ri{ri}_g{int(gray)}_o{int(opt)}")
+    dec.upload(files)
+    dec.decode()
+    assert (dec.status() == 0).all()
+    all_coef, slab = dec.coefficients(), dec.plane_slab()
+    for i, (n, f) in enumerate(zip(names, files)):
+        compare_image(dec, i, port.decode(f), all_coef, slab, n)
+
+
+def test_config2_1080p_restart8(dec, port):
+    """Config 2 geometry: 1920x1080 4:2:0 q85 Ri=8 (two images), full pixel parity."""
+    from tools.gen_jpegs import make_c2
+    files = [make_c2(0), make_c2(1)]
+    dec.upload(files)
+    dec.decode()
+    assert (dec.status() == 0).all()
+    inf = dec.info(0)
+    assert (inf.mcus_x, inf.mcus_y, inf.n_intervals, inf.n_blocks) == (120, 68, 1020, 48960)
+    all_coef, slab = dec.coefficients(), dec.plane_slab()
+    for i, f in enumerate(files):
+        compare_image(dec, i, port.decode(f), all_coef, slab, f"c2_{i}")
+
+
+def test_restart_twin_property(dec):
+    """Size-independent property: a restart-marker file and its restart-free twin (same pixels)
+    decode to identical coefficients and pixels."""
+    from tools.gen_jpegs import make_c2
+    a, b = make_c2(3, restart=True, width=640, height=360), make_c2(3, restart=False, width=640, height=360)
+    dec.upload([a, b])
+    dec.decode()
+    assert (dec.status() == 0).all()
+    c = dec.coefficients()
+    assert np.array_equal(dec.image_coefficients(0, c), dec.image_coefficients(1, c))
+    assert np.array_equal(dec.rgb(0), dec.rgb(1))
+
+
+def test_batch_results_independent_of_batch_composition(dec):
+    """Per-image outputs do not depend on what else is in the batch, nor on the order."""
+    files = list(cases.small_cases().values())[:10]
+    dec.upload(files)
+    dec.decode()
+    a = [dec.rgb(i).copy() for i in range(len(files))]
+    dec.upload(files[::-1])
+    dec.decode()
+    b = [dec.rgb(i).copy() for i in range(len(files))][::-1]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    dec.upload([files[4]])
+    dec.decode()
+    assert np.array_equal(dec.rgb(0), a[4])
+
+
+def test_bad_inputs_do_not_poison_the_batch(dec, port):
+    good = cases.small_cases()["420_64x48_q85"]
+    trunc = cases.small_cases()["420_100x70_ri2"]
+    files = [good, b"garbage", cases.progressive_jpeg(), good[:200], trunc[:len(trunc) // 2], cases.cmyk_jpeg(), good]
+    dec.upload(files)
+    dec.decode()
+    st = dec.status()
+    assert st[0] == 0 and st[6] == 0
+    assert st[1] < 0 and st[2] < 0 and st[3] < 0 and st[5] < 0
+    assert st[4] > 0                                    # decodes what is there, flags the rest
+    o = port.decode(good)
+    assert np.array_equal(dec.rgb(0), o["rgb"]) and np.array_equal(dec.rgb(6), o["rgb"])
+
+
+def test_corrupt_entropy_data_terminates(dec):
+    """Random bytes as entropy data: every loop is bounded (the reference can spin forever,
+    loadjpg.cpp:700-829) and the call returns with a status."""
+    jpg = bytearray(cases.small_cases()["420_100x70_ri2"])
+    rng = np.random.default_rng(5)
+    start = len(jpg) // 2
+    jpg[start:-2] = rng.integers(0, 255, size=len(jpg) - 2 - start, dtype=np.uint8).tobytes()
+    dec.upload([bytes(jpg)])
+    dec.decode()
+    dec.status()
+
+
+def test_host_scan_flag_matches_gpu_scan(hjd, dec):
+    files = [cases.small_cases()[k] for k in ("420_100x70_ri2", "444_100x70_ri8", "gray_33x9_ri4", "420_64x48_q85")]
+    dec.upload(files)
+    dec.decode()
+    a = [dec.rgb(i).copy() for i in range(len(files))]
+    with hjd.BatchDecoder(0, hjd.FLAG_HOST_SCAN) as d2:
+        d2.upload(files)
+        d2.decode()
+        assert (d2.status() == 0).all()
+        for i in range(len(files)):
+            assert np.array_equal(a[i], d2.rgb(i))
+
+
+def test_decode_host_end_to_end(hjd, port):
+    files = [cases.small_cases()[k] for k in ("420_100x70_ri2", "444_64x48_q85", "gray_64x64", "420_37x53_q75")]
+    arena = hjd.PinnedArena(files)
+    need = hjd.rgb_slab_bytes(arena)
+    out = np.zeros(need, dtype=np.uint8)
+    with hjd.BatchDecoder(0) as d:
+        offs, st = d.decode_host(arena, out.ctypes.data, need, chunk_images=3)
+    assert (st == 0).all()
+    for f, off in zip(files, offs):
+        o = port.decode(f)
+        n = o["rgb"].size
+        assert np.array_equal(out[int(off):int(off) + n].reshape(o["rgb"].shape), o["rgb"])
+    arena.close()

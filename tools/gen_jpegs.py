@@ -14,6 +14,7 @@ CLI:  python tools/gen_jpegs.py --config 2 --count 4 --out /tmp/jpegs
 from __future__ import annotations
 
 import argparse
+import functools
 import io
 import os
 from concurrent.futures import ProcessPoolExecutor
@@ -67,9 +68,28 @@ def encode_jpeg(rgb: np.ndarray, quality: int = 85, subsampling: str = "4:2:0",
     return buf.getvalue()
 
 
+@functools.lru_cache(maxsize=2)
+def _base_scene(width: int, height: int, group: int) -> np.ndarray:
+    # noise-free scene with a margin, shared by 64 consecutive images (float32 for later noise)
+    return synth_rgb(width + 128, height + 128, 900000 + group, noise_sigma=0.0).astype(np.float32)
+
+
+def synth_rgb_fast(width: int, height: int, i: int, noise_sigma: float = 6.0) -> np.ndarray:
+    """Bench-scale content: image i = a per-image crop/flip of its group's scene + its own sensor
+    noise (seed 1234+i).  ~5x cheaper than synth_rgb, still unique bytes per image."""
+    rng = np.random.default_rng(1234 + i)
+    base = _base_scene(width, height, i // 64)
+    dx, dy = int(rng.integers(0, 129)), int(rng.integers(0, 129))
+    img = base[dy:dy + height, dx:dx + width]
+    if rng.integers(0, 2):
+        img = img[:, ::-1]
+    img = img + rng.standard_normal(size=img.shape, dtype=np.float32) * noise_sigma
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
 def make_c2(i: int, restart: bool = True, width: int = 1920, height: int = 1080) -> bytes:
     """Config 2/3 image i (and, with restart=False, its restart-free twin: same pixels)."""
-    return encode_jpeg(synth_rgb(width, height, 1234 + i), 85, "4:2:0", 8 if restart else 0)
+    return encode_jpeg(synth_rgb_fast(width, height, i), 85, "4:2:0", 8 if restart else 0)
 
 
 def make_c4(size: int = 8192, seed: int = 4) -> bytes:
