@@ -140,13 +140,20 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
 // kernel 1a: restart-interval-parallel entropy decode
 // ------------------------------------------------------------------------------------------
 // One thread per restart interval (the unit the bitstream makes independent: byte-aligned start,
-// DC predictors reset).  Lanes free-run one Huffman symbol per loop trip; a lane that completes a
-// block raises a flag and the whole warp flushes that block's 128 bytes from its shared-memory
-// slot to HBM as one coalesced store, so the coefficient slab is written exactly once, densely.
+// DC predictors reset).  Every lane decodes one Huffman symbol per step; the step is written
+// branch-free (DC and AC share one data path, predictors and table offsets are rotated through
+// registers when the component changes) because with ~12 symbols per block some lane is in
+// every special case on every step, and a divergent sub-path costs the whole warp its full
+// instruction count.  Bit buffers are topped up on a fixed schedule (every HJD_ENT_REFILL_PERIOD
+// steps, all lanes together) rather than on demand.  A lane that completes a block raises a flag;
+// the warp then flushes up to four finished blocks per round from their shared-memory slots to
+// HBM with 128-bit accesses (8 lanes x 16 B per block), so the coefficient slab is written
+// exactly once, densely, in full 128-byte lines.
 //
 // Shared memory: the table set of this CTA's images (first-level LUTs + long-code tables) and one
-// 64 x int16 slot per thread, XOR-swizzled by lane so that scattered 2-byte coefficient stores and
-// the word-per-lane flush are both bank-conflict free.
+// 64 x int16 slot per thread whose 16-byte chunks are XOR-swizzled by (lane & 7), which keeps the
+// cooperative 128-bit flush conflict-free and spreads the scattered 2-byte coefficient stores.
+#define HJD_ENT_REFILL_PERIOD 3
 
 struct BitReader {
     const uint8_t* base;   // entropy-coded segment of the image
@@ -156,34 +163,32 @@ struct BitReader {
     int padbits;           // zero bits appended after `end`
 };
 
+// Append up to four bytes (as many as fit and as the interval still has).  FillNBits semantics
+// (loadjpg.cpp:446-484): the 00 stuffed after an FF data byte is dropped.  Bytes are taken up to
+// and including the first FF of the window so that the stuffed byte can be skipped without a
+// branch; a second FF in the same window is picked up by the next call.
 __device__ __forceinline__ void br_refill(BitReader& r)
 {
-    // FillNBits (loadjpg.cpp:446-484): FF 00 -> FF; an FF followed by anything else is data.
-    if (r.nbits > 32) return;
-    if (r.pos + 4 <= r.end) {
-        const uintptr_t a = (uintptr_t)(r.base + r.pos);
-        const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-        const uint32_t lo = __ldg(ap), hi = __ldg(ap + 1);
-        const uint32_t x = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
-        if ((((~x) - 0x01010101u) & x & 0x80808080u) == 0) {          // no FF byte: take all four
-            const uint32_t w = __byte_perm(x, 0, 0x0123);
-            r.buf |= (uint64_t)w << (32 - r.nbits);
-            r.nbits += 32;
-            r.pos += 4;
-            return;
-        }
-    }
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-        uint32_t b = 0;
-        if (r.pos < r.end) {
-            b = r.base[r.pos++];
-            if (b == 0xFFu && r.pos < r.end && r.base[r.pos] == 0) r.pos++;
-        } else {
-            r.padbits += 8;
-        }
-        r.buf |= (uint64_t)b << (56 - r.nbits);
-        r.nbits += 8;
+    const uint32_t avail = r.end - r.pos;                       // pos never passes end
+    const uintptr_t a = (uintptr_t)(r.base + r.pos);
+    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t lo = __ldg(ap), hi = __ldg(ap + 1);
+    const uint32_t x = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);       // 4 bytes, memory order
+    const uint32_t ffm = ((~x) - 0x01010101u) & x & 0x80808080u;             // lowest set bit is exact
+    const uint32_t j = ffm ? (uint32_t)(__ffs((int)ffm) - 1) >> 3 : 4u;      // first FF byte, 4 = none
+    const uint32_t room = (uint32_t)(64 - r.nbits) >> 3;
+    uint32_t take = min(min(j + 1u, 4u), min(room, avail));
+    const uint32_t skip = (take == j + 1u) ? 1u : 0u;                        // the FF went in: drop its 00
+    const uint32_t w = __byte_perm(x, 0, 0x0123);                            // big-endian
+    const uint32_t keep = (uint32_t)(0xFFFFFFFF00000000ull >> (8 * take));   // top `take` bytes
+    if (avail == 0) {                                                        // past the interval: zero padding
+        const int pad = (r.nbits <= 32) ? 32 : 0;
+        r.nbits += pad;
+        r.padbits += pad;
+    } else {
+        if (r.nbits < 64) r.buf |= ((uint64_t)(w & keep) << 32) >> r.nbits;
+        r.nbits += 8 * (int)take;
+        r.pos = min(r.pos + take + skip, r.end);
     }
 }
 
@@ -194,19 +199,19 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                       int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    uint32_t* s_slots = (uint32_t*)s_raw;                                  // [threads][32 words]
-    HjdHuffTable* s_tab = (HjdHuffTable*)(s_raw + HJD_ENT_THREADS * 128);  // [n_tabs]
+    uint8_t* s_slots = s_raw;                                   // [threads][128 bytes]
+    uint8_t* s_tab = s_raw + HJD_ENT_THREADS * 128;             // [n_tabs] HjdHuffTable
 
     const HjdEntropyWork wk = work[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31;
     const HjdTableSet* ts = tsets + wk.table_set;
-    const int n_tabs = ts->n_tabs;
     {
         const uint4* src = (const uint4*)ts->tab;
         uint4* dst = (uint4*)s_tab;
-        const int n16 = n_tabs * (int)(sizeof(HjdHuffTable) / 16);
+        const int n16 = ts->n_tabs * (int)(sizeof(HjdHuffTable) / 16);
         for (int i = tid; i < n16; i += HJD_ENT_THREADS) dst[i] = __ldg(src + i);
-        for (int i = tid; i < HJD_ENT_THREADS * 32; i += HJD_ENT_THREADS) s_slots[i] = 0;
+        uint4* z = (uint4*)s_slots;
+        for (int i = tid; i < HJD_ENT_THREADS * 8; i += HJD_ENT_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
 
@@ -215,7 +220,9 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     br.base = arena; br.pos = br.end = 0; br.buf = 0; br.nbits = 0; br.padbits = 0;
     uint32_t blocks_left = 0, gblk = 0;
     int img = 0, bpm = 1, ny = 1;
-    int dcY = 0, acY = 0, dcB = 0, acB = 0, dcR = 0, acR = 0;
+    // per component: byte offset of its DC table (low 16 bits) and AC table (high 16 bits) in s_tab;
+    // t0/p0 always belong to the component of the block being decoded
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
     if ((uint32_t)tid < wk.n_intervals) {
         const uint32_t g = wk.first_interval + tid;
         img = (int)wk.first_image;
@@ -233,96 +240,106 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
         if (br.end < br.pos || br.end > d->scan_len) br.end = br.pos;
         blocks_left = n_mcu * (uint32_t)bpm;
         gblk = (uint32_t)(d->block_base + (uint64_t)first_mcu * bpm);
-        dcY = ts->dc_of_comp[0]; acY = ts->ac_of_comp[0];
-        dcB = ts->dc_of_comp[1]; acB = ts->ac_of_comp[1];
-        dcR = ts->dc_of_comp[2]; acR = ts->ac_of_comp[2];
+        const uint32_t tsz = (uint32_t)sizeof(HjdHuffTable);
+        t0 = ts->dc_of_comp[0] * tsz | (ts->ac_of_comp[0] * tsz) << 16;
+        t1 = ts->dc_of_comp[1] * tsz | (ts->ac_of_comp[1] * tsz) << 16;
+        t2 = ts->dc_of_comp[2] * tsz | (ts->ac_of_comp[2] * tsz) << 16;
     }
 
-    uint16_t* my_slot = (uint16_t*)(s_slots + tid * 32);
+    uint8_t* my_slot = s_slots + tid * 128;
+    const uint32_t swz = (uint32_t)(lane & 7) << 4;      // byte XOR applied to the 16-byte chunk index
     int k = 0, bi = 0;                 // zig-zag index inside the block, block index inside the MCU
-    int pred0 = 0, pred1 = 0, pred2 = 0;
-    const HjdHuffTable* tdc = s_tab + dcY;
-    const HjdHuffTable* tac = s_tab + acY;
+    int p0 = 0, p1 = 0, p2 = 0;        // DC predictors, rotated with the component
     int flags = 0;
-    bool dead = false;                 // undecodable code met: zero-fill the rest of the interval
+    bool dead = false;                 // undecodable code or data exhausted: zero-fill the rest
 
-    // ---- symbol loop -----------------------------------------------------------------------
     while (__any_sync(0xffffffffu, blocks_left > 0)) {
-        bool done_block = false;
-        uint32_t flush_blk = 0;
-        if (blocks_left > 0) {
-            if (dead) {
-                k = 64;
-            } else {
-                br_refill(br);
-                const HjdHuffTable* t = (k == 0) ? tdc : tac;
-                const uint32_t peek = (uint32_t)(br.buf >> 48);
-                const uint32_t e = t->lut[peek >> (16 - HJD_LUT_BITS)];
-                uint32_t len = e >> 8, sym = e & 255u;
-                if (len == 0) {                                       // code longer than the first level
-                    len = HJD_LUT_BITS + 1;
-                    while (len <= 16 && peek >= t->limit[len]) len++;
-                    if (len > 16) {
-                        dead = true; flags |= HJD_ST_BAD_CODE; len = 0; sym = 0; k = 64;
-                    } else {
-                        sym = t->vals[((peek >> (16 - len)) + (uint32_t)t->delta[len]) & 255u];
-                    }
+        // scheduled top-up, all lanes together: afterwards >= 57 bits (or the interval's end)
+        br_refill(br);
+        br_refill(br);
+        if (br.padbits > 512) { dead = true; }
+#pragma unroll 1
+        for (int rep = 0; rep < HJD_ENT_REFILL_PERIOD; rep++) {
+            bool done_block = false;
+            uint32_t flush_blk = 0;
+            if (blocks_left > 0) {
+                if (br.nbits < 32 && !dead) {            // rare: a run of very long symbols
+                    br_refill(br);
+                    br_refill(br);
+                    br_refill(br);
+                    br_refill(br);
                 }
                 if (!dead) {
-                    br.buf <<= len; br.nbits -= (int)len;
+                    const bool is_dc = (k == 0);
+                    const uint32_t toff = is_dc ? (t0 & 0xFFFFu) : (t0 >> 16);
+                    const HjdHuffTable* t = (const HjdHuffTable*)(s_tab + toff);
+                    const uint32_t top = (uint32_t)(br.buf >> 32);
+                    const uint32_t e = t->lut[top >> (32 - HJD_LUT_BITS)];
+                    uint32_t len = e >> 8, sym = e & 255u;
+                    if (len == 0) {                                   // code longer than the first level
+                        const uint32_t peek = top >> 16;
+                        len = HJD_LUT_BITS + 1;
+                        while (len <= 16 && peek >= t->limit[len]) len++;
+                        if (len > 16) { dead = true; flags |= HJD_ST_BAD_CODE; len = 0; sym = 0; }
+                        else sym = t->vals[((peek >> (16 - len)) + (uint32_t)t->delta[len]) & 255u];
+                    }
+                    br.buf <<= len;
                     const uint32_t size = sym & 15u;
-                    int val = 0;
-                    if (size) {                                       // DetermineSign, loadjpg.cpp:396-409
-                        const uint32_t v = (uint32_t)(br.buf >> (64 - size));
-                        br.buf <<= size; br.nbits -= (int)size;
-                        val = (v < (1u << (size - 1))) ? (int)v - (int)((1u << size) - 1u) : (int)v;
+                    const uint32_t run = is_dc ? 0u : (sym >> 4);
+                    const uint32_t vv = (uint32_t)(br.buf >> 32);
+                    const uint32_t v = (vv >> 1) >> (31u - size);                 // `size` bits, 0 for size 0
+                    br.buf <<= size;
+                    br.nbits -= (int)(len + size);
+                    // DetermineSign (loadjpg.cpp:396-409); size 0 gives 0
+                    const uint32_t full = 1u << size;
+                    int val = (v < (full >> 1)) ? (int)v - (int)(full - 1u) : (int)v;
+                    if (is_dc) { p0 = (int)(short)(p0 + val); val = p0; }         // loadjpg.cpp:616-667
+                    const bool store = is_dc || (size != 0u);
+                    const uint32_t kpos = (uint32_t)k + run;                      // loadjpg.cpp:778
+                    if (store) {
+                        if (kpos <= 63u) *(uint16_t*)(my_slot + (((kpos << 1) ^ swz))) = (uint16_t)val;
+                        else flags |= HJD_ST_COEF_RANGE;                          // loadjpg.cpp:780-783
                     }
-                    if (k == 0) {                                     // DC: loadjpg.cpp:616-667
-                        const int c = (bi < ny) ? 0 : (bi == ny ? 1 : 2);
-                        int p = (c == 0) ? pred0 : (c == 1 ? pred1 : pred2);
-                        p = (int)(short)(p + val);
-                        if (c == 0) pred0 = p; else if (c == 1) pred1 = p; else pred2 = p;
-                        my_slot[(0 ^ lane) * 2] = (uint16_t)p;
-                        k = 1;
-                    } else {                                          // AC: loadjpg.cpp:768-808
-                        const uint32_t run = sym >> 4;
-                        if (size == 0) {
-                            if (run == 0) k = 64;                     // EOB
-                            else if (run == 15) k += 16;              // ZRL
-                        } else {
-                            k += (int)run;
-                            if (k <= 63) my_slot[(((k >> 1) ^ lane) << 1) | (k & 1)] = (uint16_t)val;
-                            else flags |= HJD_ST_COEF_RANGE;
-                            k++;
-                        }
+                    // EOB ends the block, ZRL skips 16, any other size-0 symbol is ignored (loadjpg.cpp:771-775)
+                    k = store ? (int)kpos + 1 : (run == 0u ? 64 : (run == 15u ? k + 16 : k));
+                    if (dead) k = 64;
+                } else {
+                    k = 64;
+                }
+                if (k >= 64) {
+                    done_block = true;
+                    flush_blk = gblk++;
+                    blocks_left--;
+                    k = 0;
+                    if (++bi == bpm) bi = 0;
+                    if (bpm > 1 && (bi == 0 || bi >= ny)) {       // component changes: Y -> Cb -> Cr -> Y
+                        const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
+                        const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
                     }
+                    if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
                 }
             }
-            if (k >= 64) {
-                done_block = true;
-                flush_blk = gblk++;
-                blocks_left--;
-                k = 0;
-                if (++bi == bpm) bi = 0;
-                const int c = (bi < ny) ? 0 : (bi == ny ? 1 : 2);
-                tdc = s_tab + ((c == 0) ? dcY : (c == 1 ? dcB : dcR));
-                tac = s_tab + ((c == 0) ? acY : (c == 1 ? acB : acR));
-                if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
+            uint32_t m = __ballot_sync(0xffffffffu, done_block);
+            if (m) {
+                __syncwarp();
+                do {                                   // up to four finished blocks per round
+                    const int o0 = __ffs(m) - 1;  m &= m - 1;
+                    const int o1 = __ffs(m) - 1;  m &= m - 1;
+                    const int o2 = __ffs(m) - 1;  m &= m - 1;
+                    const int o3 = __ffs(m) - 1;  m &= m - 1;
+                    const int q = lane >> 3;
+                    const int owner = (q == 0) ? o0 : (q == 1 ? o1 : (q == 2 ? o2 : o3));
+                    const uint32_t g = __shfl_sync(0xffffffffu, flush_blk, owner & 31);
+                    if (owner >= 0) {
+                        const int chunk = lane & 7;
+                        uint4* src = (uint4*)(s_slots + ((tid & ~31) + owner) * 128 + ((chunk ^ (owner & 7)) << 4));
+                        const uint4 w = *src;
+                        *src = make_uint4(0, 0, 0, 0);
+                        ((uint4*)coef)[(size_t)g * 8 + chunk] = w;
+                    }
+                } while (m);
+                __syncwarp();
             }
-        }
-        uint32_t m = __ballot_sync(0xffffffffu, done_block);
-        if (m) {
-            __syncwarp();
-            do {
-                const int owner = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t g = __shfl_sync(0xffffffffu, flush_blk, owner);
-                uint32_t* slot = s_slots + ((tid & ~31) + owner) * 32;
-                const uint32_t w = slot[lane ^ owner];
-                slot[lane ^ owner] = 0;
-                ((uint32_t*)coef)[(size_t)g * 32 + lane] = w;
-            } while (m);
-            __syncwarp();
         }
     }
     if (flags) atomicOr(&status[img], flags);
