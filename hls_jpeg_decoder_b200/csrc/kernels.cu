@@ -140,26 +140,41 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
 // kernel 1a: restart-interval-parallel entropy decode
 // ------------------------------------------------------------------------------------------
 // One thread per restart interval (the unit the bitstream makes independent: byte-aligned start,
-// DC predictors reset).  Every lane decodes one Huffman symbol per step; the step is written
-// branch-free (DC and AC share one data path, predictors and table offsets are rotated through
-// registers when the component changes) because with ~12 symbols per block some lane is in
-// every special case on every step, and a divergent sub-path costs the whole warp its full
-// instruction count.  Bit buffers are topped up on a fixed schedule (every HJD_ENT_REFILL_PERIOD
-// steps, all lanes together) rather than on demand.  A lane that completes a block raises a flag;
-// the warp then flushes up to four finished blocks per round from their shared-memory slots to
-// HBM with 128-bit accesses (8 lanes x 16 B per block), so the coefficient slab is written
-// exactly once, densely, in full 128-byte lines.
+// DC predictors reset).  The kernel is instruction-issue bound, and with ~12 symbols per block
+// some lane of a warp is in every special case on every step, so a divergent sub-path costs the
+// whole warp its full instruction count.  Hence:
+//   * one branch-free symbol step shared by DC and AC (predictors and table offsets are rotated
+//     through registers when the component changes);
+//   * a round = one scheduled bit-buffer top-up for all lanes + HJD_ENT_SYMS symbol steps; a lane
+//     that completes its block inside a round idles until the round ends, so block hand-over and
+//     flushing are paid once per round instead of once per symbol;
+//   * finished blocks are published in a small shared-memory list and flushed four at a time from
+//     their slots to HBM with 128-bit accesses (8 lanes x 16 B per block): the coefficient slab is
+//     written exactly once, densely, in full 128-byte lines;
+//   * shared memory is addressed with 32-bit shared-window addresses (ld/st.shared).
 //
-// Shared memory: the table set of this CTA's images (first-level LUTs + long-code tables) and one
-// 64 x int16 slot per thread whose 16-byte chunks are XOR-swizzled by (lane & 7), which keeps the
-// cooperative 128-bit flush conflict-free and spreads the scattered 2-byte coefficient stores.
-#define HJD_ENT_REFILL_PERIOD 3
+// Shared memory: [threads x 128 B] coefficient slots, 16-byte chunks XOR-swizzled by (lane & 7)
+// (conflict-free 128-bit flush, spread 2-byte scatter stores); [warps x 32 x 8 B] flush lists;
+// the table set of this CTA's images (per component: DC table then AC table, contiguous).
+#define HJD_ENT_SYMS 3
+
+__device__ __forceinline__ uint32_t hjd_lds_u16(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t hjd_lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t hjd_lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void hjd_sts_u16_sync(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void hjd_sts_v2_sync(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ uint2 hjd_lds_v2_sync(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 hjd_lds_v4_sync(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void hjd_sts_zero16_sync(uint32_t a) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(a), "r"(0) : "memory"); }
+// PTX shifts clamp the amount to 32 (result 0), unlike C++ where a shift by 32 is undefined.
+__device__ __forceinline__ uint32_t hjd_shr(uint32_t v, uint32_t n) { uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t hjd_shl(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 
 struct BitReader {
     const uint8_t* base;   // entropy-coded segment of the image
     uint32_t pos, end;     // byte cursor / end of this interval (relative to base)
-    uint64_t buf;          // MSB-aligned bit window
-    int nbits;             // valid bits in buf
+    uint32_t hi, lo;       // MSB-aligned 64-bit window (hi:lo)
+    int nbits;             // valid bits in the window
     int padbits;           // zero bits appended after `end`
 };
 
@@ -172,24 +187,21 @@ __device__ __forceinline__ void br_refill(BitReader& r)
     const uint32_t avail = r.end - r.pos;                       // pos never passes end
     const uintptr_t a = (uintptr_t)(r.base + r.pos);
     const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-    const uint32_t lo = __ldg(ap), hi = __ldg(ap + 1);
-    const uint32_t x = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);       // 4 bytes, memory order
+    const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1);
+    const uint32_t x = __funnelshift_r(w0, w1, (uint32_t)(a & 3) * 8);       // 4 bytes, memory order
     const uint32_t ffm = ((~x) - 0x01010101u) & x & 0x80808080u;             // lowest set bit is exact
-    const uint32_t j = ffm ? (uint32_t)(__ffs((int)ffm) - 1) >> 3 : 4u;      // first FF byte, 4 = none
+    const uint32_t j = (uint32_t)(__ffs((int)ffm) - 1) >> 3;                 // first FF byte; >= 4 when none
     const uint32_t room = (uint32_t)(64 - r.nbits) >> 3;
-    uint32_t take = min(min(j + 1u, 4u), min(room, avail));
+    const uint32_t take = min(min(j + 1u, 4u), min(room, avail));
     const uint32_t skip = (take == j + 1u) ? 1u : 0u;                        // the FF went in: drop its 00
-    const uint32_t w = __byte_perm(x, 0, 0x0123);                            // big-endian
-    const uint32_t keep = (uint32_t)(0xFFFFFFFF00000000ull >> (8 * take));   // top `take` bytes
-    if (avail == 0) {                                                        // past the interval: zero padding
-        const int pad = (r.nbits <= 32) ? 32 : 0;
-        r.nbits += pad;
-        r.padbits += pad;
-    } else {
-        if (r.nbits < 64) r.buf |= ((uint64_t)(w & keep) << 32) >> r.nbits;
-        r.nbits += 8 * (int)take;
-        r.pos = min(r.pos + take + skip, r.end);
-    }
+    const uint32_t w = __byte_perm(x, 0, 0x0123) & ~hjd_shr(0xFFFFFFFFu, 8 * take);   // top `take` bytes, big-endian
+    // window |= w >> nbits (as a 64-bit quantity whose top word is w)
+    const uint32_t n = (uint32_t)r.nbits;
+    r.hi |= hjd_shr(w, n);
+    r.lo |= (n >= 32u) ? hjd_shr(w, n - 32u) : hjd_shl(w, 32u - n);
+    r.nbits += 8 * (int)take;
+    r.pos = min(r.pos + take + skip, r.end);
+    if (avail == 0 && r.nbits <= 32) { r.nbits += 32; r.padbits += 32; }     // past the interval: zero padding
 }
 
 __global__ void __launch_bounds__(HJD_ENT_THREADS)
@@ -199,30 +211,37 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                       int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    uint8_t* s_slots = s_raw;                                   // [threads][128 bytes]
-    uint8_t* s_tab = s_raw + HJD_ENT_THREADS * 128;             // [n_tabs] HjdHuffTable
+    constexpr uint32_t kSlotBytes = HJD_ENT_THREADS * 128;
+    constexpr uint32_t kListBytes = HJD_ENT_THREADS * 8;
+    constexpr uint32_t kTabBytes = (uint32_t)sizeof(HjdHuffTable);
+    const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t sh_list = sh_base + kSlotBytes;
+    const uint32_t sh_tab = sh_list + kListBytes;
 
     const HjdEntropyWork wk = work[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31;
     const HjdTableSet* ts = tsets + wk.table_set;
     {
-        const uint4* src = (const uint4*)ts->tab;
-        uint4* dst = (uint4*)s_tab;
-        const int n16 = ts->n_tabs * (int)(sizeof(HjdHuffTable) / 16);
-        for (int i = tid; i < n16; i += HJD_ENT_THREADS) dst[i] = __ldg(src + i);
-        uint4* z = (uint4*)s_slots;
+        // component c's DC table goes to slot 2c, its AC table to slot 2c+1
+        const int ncomp_tabs = 3;
+        const int n16 = (int)(kTabBytes / 16);
+        for (int c = 0; c < ncomp_tabs; c++) {
+            const uint4* sdc = (const uint4*)&ts->tab[ts->dc_of_comp[c]];
+            const uint4* sac = (const uint4*)&ts->tab[ts->ac_of_comp[c]];
+            uint4* ddc = (uint4*)(s_raw + kSlotBytes + kListBytes + (2 * c) * kTabBytes);
+            uint4* dac = (uint4*)(s_raw + kSlotBytes + kListBytes + (2 * c + 1) * kTabBytes);
+            for (int i = tid; i < n16; i += HJD_ENT_THREADS) { ddc[i] = __ldg(sdc + i); dac[i] = __ldg(sac + i); }
+        }
+        uint4* z = (uint4*)s_raw;
         for (int i = tid; i < HJD_ENT_THREADS * 8; i += HJD_ENT_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
 
     // ---- per-lane interval setup -----------------------------------------------------------
     BitReader br;
-    br.base = arena; br.pos = br.end = 0; br.buf = 0; br.nbits = 0; br.padbits = 0;
+    br.base = arena; br.pos = br.end = 0; br.hi = br.lo = 0; br.nbits = 0; br.padbits = 0;
     uint32_t blocks_left = 0, gblk = 0;
     int img = 0, bpm = 1, ny = 1;
-    // per component: byte offset of its DC table (low 16 bits) and AC table (high 16 bits) in s_tab;
-    // t0/p0 always belong to the component of the block being decoded
-    uint32_t t0 = 0, t1 = 0, t2 = 0;
     if ((uint32_t)tid < wk.n_intervals) {
         const uint32_t g = wk.first_interval + tid;
         img = (int)wk.first_image;
@@ -240,106 +259,100 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
         if (br.end < br.pos || br.end > d->scan_len) br.end = br.pos;
         blocks_left = n_mcu * (uint32_t)bpm;
         gblk = (uint32_t)(d->block_base + (uint64_t)first_mcu * bpm);
-        const uint32_t tsz = (uint32_t)sizeof(HjdHuffTable);
-        t0 = ts->dc_of_comp[0] * tsz | (ts->ac_of_comp[0] * tsz) << 16;
-        t1 = ts->dc_of_comp[1] * tsz | (ts->ac_of_comp[1] * tsz) << 16;
-        t2 = ts->dc_of_comp[2] * tsz | (ts->ac_of_comp[2] * tsz) << 16;
     }
-
-    uint8_t* my_slot = s_slots + tid * 128;
-    const uint32_t swz = (uint32_t)(lane & 7) << 4;      // byte XOR applied to the 16-byte chunk index
+    // shared address of the current component's DC table (its AC table follows); rotated with p0..p2
+    uint32_t t0 = sh_tab, t1 = sh_tab + 2 * kTabBytes, t2 = sh_tab + 4 * kTabBytes;
+    int p0 = 0, p1 = 0, p2 = 0;        // DC predictors
+    const uint32_t my_slot = sh_base + (uint32_t)tid * 128u;
+    const uint32_t swz = (uint32_t)(lane & 7) << 4;      // XOR on the 16-byte chunk index
+    const uint32_t warp_slots = sh_base + (uint32_t)(tid & ~31) * 128u;
+    const uint32_t warp_list = sh_list + (uint32_t)(tid & ~31) * 8u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     int k = 0, bi = 0;                 // zig-zag index inside the block, block index inside the MCU
-    int p0 = 0, p1 = 0, p2 = 0;        // DC predictors, rotated with the component
     int flags = 0;
     bool dead = false;                 // undecodable code or data exhausted: zero-fill the rest
 
     while (__any_sync(0xffffffffu, blocks_left > 0)) {
-        // scheduled top-up, all lanes together: afterwards >= 57 bits (or the interval's end)
+        // scheduled top-up, all lanes together
         br_refill(br);
-        br_refill(br);
-        if (br.padbits > 512) { dead = true; }
-#pragma unroll 1
-        for (int rep = 0; rep < HJD_ENT_REFILL_PERIOD; rep++) {
-            bool done_block = false;
-            uint32_t flush_blk = 0;
-            if (blocks_left > 0) {
-                if (br.nbits < 32 && !dead) {            // rare: a run of very long symbols
-                    br_refill(br);
-                    br_refill(br);
-                    br_refill(br);
-                    br_refill(br);
-                }
-                if (!dead) {
-                    const bool is_dc = (k == 0);
-                    const uint32_t toff = is_dc ? (t0 & 0xFFFFu) : (t0 >> 16);
-                    const HjdHuffTable* t = (const HjdHuffTable*)(s_tab + toff);
-                    const uint32_t top = (uint32_t)(br.buf >> 32);
-                    const uint32_t e = t->lut[top >> (32 - HJD_LUT_BITS)];
-                    uint32_t len = e >> 8, sym = e & 255u;
-                    if (len == 0) {                                   // code longer than the first level
-                        const uint32_t peek = top >> 16;
-                        len = HJD_LUT_BITS + 1;
-                        while (len <= 16 && peek >= t->limit[len]) len++;
-                        if (len > 16) { dead = true; flags |= HJD_ST_BAD_CODE; len = 0; sym = 0; }
-                        else sym = t->vals[((peek >> (16 - len)) + (uint32_t)t->delta[len]) & 255u];
+        if (br.nbits <= 40) br_refill(br);               // busy stretch: keep the reserve up
+        if (br.padbits > 512) dead = true;
+        const bool live = blocks_left > 0;
+        bool done_block = !live ? false : dead;
+        if (live && !dead) {
+#pragma unroll
+            for (int rep = 0; rep < HJD_ENT_SYMS; rep++) {
+                if (!done_block) {
+                    if (br.nbits < 32) {                 // rare: several very long symbols in a row
+                        br_refill(br); br_refill(br); br_refill(br); br_refill(br);
                     }
-                    br.buf <<= len;
+                    const uint32_t is_ac = (uint32_t)min(k, 1);
+                    const uint32_t t = t0 + is_ac * kTabBytes;
+                    const uint32_t e = hjd_lds_u16(t + ((br.hi >> (32 - HJD_LUT_BITS)) << 1));
+                    uint32_t len = e >> 8, sym = e & 255u;
+                    if (len == 0) {                      // code longer than the first-level table
+                        const uint32_t peek = br.hi >> 16;
+                        len = HJD_LUT_BITS + 1;
+                        while (len <= 16 && peek >= hjd_lds_u32(t + HJD_LUT_SIZE * 2 + len * 4)) len++;
+                        if (len > 16) { dead = true; flags |= HJD_ST_BAD_CODE; len = 0; sym = 0; }
+                        else {
+                            const uint32_t dl = hjd_lds_u32(t + HJD_LUT_SIZE * 2 + 68 + len * 4);
+                            sym = hjd_lds_u8(t + HJD_LUT_SIZE * 2 + 136 + (((peek >> (16 - len)) + dl) & 255u));
+                        }
+                    }
                     const uint32_t size = sym & 15u;
-                    const uint32_t run = is_dc ? 0u : (sym >> 4);
-                    const uint32_t vv = (uint32_t)(br.buf >> 32);
-                    const uint32_t v = (vv >> 1) >> (31u - size);                 // `size` bits, 0 for size 0
-                    br.buf <<= size;
-                    br.nbits -= (int)(len + size);
-                    // DetermineSign (loadjpg.cpp:396-409); size 0 gives 0
-                    const uint32_t full = 1u << size;
-                    int val = (v < (full >> 1)) ? (int)v - (int)(full - 1u) : (int)v;
-                    if (is_dc) { p0 = (int)(short)(p0 + val); val = p0; }         // loadjpg.cpp:616-667
-                    const bool store = is_dc || (size != 0u);
-                    const uint32_t kpos = (uint32_t)k + run;                      // loadjpg.cpp:778
+                    const uint32_t run = is_ac ? (sym >> 4) : 0u;
+                    // value bits follow the code
+                    const uint32_t after = __funnelshift_l(br.lo, br.hi, len);            // window << len, top word
+                    const uint32_t v = hjd_shr(after, 32u - size);                         // 0 for size 0
+                    // DetermineSign (loadjpg.cpp:396-409): leading 0 bit -> v - (2^size - 1)
+                    const int neg = ~((int)after >> 31);                                   // all ones if negative
+                    int val = (int)v + (neg & (int)(hjd_shl(0xFFFFFFFFu, size) + 1u));
+                    const uint32_t used = len + size;                                      // <= 31
+                    br.hi = __funnelshift_l(br.lo, br.hi, used);
+                    br.lo <<= used;
+                    br.nbits -= (int)used;
+                    if (!is_ac) { p0 = (int)(short)(p0 + val); val = p0; }                 // loadjpg.cpp:616-667
+                    const bool store = (!is_ac) || (size != 0u);
+                    const uint32_t kpos = (uint32_t)k + run;                               // loadjpg.cpp:778
                     if (store) {
-                        if (kpos <= 63u) *(uint16_t*)(my_slot + (((kpos << 1) ^ swz))) = (uint16_t)val;
-                        else flags |= HJD_ST_COEF_RANGE;                          // loadjpg.cpp:780-783
+                        if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)val);
+                        else flags |= HJD_ST_COEF_RANGE;                                   // loadjpg.cpp:780-783
                     }
                     // EOB ends the block, ZRL skips 16, any other size-0 symbol is ignored (loadjpg.cpp:771-775)
                     k = store ? (int)kpos + 1 : (run == 0u ? 64 : (run == 15u ? k + 16 : k));
-                    if (dead) k = 64;
-                } else {
-                    k = 64;
-                }
-                if (k >= 64) {
-                    done_block = true;
-                    flush_blk = gblk++;
-                    blocks_left--;
-                    k = 0;
-                    if (++bi == bpm) bi = 0;
-                    if (bpm > 1 && (bi == 0 || bi >= ny)) {       // component changes: Y -> Cb -> Cr -> Y
-                        const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
-                        const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
-                    }
-                    if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
+                    done_block = (k >= 64) || dead;
                 }
             }
-            uint32_t m = __ballot_sync(0xffffffffu, done_block);
-            if (m) {
-                __syncwarp();
-                do {                                   // up to four finished blocks per round
-                    const int o0 = __ffs(m) - 1;  m &= m - 1;
-                    const int o1 = __ffs(m) - 1;  m &= m - 1;
-                    const int o2 = __ffs(m) - 1;  m &= m - 1;
-                    const int o3 = __ffs(m) - 1;  m &= m - 1;
-                    const int q = lane >> 3;
-                    const int owner = (q == 0) ? o0 : (q == 1 ? o1 : (q == 2 ? o2 : o3));
-                    const uint32_t g = __shfl_sync(0xffffffffu, flush_blk, owner & 31);
-                    if (owner >= 0) {
-                        const int chunk = lane & 7;
-                        uint4* src = (uint4*)(s_slots + ((tid & ~31) + owner) * 128 + ((chunk ^ (owner & 7)) << 4));
-                        const uint4 w = *src;
-                        *src = make_uint4(0, 0, 0, 0);
-                        ((uint4*)coef)[(size_t)g * 8 + chunk] = w;
-                    }
-                } while (m);
-                __syncwarp();
+        }
+        // ---- block hand-over ---------------------------------------------------------------
+        uint32_t flush_blk = 0;
+        if (done_block) {
+            flush_blk = gblk++;
+            blocks_left--;
+            k = 0;
+            if (++bi == bpm) bi = 0;
+            if (bpm > 1 && (bi == 0 || bi >= ny)) {       // component changes: Y -> Cb -> Cr -> Y
+                const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
+                const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
             }
+            if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
+        }
+        // ---- cooperative flush of the finished blocks --------------------------------------
+        const uint32_t m = __ballot_sync(0xffffffffu, done_block);
+        if (m) {
+            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane);
+            __syncwarp();
+            const int n_done = __popc(m);
+            const uint32_t chunk = (uint32_t)lane & 7u;
+            for (int idx = lane >> 3; idx < n_done; idx += 4) {
+                const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);          // {block, owner lane}
+                const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
+                const uint4 w = hjd_lds_v4_sync(src);
+                hjd_sts_zero16_sync(src);
+                ((uint4*)coef)[(size_t)ent.x * 8 + chunk] = w;
+            }
+            __syncwarp();
         }
     }
     if (flags) atomicOr(&status[img], flags);
@@ -350,7 +363,7 @@ cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc*
                                        int16_t* coef, int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    const size_t smem = HJD_ENT_THREADS * 128 + HJD_MAX_TABLES * sizeof(HjdHuffTable);
+    const size_t smem = HJD_ENT_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
