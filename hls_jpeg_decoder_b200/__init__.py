@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = ["ConvertJpgFile", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhjd.so")
@@ -33,6 +33,7 @@ INCLUDE_PATH = os.path.join(os.path.dirname(_HERE), "include", "hjd.h")
 
 FLAG_KEEP_PLANES = 1
 FLAG_HOST_SCAN = 2
+FLAG_FUSED = 4
 
 IMG_WARN_BAD_CODE, IMG_WARN_COEF_RANGE, IMG_WARN_OVERRUN, IMG_WARN_RESTART = 1, 2, 4, 8
 
@@ -81,6 +82,7 @@ _SIGS = {
     "hjd_batch_upload_arena": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int]),
     "hjd_batch_decode": (c_int, [c_void_p]),
     "hjd_batch_sync": (c_int, [c_void_p]),
+    "hjd_batch_set_overlap": (c_int, [c_void_p, c_int]),
     "hjd_batch_num_images": (c_int, [c_void_p]),
     "hjd_batch_get_info": (c_int, [c_void_p, c_int, POINTER(ImageInfo)]),
     "hjd_batch_get_status": (c_int, [c_void_p, c_void_p]),
@@ -270,6 +272,11 @@ class BatchDecoder:
 
     def sync(self) -> None:
         _check(lib().hjd_batch_sync(self._h), "hjd_batch_sync")
+
+    def set_overlap(self, on) -> None:
+        """Chunked multi-stream execution: 0/False = one stream (per-stage timings valid), 1/True =
+        default chunking, n > 1 = target blocks per chunk.  Takes effect at the next upload."""
+        _check(lib().hjd_batch_set_overlap(self._h, int(on)), "hjd_batch_set_overlap")
 
     def mark(self, slot: int) -> None:
         _check(lib().hjd_batch_mark(self._h, slot), "hjd_batch_mark")

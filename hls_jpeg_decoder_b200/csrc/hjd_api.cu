@@ -76,6 +76,21 @@ struct PinBuf {
 // ------------------------------------------------------------------------------------------
 struct FileRef { const uint8_t* ptr; int64_t size; uint64_t dev_off; };
 
+// A contiguous range of images that is uploaded / decoded / downloaded as one unit on one stream.
+// Chunks of one batch use disjoint regions of the same slabs, so they can be in flight together:
+// copy engines and SMs overlap, and the memory-bound colour kernel of one chunk shares the SMs with
+// the issue-bound entropy / IDCT kernels of another.
+struct Chunk {
+    int img0 = 0, img1 = 0;
+    uint32_t work0 = 0, work1 = 0;
+    uint64_t arena_lo = 0, arena_hi = 0;      // device arena byte range holding these files
+    uint64_t rgb_lo = 0, rgb_hi = 0;
+    uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0;
+    uint64_t blocks = 0;
+};
+
+#define HJD_NSTREAMS 3
+
 struct hjd_batch {
     int device = 0;
     unsigned flags = 0;
@@ -83,6 +98,12 @@ struct hjd_batch {
     bool own_stream = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t mark[4] = {nullptr, nullptr, nullptr, nullptr};   // hjd_batch_mark
+    cudaStream_t aux[HJD_NSTREAMS] = {nullptr, nullptr, nullptr}; // chunk streams
+    cudaEvent_t ev_fork = nullptr, ev_join[HJD_NSTREAMS] = {nullptr, nullptr, nullptr};
+    std::vector<Chunk> chunks;
+    std::vector<FileRef> files;
+    const uint8_t* contig_src = nullptr;      // host address of device-arena offset 0 (arena uploads)
+    int overlap = 1;                                               // 0: one chunk, one stream (stage timings)
 
     // host metadata of the uploaded batch
     std::vector<HjdImageDesc> imgs;
@@ -94,7 +115,8 @@ struct hjd_batch {
     std::vector<uint8_t> host_restart_warn;     // HJD_FLAG_HOST_SCAN only
     std::unordered_map<uint64_t, uint32_t> tset_of, qset_of;
     uint64_t total_blocks = 0, rgb_bytes = 0, plane_bytes = 0, scan_bytes = 0, pixels = 0, arena_bytes = 0;
-    uint32_t total_intervals = 0, max_blocks = 0, max_w = 0, max_h = 0;
+    uint32_t total_intervals = 0, max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0;
+    size_t fused_smem = 0;
     bool any_parse_error = false;
     bool uploaded = false, decoded = false;
     int launches = 0;
@@ -145,6 +167,9 @@ extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
     b->own_stream = true;
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev[i]);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&b->mark[i]);
+    for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking);
+    for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         float cos_tab[64], c0, c00;
         compute_idct_constants(cos_tab, &c0, &c00);
@@ -168,6 +193,8 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     b->h_meta.release();
     for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     for (int i = 0; i < 4; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
+    for (int i = 0; i < HJD_NSTREAMS; i++) { if (b->aux[i]) { cudaStreamSynchronize(b->aux[i]); cudaStreamDestroy(b->aux[i]); } if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]); }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -183,20 +210,23 @@ extern "C" int hjd_batch_set_stream(hjd_batch* b, void* cuda_stream)
     return HJD_OK;
 }
 
-// Parse + lay out + upload.  files[i].dev_off must already hold the arena offset of file i.
-static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_t* contiguous_src,
-                         uint64_t contiguous_bytes)
+// Parse + lay out + upload the metadata.  b->files[i].dev_off must already hold the arena offset of
+// file i.  The files themselves are copied by copy_files(), whole or chunk by chunk.
+static int upload_common(hjd_batch* b, bool chunked)
 {
+    std::vector<FileRef>& files = b->files;
     CU(cudaSetDevice(b->device));
     CU(cudaStreamSynchronize(b->stream));     // staging buffers of the previous batch are free again
     const int n = (int)files.size();
+    b->chunks.clear();
     b->imgs.assign(n, HjdImageDesc());
     b->parse_status.assign(n, 0);
     b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear();
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
     b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
-    b->total_intervals = b->max_blocks = b->max_w = b->max_h = 0;
+    b->total_intervals = b->max_blocks = b->max_w = b->max_h = b->max_strips = 0;
+    b->fused_smem = 0;
     b->any_parse_error = false;
     b->uploaded = b->decoded = false;
 
@@ -263,6 +293,13 @@ static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_
         if (d.n_blocks > b->max_blocks) b->max_blocks = (uint32_t)d.n_blocks;
         if (ps.width > b->max_w) b->max_w = ps.width;
         if (ps.height > b->max_h) b->max_h = ps.height;
+        {
+            const uint32_t S = HJD_FUSED_THREADS / d.blocks_per_mcu;
+            const uint32_t strips = (d.mcus_x + S - 1) / S * d.mcus_y;
+            if (strips > b->max_strips) b->max_strips = strips;
+            const size_t sm = hjd_fused_smem_bytes(ps.ncomp, ps.hf, ps.vf);
+            if (sm > b->fused_smem) b->fused_smem = sm;
+        }
 
         if (b->flags & HJD_FLAG_HOST_SCAN) {
             const size_t at = b->host_istart.size();
@@ -274,11 +311,53 @@ static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_
     }
     if (b->total_blocks >= 0xFFFFFFFFull) return fail(HJD_ERR_ARG, "hjd_batch_upload", "batch exceeds 2^32 blocks");
 
-    // entropy work list: runs of <= HJD_ENT_THREADS consecutive intervals sharing one table set
+    // chunk plan: contiguous image ranges of roughly equal block counts
     {
-        uint32_t cur_first = 0, cur_n = 0, cur_img = 0, cur_ts = 0;
+        int want = 1;
+        if (chunked && b->overlap) {
+            const uint64_t per_chunk = b->overlap > 1 ? (uint64_t)b->overlap : 1500000ull;
+            want = (int)(b->total_blocks / per_chunk);
+            if (want > 8) want = 8;
+            if (want > n) want = n;
+            if (want < 1) want = 1;
+        }
+        const uint64_t target = (b->total_blocks + want - 1) / (uint64_t)want;
+        Chunk c;
+        c.img0 = 0;
         for (int i = 0; i < n; i++) {
+            c.blocks += b->imgs[i].n_blocks;
+            const bool last = (i == n - 1);
+            if (last || (c.blocks >= target && (int)b->chunks.size() < want - 1)) {
+                c.img1 = i + 1;
+                b->chunks.push_back(c);
+                c = Chunk();
+                c.img0 = i + 1;
+            }
+        }
+        if (n == 0) b->chunks.clear();
+    }
+    // per chunk: extents, grid bounds and the entropy work list (runs of <= HJD_ENT_THREADS consecutive
+    // intervals sharing one table set; a run never crosses a chunk boundary)
+    for (Chunk& c : b->chunks) {
+        c.work0 = (uint32_t)b->work.size();
+        c.arena_lo = ~0ull; c.arena_hi = 0;
+        c.rgb_lo = b->imgs[c.img0].rgb_off;
+        c.rgb_hi = (c.img1 < n) ? b->imgs[c.img1].rgb_off : b->rgb_bytes;
+        uint32_t cur_first = 0, cur_n = 0, cur_img = 0, cur_ts = 0;
+        for (int i = c.img0; i < c.img1; i++) {
             const HjdImageDesc& d = b->imgs[i];
+            if (files[i].ptr && files[i].size > 0) {
+                if (files[i].dev_off < c.arena_lo) c.arena_lo = files[i].dev_off;
+                if (files[i].dev_off + (uint64_t)files[i].size > c.arena_hi) c.arena_hi = files[i].dev_off + (uint64_t)files[i].size;
+            }
+            if (d.n_blocks > c.max_blocks) c.max_blocks = (uint32_t)d.n_blocks;
+            if (d.width > c.max_w) c.max_w = d.width;
+            if (d.height > c.max_h) c.max_h = d.height;
+            if (d.blocks_per_mcu) {
+                const uint32_t S = HJD_FUSED_THREADS / d.blocks_per_mcu;
+                const uint32_t strips = (d.mcus_x + S - 1) / S * d.mcus_y;
+                if (strips > c.max_strips) c.max_strips = strips;
+            }
             uint32_t left = d.n_intervals, g = d.interval_base;
             while (left) {
                 if (cur_n && (cur_ts != d.table_set || cur_n == HJD_ENT_THREADS)) {
@@ -291,6 +370,8 @@ static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_
             }
         }
         if (cur_n) b->work.push_back(HjdEntropyWork{cur_first, cur_n, cur_img, cur_ts});
+        c.work1 = (uint32_t)b->work.size();
+        if (c.arena_lo == ~0ull) c.arena_lo = c.arena_hi = 0;
     }
 
     // device slabs
@@ -303,7 +384,7 @@ static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_
     CU(b->d_coef.ensure(b->total_blocks * 128 + 256));
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
-    if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
+    if (!(b->flags & HJD_FLAG_FUSED)) CU(b->d_planes.ensure(b->plane_bytes + 256));
 
     // metadata: one pinned staging block, then async copies
     const size_t sz_imgs = sizeof(HjdImageDesc) * (size_t)n;
@@ -327,47 +408,165 @@ static int upload_common(hjd_batch* b, std::vector<FileRef>& files, const uint8_
     if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemsetAsync(b->d_status.p, 0, sizeof(int32_t) * (size_t)(n + 1), b->stream));
 
-    // the files themselves
-    if (contiguous_src) {
-        CU(cudaMemcpyAsync(b->d_arena.p, contiguous_src, contiguous_bytes, cudaMemcpyHostToDevice, b->stream));
-    } else {
-        for (int i = 0; i < n; i++)
-            if (files[i].ptr && files[i].size > 0)
-                CU(cudaMemcpyAsync((uint8_t*)b->d_arena.p + files[i].dev_off, files[i].ptr, (size_t)files[i].size,
-                                   cudaMemcpyHostToDevice, b->stream));
-    }
     b->uploaded = true;
     return HJD_OK;
+}
+
+// Host -> device copy of the files of images [img0, img1) (one copy for arena uploads).
+static int copy_files(hjd_batch* b, const Chunk& c, cudaStream_t st)
+{
+    if (c.arena_hi <= c.arena_lo) return HJD_OK;
+    if (b->contig_src) {
+        CU(cudaMemcpyAsync((uint8_t*)b->d_arena.p + c.arena_lo, b->contig_src + c.arena_lo, c.arena_hi - c.arena_lo,
+                           cudaMemcpyHostToDevice, st));
+    } else {
+        for (int i = c.img0; i < c.img1; i++) {
+            const FileRef& f = b->files[i];
+            if (f.ptr && f.size > 0)
+                CU(cudaMemcpyAsync((uint8_t*)b->d_arena.p + f.dev_off, f.ptr, (size_t)f.size, cudaMemcpyHostToDevice, st));
+        }
+    }
+    return HJD_OK;
+}
+
+static int prepare_separate(hjd_batch* b, const uint8_t* const* bufs, const int64_t* sizes, int n, bool chunked)
+{
+    b->files.assign((size_t)n, FileRef{nullptr, 0, 0});
+    uint64_t off = 0;
+    for (int i = 0; i < n; i++) {
+        b->files[i] = FileRef{bufs[i], sizes[i], off};
+        off += align_up(sizes[i] > 0 ? (uint64_t)sizes[i] : 0, 16);
+    }
+    b->arena_bytes = off;
+    b->contig_src = nullptr;
+    return upload_common(b, chunked);
+}
+
+static int prepare_arena(hjd_batch* b, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n,
+                         bool chunked)
+{
+    b->files.assign((size_t)n, FileRef{nullptr, 0, 0});
+    int64_t lo = n ? offsets[0] : 0, hi = 0;
+    for (int i = 0; i < n; i++) {
+        if (offsets[i] < 0 || sizes[i] < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload_arena", "negative offset/size");
+        if (i && offsets[i] < offsets[i - 1]) return fail(HJD_ERR_ARG, "hjd_batch_upload_arena", "offsets must be ascending");
+        if (offsets[i] < lo) lo = offsets[i];
+        if (offsets[i] + sizes[i] > hi) hi = offsets[i] + sizes[i];
+    }
+    const int64_t lo_al = lo & ~(int64_t)15;      // keep the 16-byte phase of every file
+    for (int i = 0; i < n; i++) b->files[i] = FileRef{arena + offsets[i], sizes[i], (uint64_t)(offsets[i] - lo_al)};
+    b->arena_bytes = n ? (uint64_t)(hi - lo_al) : 0;
+    b->contig_src = n ? arena + lo_al : nullptr;
+    return upload_common(b, chunked);
 }
 
 extern "C" int hjd_batch_upload(hjd_batch* b, const uint8_t* const* bufs, const int64_t* sizes, int n)
 {
     if (!b || !bufs || !sizes || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload", "bad arguments");
-    std::vector<FileRef> files((size_t)n);
-    uint64_t off = 0;
-    for (int i = 0; i < n; i++) {
-        files[i] = FileRef{bufs[i], sizes[i], off};
-        off += align_up(sizes[i] > 0 ? (uint64_t)sizes[i] : 0, 16);
-    }
-    b->arena_bytes = off;
-    return upload_common(b, files, nullptr, 0);
+    int rc = prepare_separate(b, bufs, sizes, n, b->overlap > 1);
+    if (rc) return rc;
+    for (const Chunk& c : b->chunks) { rc = copy_files(b, c, b->stream); if (rc) return rc; }
+    return HJD_OK;
 }
 
 extern "C" int hjd_batch_upload_arena(hjd_batch* b, const uint8_t* arena, const int64_t* offsets,
                                       const int64_t* sizes, int n)
 {
     if (!b || !arena || !offsets || !sizes || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload_arena", "bad arguments");
-    std::vector<FileRef> files((size_t)n);
-    int64_t lo = n ? offsets[0] : 0, hi = 0;
-    for (int i = 0; i < n; i++) {
-        if (offsets[i] < 0 || sizes[i] < 0) return fail(HJD_ERR_ARG, "hjd_batch_upload_arena", "negative offset/size");
-        if (offsets[i] < lo) lo = offsets[i];
-        if (offsets[i] + sizes[i] > hi) hi = offsets[i] + sizes[i];
+    int rc = prepare_arena(b, arena, offsets, sizes, n, b->overlap > 1);
+    if (rc) return rc;
+    for (const Chunk& c : b->chunks) { rc = copy_files(b, c, b->stream); if (rc) return rc; }
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_set_overlap(hjd_batch* b, int on)
+{
+    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_set_overlap", "null batch");
+    b->overlap = on < 0 ? 0 : on;     // 0 serial, 1 default chunking, > 1: target blocks per chunk; next upload
+    return HJD_OK;
+}
+
+// Kernels of one chunk on one stream.  ev != nullptr: record stage boundaries (serial mode only).
+static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent_t* ev)
+{
+    const uint8_t* arena = (const uint8_t*)b->d_arena.p;
+    const HjdImageDesc* imgs = (const HjdImageDesc*)b->d_imgs.p;
+    int32_t* status = (int32_t*)b->d_status.p;
+    const int n = c.img1 - c.img0;
+    if (!(b->flags & HJD_FLAG_HOST_SCAN) && n > 0) {
+        CU(hjd_launch_marker_scan(arena, imgs, (uint32_t*)b->d_istart.p, status, c.img0, n, st));
+        b->launches += 1;
     }
-    const int64_t lo_al = lo & ~(int64_t)15;      // keep the 16-byte phase of every file
-    for (int i = 0; i < n; i++) files[i] = FileRef{arena + offsets[i], sizes[i], (uint64_t)(offsets[i] - lo_al)};
-    b->arena_bytes = n ? (uint64_t)(hi - lo_al) : 0;
-    return upload_common(b, files, n ? arena + lo_al : nullptr, b->arena_bytes);
+    if (ev) CU(cudaEventRecord(ev[1], st));
+    if (c.work1 > c.work0) {
+        CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
+                                      (const HjdEntropyWork*)b->d_work.p + c.work0, (int)(c.work1 - c.work0),
+                                      (int16_t*)b->d_coef.p, status, st));
+        b->launches += 1;
+    }
+    if (ev) CU(cudaEventRecord(ev[2], st));
+    if (b->flags & HJD_FLAG_FUSED) {
+        if (c.blocks) {
+            CU(hjd_launch_idct_color((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
+                                     (uint8_t*)b->d_rgb.p, n, c.max_strips, b->fused_smem, st));
+            b->launches += (n + 65534) / 65535;
+        }
+        if (ev) CU(cudaEventRecord(ev[3], st));
+    } else {
+        if (c.blocks) {
+            CU(hjd_launch_idct_planes((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
+                                      (uint8_t*)b->d_planes.p, n, c.max_blocks, st));
+            b->launches += (n + 65534) / 65535;
+        }
+        if (ev) CU(cudaEventRecord(ev[3], st));
+        if (c.blocks) {
+            CU(hjd_launch_color((const uint8_t*)b->d_planes.p, imgs + c.img0, (uint8_t*)b->d_rgb.p, n, c.max_w, c.max_h, st));
+            b->launches += (n + 65534) / 65535;
+        }
+    }
+    return HJD_OK;
+}
+
+// All chunks: optional H2D of the files, kernels, optional D2H of the RGB region into rgb_host.
+static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
+{
+    cudaStream_t main = b->stream;
+    b->launches = 0;
+    if (b->any_parse_error && b->rgb_bytes) CU(cudaMemsetAsync(b->d_rgb.p, 0, b->rgb_bytes, main));
+    CU(cudaEventRecord(b->ev[0], main));
+    if (b->chunks.size() <= 1) {
+        // serial: one stream, stage boundaries recorded
+        if (b->chunks.empty()) {
+            for (int k = 1; k <= 3; k++) CU(cudaEventRecord(b->ev[k], main));
+        } else {
+            const Chunk& c = b->chunks[0];
+            if (h2d) { int rc = copy_files(b, c, main); if (rc) return rc; CU(cudaEventRecord(b->ev[0], main)); }
+            int rc = launch_chunk(b, c, main, b->ev);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(b->ev[4], main));
+        if (rgb_host && b->rgb_bytes) CU(cudaMemcpyAsync(rgb_host, b->d_rgb.p, b->rgb_bytes, cudaMemcpyDeviceToHost, main));
+        return HJD_OK;
+    }
+    for (int k = 1; k <= 3; k++) CU(cudaEventRecord(b->ev[k], main));     // no per-stage times when chunks overlap
+    CU(cudaEventRecord(b->ev_fork, main));
+    for (int s = 0; s < HJD_NSTREAMS; s++) CU(cudaStreamWaitEvent(b->aux[s], b->ev_fork, 0));
+    for (size_t k = 0; k < b->chunks.size(); k++) {
+        const Chunk& c = b->chunks[k];
+        cudaStream_t st = b->aux[k % HJD_NSTREAMS];
+        if (h2d) { int rc = copy_files(b, c, st); if (rc) return rc; }
+        int rc = launch_chunk(b, c, st, nullptr);
+        if (rc) return rc;
+        if (rgb_host && c.rgb_hi > c.rgb_lo)
+            CU(cudaMemcpyAsync(rgb_host + c.rgb_lo, (const uint8_t*)b->d_rgb.p + c.rgb_lo, c.rgb_hi - c.rgb_lo,
+                               cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < HJD_NSTREAMS; s++) {
+        CU(cudaEventRecord(b->ev_join[s], b->aux[s]));
+        CU(cudaStreamWaitEvent(main, b->ev_join[s], 0));
+    }
+    CU(cudaEventRecord(b->ev[4], main));
+    return HJD_OK;
 }
 
 extern "C" int hjd_batch_decode(hjd_batch* b)
@@ -375,39 +574,8 @@ extern "C" int hjd_batch_decode(hjd_batch* b)
     if (!b) return fail(HJD_ERR_ARG, "hjd_batch_decode", "null batch");
     if (!b->uploaded) return fail(HJD_ERR_STATE, "hjd_batch_decode", "nothing uploaded");
     CU(cudaSetDevice(b->device));
-    const int n = (int)b->imgs.size();
-    cudaStream_t st = b->stream;
-    const uint8_t* arena = (const uint8_t*)b->d_arena.p;
-    const HjdImageDesc* imgs = (const HjdImageDesc*)b->d_imgs.p;
-    int32_t* status = (int32_t*)b->d_status.p;
-    b->launches = 0;
-
-    if (b->any_parse_error) CU(cudaMemsetAsync(b->d_rgb.p, 0, b->rgb_bytes, st));
-    CU(cudaEventRecord(b->ev[0], st));
-    if (!(b->flags & HJD_FLAG_HOST_SCAN) && n > 0) {
-        CU(hjd_launch_marker_scan(arena, imgs, (uint32_t*)b->d_istart.p, status, n, st));
-        b->launches += 1;
-    }
-    CU(cudaEventRecord(b->ev[1], st));
-    if (!b->work.empty()) {
-        CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
-                                      (const HjdEntropyWork*)b->d_work.p, (int)b->work.size(),
-                                      (int16_t*)b->d_coef.p, status, st));
-        b->launches += 1;
-    }
-    CU(cudaEventRecord(b->ev[2], st));
-    if (b->total_blocks) {
-        CU(b->d_planes.ensure(b->plane_bytes + 256));
-        CU(hjd_launch_idct_planes((const int16_t*)b->d_coef.p, imgs, (const HjdQuantSet*)b->d_qsets.p,
-                                  (uint8_t*)b->d_planes.p, n, b->max_blocks, st));
-        b->launches += (n + 65534) / 65535;
-    }
-    CU(cudaEventRecord(b->ev[3], st));
-    if (b->total_blocks) {
-        CU(hjd_launch_color((const uint8_t*)b->d_planes.p, imgs, (uint8_t*)b->d_rgb.p, n, b->max_w, b->max_h, st));
-        b->launches += (n + 65534) / 65535;
-    }
-    CU(cudaEventRecord(b->ev[4], st));
+    int rc = run_chunks(b, false, nullptr);
+    if (rc) return rc;
     b->decoded = true;
     return HJD_OK;
 }
@@ -521,7 +689,7 @@ extern "C" int hjd_batch_download_coef(hjd_batch* b, int16_t* dst)
 
 extern "C" int hjd_batch_download_planes(hjd_batch* b, uint8_t* dst)
 {
-    if (b && !b->d_planes.p) return fail(HJD_ERR_STATE, "hjd_batch_download_planes", "planes not kept");
+    if (b && (b->flags & HJD_FLAG_FUSED)) return fail(HJD_ERR_STATE, "hjd_batch_download_planes", "HJD_FLAG_FUSED keeps the planes in shared memory only");
     return download(b, dst, b ? b->d_planes.p : nullptr, b ? b->plane_bytes : 0, "hjd_batch_download_planes");
 }
 
@@ -543,22 +711,18 @@ extern "C" int hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const i
                                      int n, uint8_t* rgb_out, uint64_t rgb_capacity, uint64_t* rgb_offsets_out,
                                      int32_t* status_out, int chunk_images)
 {
+    (void)chunk_images;   // chunking is planned from the block counts (see upload_common)
     if (!b || !arena || !offsets || !sizes || !rgb_out || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "bad arguments");
-    if (chunk_images <= 0) chunk_images = n;
-    uint64_t out_off = 0;
-    for (int first = 0; first < n; first += chunk_images) {
-        const int cnt = (n - first < chunk_images) ? n - first : chunk_images;
-        int rc = hjd_batch_upload_arena(b, arena, offsets + first, sizes + first, cnt);
-        if (rc) return rc;
-        if (out_off + b->rgb_bytes > rgb_capacity) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "rgb_out too small");
-        rc = hjd_batch_decode(b);
-        if (rc) return rc;
-        if (b->rgb_bytes) CU(cudaMemcpyAsync(rgb_out + out_off, b->d_rgb.p, b->rgb_bytes, cudaMemcpyDeviceToHost, b->stream));
-        if (rgb_offsets_out)
-            for (int i = 0; i < cnt; i++) rgb_offsets_out[first + i] = out_off + b->imgs[i].rgb_off;
-        if (status_out) { rc = hjd_batch_get_status(b, status_out + first); if (rc) return rc; }
-        out_off += b->rgb_bytes;
-    }
+    CU(cudaSetDevice(b->device));
+    int rc = prepare_arena(b, arena, offsets, sizes, n, true);    // parse + metadata; files not copied yet
+    if (rc) return rc;
+    if (b->rgb_bytes > rgb_capacity) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "rgb_out too small");
+    rc = run_chunks(b, true, rgb_out);                            // per chunk: H2D, kernels, D2H
+    if (rc) return rc;
+    b->decoded = true;
+    if (rgb_offsets_out)
+        for (int i = 0; i < n; i++) rgb_offsets_out[i] = b->imgs[i].rgb_off;
+    if (status_out) { rc = hjd_batch_get_status(b, status_out); if (rc) return rc; }
     CU(cudaStreamSynchronize(b->stream));
     return HJD_OK;
 }

@@ -129,10 +129,10 @@ hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restr
 }
 
 cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* imgs, uint32_t* interval_start,
-                                   int32_t* status, int n_images, cudaStream_t st)
+                                   int32_t* status, int first_image, int n_images, cudaStream_t st)
 {
     if (n_images <= 0) return cudaSuccess;
-    hjd_k_marker_scan<<<n_images, 256, 0, st>>>(arena, imgs, interval_start, status, 0);
+    hjd_k_marker_scan<<<n_images, 256, 0, st>>>(arena, imgs, interval_start, status, first_image);
     return cudaGetLastError();
 }
 
@@ -434,6 +434,70 @@ __device__ __forceinline__ float hjd_exact_sum(const float bp[64], const float* 
     return sum;
 }
 
+// One 8x8 block: dequantise, IDCT, +128, clamp; rows go to dst[y*pitch + 0..7] (planes in HBM for
+// the unfused kernel, a shared-memory tile for the fused one).  s_cos: the cos table in shared
+// memory (the exact re-evaluation indexes it dynamically).
+__device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, const uint4* __restrict__ qp,
+                                               const float* s_cos, uint8_t* dst, uint32_t pitch)
+{
+    uint4 c[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i] = cp[i]; q[i] = __ldg(qp + i); }
+
+    float bp[64];
+    float a_dc;
+    const float a_ac = hjd_dequant_block(c, q, bp, &a_dc);
+    // re-evaluation window on the 0.25*sum scale: 24 * 2^-24 * A; DC-only blocks are exact (no window)
+    const float win = (a_ac == 0.f) ? -1.f : (a_ac + a_dc) * 1.430511474609375e-06f;
+
+    // pass 1 (horizontal frequency u -> position x): r[8v+x] = sum_u bp[8v+u] * cos[x][u]
+    float r[64];
+#pragma unroll
+    for (int v = 0; v < 8; v++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            float acc = bp[8 * v];                 // cos[x][0] == 1
+#pragma unroll
+            for (int u = 1; u < 8; u++) acc = fmaf(bp[8 * v + u], c_cos[x * 8 + u], acc);
+            r[8 * v + x] = acc;
+        }
+    // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples:
+    // |h - rint(h)| <= win  <=  an integer (truncation boundary) lies within the error window of h;
+    // everywhere else trunc(h) is provably the reference's value.
+    uint32_t row_lo[8], row_hi[8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) { row_lo[y] = 0; row_hi[y] = 0; }
+    uint32_t near_lo = 0, near_hi = 0;             // bit (8y + x)
+#pragma unroll
+    for (int x = 0; x < 8; x++)
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+            float acc = r[x];                      // v = 0, cos[y][0] == 1
+#pragma unroll
+            for (int v = 1; v < 8; v++) acc = fmaf(r[8 * v + x], c_cos[y * 8 + v], acc);
+            const float h = 0.25f * acc;
+            const float n = rintf(h);
+            const bool nearint = (fabsf(h - n) <= win) && (n != 0.f);   // (-1, 1) truncates to 0: no boundary at 0
+            const uint32_t pix = (uint32_t)hjd_finish_sample(acc);
+            if (x < 4) row_lo[y] |= pix << (8 * x); else row_hi[y] |= pix << (8 * (x - 4));
+            if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
+            else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + x); }
+        }
+
+#pragma unroll
+    for (int y = 0; y < 8; y++) *(uint2*)(dst + (size_t)y * pitch) = make_uint2(row_lo[y], row_hi[y]);
+
+    // exact re-evaluation of the flagged samples (same thread, later store wins)
+    while (near_lo | near_hi) {
+        int pos;
+        if (near_lo) { pos = __ffs(near_lo) - 1; near_lo &= near_lo - 1; }
+        else         { pos = 32 + __ffs(near_hi) - 1; near_hi &= near_hi - 1; }
+        const int y = pos >> 3, x = pos & 7;
+        const float sum = hjd_exact_sum(bp, s_cos + x * 8, s_cos + y * 8);
+        dst[(size_t)y * pitch + x] = (uint8_t)hjd_finish_sample(sum);
+    }
+}
+
 __global__ void __launch_bounds__(HJD_IDCT_THREADS)
 hjd_k_idct_planes(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
                   const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ planes, int img_base)
@@ -457,64 +521,8 @@ hjd_k_idct_planes(const int16_t* __restrict__ coef, const HjdImageDesc* __restri
         comp = (bi == ny) ? 1 : 2; pitch = d->c_pitch; poff = comp == 1 ? d->cb_off : d->cr_off;
         bx = mx; by = my;
     }
-
-    uint4 c[8], q[8];
-    const uint4* cp = (const uint4*)(coef + (d->block_base + b) * 64);
-    const uint4* qp = (const uint4*)(qsets[d->quant_set].q[comp]);
-#pragma unroll
-    for (int i = 0; i < 8; i++) { c[i] = cp[i]; q[i] = __ldg(qp + i); }
-
-    float bp[64];
-    float a_dc;
-    const float a_ac = hjd_dequant_block(c, q, bp, &a_dc);
-    // re-evaluation window on the 0.25*sum scale: 24 * 2^-24 * A; DC-only blocks are exact
-    const float win = (a_ac == 0.f) ? -1.f : (a_ac + a_dc) * 1.430511474609375e-06f;
-
-    // pass 1 (horizontal frequency u -> position x): r[8v+x] = sum_u bp[8v+u] * cos[x][u]
-    float r[64];
-#pragma unroll
-    for (int v = 0; v < 8; v++)
-#pragma unroll
-        for (int x = 0; x < 8; x++) {
-            float acc = bp[8 * v];                 // cos[x][0] == 1
-#pragma unroll
-            for (int u = 1; u < 8; u++) acc = fmaf(bp[8 * v + u], c_cos[x * 8 + u], acc);
-            r[8 * v + x] = acc;
-        }
-    // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples
-    uint32_t row_lo[8], row_hi[8];
-#pragma unroll
-    for (int y = 0; y < 8; y++) { row_lo[y] = 0; row_hi[y] = 0; }
-    uint32_t near_lo = 0, near_hi = 0;             // bit (8y + x)
-#pragma unroll
-    for (int x = 0; x < 8; x++)
-#pragma unroll
-        for (int y = 0; y < 8; y++) {
-            float acc = r[x];                      // v = 0, cos[y][0] == 1
-#pragma unroll
-            for (int v = 1; v < 8; v++) acc = fmaf(r[8 * v + x], c_cos[y * 8 + v], acc);
-            const float h = 0.25f * acc;
-            const float n = rintf(h);
-            const bool nearint = (fabsf(h - n) <= win) && (n != 0.f);
-            const uint32_t pix = (uint32_t)hjd_finish_sample(acc);
-            if (x < 4) row_lo[y] |= pix << (8 * x); else row_hi[y] |= pix << (8 * (x - 4));
-            if (y < 4) near_lo |= nearint ? (1u << (8 * y + x)) : 0u;
-            else       near_hi |= nearint ? (1u << (8 * (y - 4) + x)) : 0u;
-        }
-
-    uint8_t* dst = planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8;
-#pragma unroll
-    for (int y = 0; y < 8; y++) *(uint2*)(dst + (uint64_t)y * pitch) = make_uint2(row_lo[y], row_hi[y]);
-
-    // exact re-evaluation of the flagged samples (same thread, later store wins)
-    while (near_lo | near_hi) {
-        int pos;
-        if (near_lo) { pos = __ffs(near_lo) - 1; near_lo &= near_lo - 1; }
-        else         { pos = 32 + __ffs(near_hi) - 1; near_hi &= near_hi - 1; }
-        const int y = pos >> 3, x = pos & 7;
-        const float sum = hjd_exact_sum(bp, s_cos + x * 8, s_cos + y * 8);
-        dst[(uint64_t)y * pitch + x] = (uint8_t)hjd_finish_sample(sum);
-    }
+    hjd_idct_block((const uint4*)(coef + (d->block_base + b) * 64), (const uint4*)(qsets[d->quant_set].q[comp]),
+                   s_cos, planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8, pitch);
 }
 
 cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
@@ -538,15 +546,19 @@ cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs
 // (loadjpg.cpp:873-879 with the swapped argument names of the call at 918 resolved).
 // Chroma is replicated, nearest neighbour (loadjpg.cpp:911-912).
 
-__device__ __forceinline__ uint32_t hjd_clamp255(int v) { return (uint32_t)min(max(v, 0), 255); }
-
-__device__ __forceinline__ void hjd_ycc_pixel(int yv, float rr, float g1, float g2, float bb,
-                                              uint32_t& R, uint32_t& G, uint32_t& B)
+// No integer<->float conversion instructions (a quarter-rate-or-worse pipe that bounded the first
+// version of this kernel): a byte b becomes the float 2^23 + b by dropping it into the mantissa of
+// 0x4B000000 (PRMT), and trunc+clamp of a result c in [0, 255] is the low mantissa byte of
+// c + 2^23 rounded DOWN.  Clamping before flooring equals the reference's truncate-then-clamp.
+template <int SEL>
+__device__ __forceinline__ float hjd_byte_biased(uint32_t word)     // 2^23 + byte SEL of word, exactly
 {
-    const float fy = (float)yv;
-    R = hjd_clamp255(__float2int_rz(__fadd_rn(fy, rr)));
-    G = hjd_clamp255(__float2int_rz(__fsub_rn(__fsub_rn(fy, g1), g2)));
-    B = hjd_clamp255(__float2int_rz(__fadd_rn(fy, bb)));
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | SEL));
+}
+
+__device__ __forceinline__ uint32_t hjd_trunc_clamp_bits(float v)   // low byte = clamp((int)v, 0, 255)
+{
+    return __float_as_uint(__fadd_rd(fminf(fmaxf(v, 0.f), 255.f), 8388608.0f));
 }
 
 // 16 pixels -> 48 packed bytes.  HS = log2(horizontal luma factor): chroma sample i >> HS.
@@ -554,26 +566,44 @@ template <int HS>
 __device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_t cbw[4], const uint32_t crw[4],
                                              uint32_t out[12])
 {
-#pragma unroll
-    for (int i = 0; i < 12; i++) out[i] = 0;
+    uint32_t ch[48];                      // per output byte: a word whose low byte is the value
     float rr = 0.f, g1 = 0.f, g2 = 0.f, bb = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         if (HS == 0 || (i & 1) == 0) {
             const int ci = i >> HS;
-            const int cb = (int)((cbw[ci >> 2] >> (8 * (ci & 3))) & 255u) - 128;
-            const int cr = (int)((crw[ci >> 2] >> (8 * (ci & 3))) & 255u) - 128;
-            rr = __fmul_rn(1.402f, (float)cr);
-            g1 = __fmul_rn(0.34414f, (float)cb);
-            g2 = __fmul_rn(0.71414f, (float)cr);
-            bb = __fmul_rn(1.772f, (float)cb);
+            float cb, cr;                 // (Cb - 128), (Cr - 128), exact
+            switch (ci & 3) {
+                case 0: cb = hjd_byte_biased<0>(cbw[ci >> 2]); cr = hjd_byte_biased<0>(crw[ci >> 2]); break;
+                case 1: cb = hjd_byte_biased<1>(cbw[ci >> 2]); cr = hjd_byte_biased<1>(crw[ci >> 2]); break;
+                case 2: cb = hjd_byte_biased<2>(cbw[ci >> 2]); cr = hjd_byte_biased<2>(crw[ci >> 2]); break;
+                default: cb = hjd_byte_biased<3>(cbw[ci >> 2]); cr = hjd_byte_biased<3>(crw[ci >> 2]); break;
+            }
+            cb = __fadd_rn(cb, -8388736.0f);
+            cr = __fadd_rn(cr, -8388736.0f);
+            rr = __fmul_rn(1.402f, cr);
+            g1 = __fmul_rn(0.34414f, cb);
+            g2 = __fmul_rn(0.71414f, cr);
+            bb = __fmul_rn(1.772f, cb);
         }
-        const int yv = (int)((yw[i >> 2] >> (8 * (i & 3))) & 255u);
-        uint32_t R, G, B;
-        hjd_ycc_pixel(yv, rr, g1, g2, bb, R, G, B);
-        out[(3 * i) >> 2]     |= R << (8 * ((3 * i) & 3));
-        out[(3 * i + 1) >> 2] |= G << (8 * ((3 * i + 1) & 3));
-        out[(3 * i + 2) >> 2] |= B << (8 * ((3 * i + 2) & 3));
+        float fy;
+        switch (i & 3) {
+            case 0: fy = hjd_byte_biased<0>(yw[i >> 2]); break;
+            case 1: fy = hjd_byte_biased<1>(yw[i >> 2]); break;
+            case 2: fy = hjd_byte_biased<2>(yw[i >> 2]); break;
+            default: fy = hjd_byte_biased<3>(yw[i >> 2]); break;
+        }
+        fy = __fadd_rn(fy, -8388608.0f);
+        // loadjpg.cpp:873-879 with the argument swap of the call at 918 resolved
+        ch[3 * i]     = hjd_trunc_clamp_bits(__fadd_rn(fy, rr));
+        ch[3 * i + 1] = hjd_trunc_clamp_bits(__fsub_rn(__fsub_rn(fy, g1), g2));
+        ch[3 * i + 2] = hjd_trunc_clamp_bits(__fadd_rn(fy, bb));
+    }
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+        const uint32_t lo = __byte_perm(ch[4 * w], ch[4 * w + 1], 0x0040);
+        const uint32_t hi = __byte_perm(ch[4 * w + 2], ch[4 * w + 3], 0x0040);
+        out[w] = __byte_perm(lo, hi, 0x5410);
     }
 }
 
@@ -635,6 +665,131 @@ cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, ui
     for (int base = 0; base < n_images; base += 65535) {
         const int n = min(65535, n_images - base);
         hjd_k_color<<<dim3(gx, n), HJD_COLOR_THREADS, 0, st>>>(planes, imgs, rgb, base);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels 2+3 fused: dequant + IDCT -> shared-memory planes -> upsample + colour -> RGB
+// ------------------------------------------------------------------------------------------
+// One CTA = one strip of consecutive MCUs of one MCU row (loadjpg.cpp:1179-1180 couples DecodeMCU
+// and YCrCB_to_RGB24_Block8x8 per MCU in the same way).  Phase A: one thread per 8x8 block writes
+// its samples into shared-memory Y/Cb/Cr tiles (never to HBM).  Phase B: 16-pixel runs are colour
+// converted from the tiles into a shared RGB tile.  Phase C: the RGB tile is copied out with
+// linear 128-bit stores, each warp store covering 512 contiguous bytes of an image row.
+// HBM traffic per image: coefficients in (once), RGB out (once).
+
+__global__ void __launch_bounds__(HJD_FUSED_THREADS, 4)
+hjd_k_idct_color(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
+                 const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb, int img_base)
+{
+    extern __shared__ __align__(16) uint8_t s_fused[];
+    const HjdImageDesc* d = imgs + (blockIdx.y + img_base);
+    const uint32_t bpm = d->blocks_per_mcu;
+    if (bpm == 0) return;                                      // image skipped by the parser
+    const uint32_t hf = d->hf, vf = d->vf;
+    const uint32_t S = HJD_FUSED_THREADS / bpm;                // MCUs per strip
+    const uint32_t strips_x = (d->mcus_x + S - 1) / S;
+    if (blockIdx.x >= strips_x * d->mcus_y) return;            // uniform per CTA
+    const uint32_t my = blockIdx.x / strips_x, sx = blockIdx.x - my * strips_x;
+    const uint32_t mcu0 = sx * S, nm = min(S, d->mcus_x - mcu0);
+    const uint32_t ny = d->ncomp == 3 ? hf * vf : 1u;
+    const bool gray = d->ncomp == 1;
+
+    const uint32_t yw = S * 8 * hf, yh = 8 * vf, cw = S * 8;   // tile geometry (pitches)
+    float* s_cos = (float*)s_fused;
+    uint8_t* tY = s_fused + 256;
+    uint8_t* tCb = tY + yw * yh;
+    uint8_t* tCr = tCb + (gray ? 0u : cw * 8u);
+    uint8_t* tRGB = tCr + (gray ? 0u : cw * 8u);
+    const uint32_t rgb_pitch = yw * 3;
+
+    const uint32_t t = threadIdx.x;
+    if (t < 64) s_cos[t] = c_cos[t];
+    __syncthreads();
+
+    // ---- phase A: IDCT, one thread per block -------------------------------------------------
+    if (t < nm * bpm) {
+        const uint32_t mcu = t / bpm, bi = t - mcu * bpm;
+        int comp; uint8_t* dst; uint32_t pitch;
+        if (bi < ny) { comp = 0; pitch = yw; dst = tY + (bi / hf) * 8 * yw + (mcu * hf + bi % hf) * 8; }
+        else { comp = (bi == ny) ? 1 : 2; pitch = cw; dst = (comp == 1 ? tCb : tCr) + mcu * 8; }
+        const uint64_t blk = d->block_base + ((uint64_t)my * d->mcus_x + mcu0) * bpm + t;
+        hjd_idct_block((const uint4*)(coef + blk * 64), (const uint4*)(qsets[d->quant_set].q[comp]), s_cos, dst, pitch);
+    }
+    __syncthreads();
+
+    // ---- phase B: upsample + colour, 16 pixels per unit ------------------------------------------
+    const uint32_t x0 = mcu0 * 8 * hf, y0 = my * 8 * vf;
+    const uint32_t pw = min(nm * 8 * hf, d->width - x0);       // valid pixels of this strip (loadjpg.cpp:907-908)
+    const uint32_t ph = min(yh, d->height - y0);
+    const uint32_t segs = (pw + 15) >> 4;
+    const int hs = (int)hf - 1, vs = (int)vf - 1;
+    for (uint32_t u = t; u < segs * ph; u += HJD_FUSED_THREADS) {
+        const uint32_t row = u / segs, seg = u - row * segs;
+        const uint4 yv = *(const uint4*)(tY + row * yw + seg * 16);
+        const uint32_t yw4[4] = {yv.x, yv.y, yv.z, yv.w};
+        uint32_t cbw[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+        uint32_t crw[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+        if (!gray) {
+            const uint32_t coff = (row >> vs) * cw + ((seg * 16) >> hs);
+            const uint2 b0 = *(const uint2*)(tCb + coff), r0 = *(const uint2*)(tCr + coff);
+            cbw[0] = b0.x; cbw[1] = b0.y; crw[0] = r0.x; crw[1] = r0.y;
+            if (hs == 0) {
+                const uint2 b1 = *(const uint2*)(tCb + coff + 8), r1 = *(const uint2*)(tCr + coff + 8);
+                cbw[2] = b1.x; cbw[3] = b1.y; crw[2] = r1.x; crw[3] = r1.y;
+            }
+        }
+        uint32_t out[12];
+        if (hs) hjd_color_16<1>(yw4, cbw, crw, out); else hjd_color_16<0>(yw4, cbw, crw, out);
+        uint4* o = (uint4*)(tRGB + row * rgb_pitch + seg * 48);
+        o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        o[2] = make_uint4(out[8], out[9], out[10], out[11]);
+    }
+    __syncthreads();
+
+    // ---- phase C: linear copy-out (loadjpg.cpp:921-925 layout) ------------------------------------
+    const uint32_t row_bytes = pw * 3;
+    const uint64_t img_pitch = (uint64_t)d->width * 3;
+    uint8_t* g0 = rgb + d->rgb_off + (uint64_t)y0 * img_pitch + (uint64_t)x0 * 3;
+    if (((row_bytes | (uint32_t)img_pitch | (x0 * 3)) & 15u) == 0 && (d->rgb_off & 15u) == 0) {
+        const uint32_t chunks = row_bytes >> 4;
+        for (uint32_t i = t; i < chunks * ph; i += HJD_FUSED_THREADS) {
+            const uint32_t row = i / chunks, c = i - row * chunks;
+            *(uint4*)(g0 + row * img_pitch + c * 16) = *(const uint4*)(tRGB + row * rgb_pitch + c * 16);
+        }
+    } else {
+        for (uint32_t i = t; i < row_bytes * ph; i += HJD_FUSED_THREADS) {
+            const uint32_t row = i / row_bytes, c = i - row * row_bytes;
+            g0[row * img_pitch + c] = tRGB[row * rgb_pitch + c];
+        }
+    }
+}
+
+size_t hjd_fused_smem_bytes(int ncomp, int hf, int vf)
+{
+    // cos table + Y tile + Cb/Cr tiles + RGB tile for a strip of S = floor(threads / blocks_per_mcu) MCUs
+    const size_t bpm = ncomp == 3 ? (size_t)hf * vf + 2 : 1;
+    const size_t S = HJD_FUSED_THREADS / bpm;
+    const size_t ypix = S * 64 * (ncomp == 3 ? (size_t)hf * vf : 1);
+    return 256 + ypix + (ncomp == 3 ? 2 * S * 64 : 0) + 3 * ypix;
+}
+
+cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
+                                  uint8_t* rgb, int n_images, uint32_t max_strips, size_t smem, cudaStream_t st)
+{
+    if (n_images <= 0 || max_strips == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(hjd_k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)hjd_fused_smem_bytes(1, 1, 1));   // grayscale is the largest tile
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    for (int base = 0; base < n_images; base += 65535) {
+        const int n = min(65535, n_images - base);
+        hjd_k_idct_color<<<dim3(max_strips, n), HJD_FUSED_THREADS, smem, st>>>(coef, imgs, qsets, rgb, base);
     }
     return cudaGetLastError();
 }

@@ -59,8 +59,9 @@ extern "C" {
 #define HJD_IMG_WARN_RESTART       8   /* RSTn count differs from ceil(MCUs/Ri)-1 */
 
 /* hjd_batch_create flags */
-#define HJD_FLAG_KEEP_PLANES   1u   /* run the unfused IDCT -> planes -> colour kernels (parity taps) */
+#define HJD_FLAG_KEEP_PLANES   1u   /* (default behaviour; kept for compatibility) Y/Cb/Cr planes stay in HBM */
 #define HJD_FLAG_HOST_SCAN     2u   /* find RSTn markers on the host instead of the GPU pre-pass */
+#define HJD_FLAG_FUSED         4u   /* kernels 2+3 fused: planes live in shared memory only (no plane tap) */
 
 typedef struct hjd_batch hjd_batch;
 
@@ -126,6 +127,13 @@ int  hjd_batch_upload_arena(hjd_batch* b, const uint8_t* arena, const int64_t* o
  * marker scan -> entropy decode -> dequant/IDCT -> upsample/colour.  Results stay in HBM. */
 int  hjd_batch_decode(hjd_batch* b);
 int  hjd_batch_sync(hjd_batch* b);
+/* hjd_batch_decode_host splits large batches into up to 8 chunks on 3 streams so that the H2D copy,
+ * the kernels and the D2H copy of different chunks overlap (default, on = 1).  HBM-resident decodes
+ * (hjd_batch_upload* + hjd_batch_decode) run on one stream, in order: measured on B200, overlapping
+ * their kernels gains nothing (all are issue-bound) and per-stage timings need the serial order.
+ * on = 0: never chunk; on > 1: chunk both paths with this target number of 8x8 blocks per chunk
+ * (testing / tuning).  Takes effect at the next upload. */
+int  hjd_batch_set_overlap(hjd_batch* b, int on);
 
 int  hjd_batch_num_images(const hjd_batch* b);
 int  hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* out);

@@ -30,9 +30,12 @@ def golden_files():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.jpg")))
 
 
-@pytest.fixture(scope="module")
-def dec(hjd):
-    d = hjd.BatchDecoder(0, hjd.FLAG_KEEP_PLANES)
+@pytest.fixture(scope="module", params=["fused", "planes"])
+def dec(hjd, request):
+    """planes: the default product path (kernels 2 and 3, Y/Cb/Cr planes in HBM = parity tap);
+    fused: HJD_FLAG_FUSED, kernels 2+3 fused with the planes in shared memory only."""
+    d = hjd.BatchDecoder(0, hjd.FLAG_FUSED if request.param == "fused" else 0)
+    d.keeps_planes = request.param == "planes"
     yield d
     d.close()
 
@@ -43,12 +46,13 @@ def compare_image(dec, i, oracle, all_coef, slab, name):
     assert coef.shape == oracle["coef"].shape, name
     bad_blocks = int((coef != oracle["coef"]).any(axis=1).sum())
     assert bad_blocks == 0, f"{name}: {bad_blocks} of {coef.shape[0]} coefficient blocks differ"
-    planes = dec.planes(i, slab)
-    for pname, a, b in zip("Y Cb Cr".split(), planes, oracle["planes"]):
-        if a is None:
-            continue
-        diff = int((a != b).sum())
-        assert diff == 0, f"{name}: plane {pname}: {diff} of {a.size} samples differ"
+    if slab is not None:
+        planes = dec.planes(i, slab)
+        for pname, a, b in zip("Y Cb Cr".split(), planes, oracle["planes"]):
+            if a is None:
+                continue
+            diff = int((a != b).sum())
+            assert diff == 0, f"{name}: plane {pname}: {diff} of {a.size} samples differ"
     rgb = dec.rgb(i)
     assert rgb.shape == oracle["rgb"].shape
     d = np.abs(rgb.astype(np.int16) - oracle["rgb"].astype(np.int16))
@@ -66,7 +70,7 @@ def test_golden_batch(dec, port):
     dec.decode()
     st = dec.status()
     assert (st == 0).all(), dict(zip(names, st.tolist()))
-    all_coef, slab = dec.coefficients(), dec.plane_slab()
+    all_coef, slab = dec.coefficients(), (dec.plane_slab() if dec.keeps_planes else None)
     for i, (n, f) in enumerate(zip(names, files)):
         g = GOLDEN[n]
         coef = dec.image_coefficients(i, all_coef)
@@ -88,7 +92,7 @@ def test_lenna_config1(hjd, dec, port, tmp_path):
     coef = dec.coefficients()
     assert sha(coef) == "46c20f75d72e2525a21b3a0559c4fe098143cd9aed7468ac8c5ca78ec653a418"
     o = port.decode(jpg)
-    compare_image(dec, 0, o, coef, dec.plane_slab(), "lenna")
+    compare_image(dec, 0, o, coef, dec.plane_slab() if dec.keeps_planes else None, "lenna")
     assert sha(dec.rgb(0)) == GOLDEN["__lenna__"]["rgb_sha256"]
     # the drop-in entry points
     out = str(tmp_path / "out.bmp")
@@ -118,7 +122,7 @@ def test_random_images(dec, port, seed):
     dec.upload(files)
     dec.decode()
     assert (dec.status() == 0).all()
-    all_coef, slab = dec.coefficients(), dec.plane_slab()
+    all_coef, slab = dec.coefficients(), (dec.plane_slab() if dec.keeps_planes else None)
     for i, (n, f) in enumerate(zip(names, files)):
         compare_image(dec, i, port.decode(f), all_coef, slab, n)
 
@@ -132,7 +136,7 @@ def test_config2_1080p_restart8(dec, port):
     assert (dec.status() == 0).all()
     inf = dec.info(0)
     assert (inf.mcus_x, inf.mcus_y, inf.n_intervals, inf.n_blocks) == (120, 68, 1020, 48960)
-    all_coef, slab = dec.coefficients(), dec.plane_slab()
+    all_coef, slab = dec.coefficients(), (dec.plane_slab() if dec.keeps_planes else None)
     for i, f in enumerate(files):
         compare_image(dec, i, port.decode(f), all_coef, slab, f"c2_{i}")
 
@@ -218,3 +222,31 @@ def test_decode_host_end_to_end(hjd, port):
         n = o["rgb"].size
         assert np.array_equal(out[int(off):int(off) + n].reshape(o["rgb"].shape), o["rgb"])
     arena.close()
+
+
+def test_chunked_overlapped_execution_matches_serial(hjd, port):
+    """Multi-stream chunked execution (forced with a tiny blocks-per-chunk target) gives the same
+    bytes as the serial path, resident and host-buffer variants."""
+    files = list(cases.small_cases().values())
+    with hjd.BatchDecoder(0) as d:
+        d.set_overlap(0)
+        d.upload(files)
+        d.decode()
+        want = [d.rgb(i).copy() for i in range(len(files))]
+        want_coef = d.coefficients().copy()
+        d.set_overlap(40)                      # ~40 blocks per chunk -> 8 chunks on 3 streams
+        d.upload(files)
+        d.decode()
+        assert (d.status() == 0).all()
+        assert np.array_equal(d.coefficients(), want_coef)
+        for i in range(len(files)):
+            assert np.array_equal(d.rgb(i), want[i])
+        arena = hjd.PinnedArena(files)
+        need = hjd.rgb_slab_bytes(arena)
+        out = np.zeros(need, dtype=np.uint8)
+        offs, st = d.decode_host(arena, out.ctypes.data, need)
+        assert (st == 0).all()
+        for i, off in enumerate(offs):
+            n = want[i].size
+            assert np.array_equal(out[int(off):int(off) + n].reshape(want[i].shape), want[i])
+        arena.close()
