@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = ["ConvertJpgFile", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED", "FLAG_NO_SELFSYNC"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhjd.so")
@@ -34,6 +34,7 @@ INCLUDE_PATH = os.path.join(os.path.dirname(_HERE), "include", "hjd.h")
 FLAG_KEEP_PLANES = 1
 FLAG_HOST_SCAN = 2
 FLAG_FUSED = 4
+FLAG_NO_SELFSYNC = 8
 
 IMG_WARN_BAD_CODE, IMG_WARN_COEF_RANGE, IMG_WARN_OVERRUN, IMG_WARN_RESTART = 1, 2, 4, 8
 
@@ -84,6 +85,7 @@ _SIGS = {
     "hjd_batch_sync": (c_int, [c_void_p]),
     "hjd_batch_set_overlap": (c_int, [c_void_p, c_int]),
     "hjd_batch_num_images": (c_int, [c_void_p]),
+    "hjd_batch_selfsync_rounds": (c_int, [c_void_p]),
     "hjd_batch_get_info": (c_int, [c_void_p, c_int, POINTER(ImageInfo)]),
     "hjd_batch_get_status": (c_int, [c_void_p, c_void_p]),
     "hjd_batch_get_timings": (c_int, [c_void_p, POINTER(Timings)]),
@@ -293,6 +295,10 @@ class BatchDecoder:
         return {k: getattr(t, k) for k, _ in Timings._fields_}
 
     # -- results -----------------------------------------------------------------------------
+    @property
+    def selfsync_rounds(self) -> int:
+        return lib().hjd_batch_selfsync_rounds(self._h)
+
     @property
     def num_images(self) -> int:
         return lib().hjd_batch_num_images(self._h)

@@ -7,6 +7,7 @@
 #include "hjd_types.h"
 #include "jpeg_parse.h"
 #include "kernels.cuh"
+#include "selfsync.cuh"
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -112,6 +113,11 @@ struct hjd_batch {
     std::vector<HjdQuantSet> qsets;
     std::vector<HjdEntropyWork> work;
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
+    std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
+    std::vector<HjdSsWork> sswork;
+    uint32_t ss_subs = 0, ss_chunks = 0, ss_mcus = 0;
+    uint64_t ss_dst_bytes = 0;
+    int ss_rounds = 0;                          // sync rounds of the last decode
     std::vector<uint8_t> host_restart_warn;     // HJD_FLAG_HOST_SCAN only
     std::unordered_map<uint64_t, uint32_t> tset_of, qset_of;
     uint64_t total_blocks = 0, rgb_bytes = 0, plane_bytes = 0, scan_bytes = 0, pixels = 0, arena_bytes = 0;
@@ -122,7 +128,8 @@ struct hjd_batch {
     int launches = 0;
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_istart, d_coef, d_planes, d_rgb, d_status;
-    PinBuf h_meta;
+    DevBuf d_ss, d_sswork, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssE1, d_ssX, d_ssnb, d_dcsums, d_flag;
+    PinBuf h_meta, h_flag;
 };
 
 static void compute_idct_constants(float cos_tab[64], float* cc0, float* cc00)
@@ -190,7 +197,10 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release();
     b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
-    b->h_meta.release();
+    b->d_ss.release(); b->d_sswork.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
+    b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssE1.release(); b->d_ssX.release(); b->d_ssnb.release();
+    b->d_dcsums.release(); b->d_flag.release();
+    b->h_meta.release(); b->h_flag.release();
     for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     for (int i = 0; i < 4; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
     for (int i = 0; i < HJD_NSTREAMS; i++) { if (b->aux[i]) { cudaStreamSynchronize(b->aux[i]); cudaStreamDestroy(b->aux[i]); } if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]); }
@@ -224,6 +234,9 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear();
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
+    b->ss.clear(); b->sswork.clear();
+    b->ss_subs = b->ss_chunks = b->ss_mcus = 0;
+    b->ss_dst_bytes = 0;
     b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
     b->total_intervals = b->max_blocks = b->max_w = b->max_h = b->max_strips = 0;
     b->fused_smem = 0;
@@ -275,6 +288,28 @@ static int upload_common(hjd_batch* b, bool chunked)
         d.n_intervals = ps.restart_interval ? (d.n_mcus + ps.restart_interval - 1) / ps.restart_interval : 1;
         d.scan_len = (uint32_t)ps.scan_len;
         d.scan_off = files[i].dev_off + ps.scan_off;
+        if (!(b->flags & HJD_FLAG_NO_SELFSYNC) && ps.restart_interval == 0 && ps.scan_len >= HJD_SS_MIN_BYTES) {
+            // restart-free scan: kernel 1b (speculative self-synchronising decode) instead of one thread
+            HjdSsImage si;
+            memset(&si, 0, sizeof si);
+            si.img = (uint32_t)i;
+            si.sub_base = b->ss_subs;
+            si.n_subs = (uint32_t)((ps.scan_len + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES);
+            si.lead = (uint32_t)(d.scan_off & 15);
+            si.chunk_base = b->ss_chunks;
+            si.n_chunks = (uint32_t)((ps.scan_len + si.lead + 15) / 16);
+            si.mcu_base = b->ss_mcus;
+            si.dst_off = b->ss_dst_bytes;
+            d.n_intervals = 0;
+            d.sub_base = si.sub_base;
+            d.n_subs = si.n_subs;
+            for (uint32_t f = 0; f < si.n_subs; f += HJD_SS_THREADS) b->sswork.push_back(HjdSsWork{(uint32_t)b->ss.size(), f});
+            b->ss.push_back(si);
+            b->ss_subs += si.n_subs;
+            b->ss_chunks += si.n_chunks;
+            b->ss_mcus += d.n_mcus;
+            b->ss_dst_bytes += align_up(ps.scan_len + HJD_SS_SLACK, 256);
+        }
         d.table_set = tset; d.quant_set = qset;
         d.n_blocks = (uint64_t)d.n_mcus * d.blocks_per_mcu;
         d.y_pitch = d.mcus_x * 8 * ps.hf;
@@ -301,7 +336,7 @@ static int upload_common(hjd_batch* b, bool chunked)
             if (sm > b->fused_smem) b->fused_smem = sm;
         }
 
-        if (b->flags & HJD_FLAG_HOST_SCAN) {
+        if ((b->flags & HJD_FLAG_HOST_SCAN) && d.n_intervals) {
             const size_t at = b->host_istart.size();
             b->host_istart.resize(at + d.n_intervals, (uint32_t)ps.scan_len);
             const uint32_t found = hjd_host_find_intervals(files[i].ptr + ps.scan_off, ps.scan_len,
@@ -385,6 +420,24 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
     if (!(b->flags & HJD_FLAG_FUSED)) CU(b->d_planes.ensure(b->plane_bytes + 256));
+    if (!b->ss.empty()) {
+        uint32_t scan_n = b->ss_chunks + 1;
+        if (b->ss_subs + 1 > scan_n) scan_n = b->ss_subs + 1;
+        if (3 * b->ss_mcus + 1 > scan_n) scan_n = 3 * b->ss_mcus + 1;
+        CU(b->d_ss.ensure(sizeof(HjdSsImage) * b->ss.size()));
+        CU(b->d_sswork.ensure(sizeof(HjdSsWork) * b->sswork.size()));
+        CU(b->d_destuff.ensure(b->ss_dst_bytes + 256));
+        CU(b->d_dlen.ensure(sizeof(uint32_t) * b->ss.size()));
+        CU(b->d_counts.ensure(sizeof(uint32_t) * ((size_t)b->ss_chunks + 2)));
+        CU(b->d_scantmp.ensure(sizeof(uint32_t) * ((size_t)scan_n / 2048 + 4)));
+        CU(b->d_ssE0.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
+        CU(b->d_ssE1.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
+        CU(b->d_ssX.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
+        CU(b->d_ssnb.ensure(sizeof(uint32_t) * ((size_t)b->ss_subs + 2)));
+        CU(b->d_dcsums.ensure(sizeof(uint32_t) * (3 * (size_t)b->ss_mcus + 2)));
+        CU(b->d_flag.ensure(sizeof(int) * 4));
+        CU(b->h_flag.ensure(sizeof(int) * 4));
+    }
 
     // metadata: one pinned staging block, then async copies
     const size_t sz_imgs = sizeof(HjdImageDesc) * (size_t)n;
@@ -392,8 +445,11 @@ static int upload_common(hjd_batch* b, bool chunked)
     const size_t sz_qs = sizeof(HjdQuantSet) * b->qsets.size();
     const size_t sz_wk = sizeof(HjdEntropyWork) * b->work.size();
     const size_t sz_is = sizeof(uint32_t) * b->host_istart.size();
+    const size_t sz_ss = sizeof(HjdSsImage) * b->ss.size();
+    const size_t sz_sw = sizeof(HjdSsWork) * b->sswork.size();
     size_t o_imgs = 0, o_ts = align_up(o_imgs + sz_imgs, 256), o_qs = align_up(o_ts + sz_ts, 256),
-           o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256), tot = o_is + sz_is;
+           o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256),
+           o_ss = align_up(o_is + sz_is, 256), o_sw = align_up(o_ss + sz_ss, 256), tot = o_sw + sz_sw;
     CU(b->h_meta.ensure(tot + 256));
     uint8_t* hm = (uint8_t*)b->h_meta.p;
     memcpy(hm + o_imgs, b->imgs.data(), sz_imgs);
@@ -401,11 +457,15 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_qs) memcpy(hm + o_qs, b->qsets.data(), sz_qs);
     if (sz_wk) memcpy(hm + o_wk, b->work.data(), sz_wk);
     if (sz_is) memcpy(hm + o_is, b->host_istart.data(), sz_is);
+    if (sz_ss) memcpy(hm + o_ss, b->ss.data(), sz_ss);
+    if (sz_sw) memcpy(hm + o_sw, b->sswork.data(), sz_sw);
     if (sz_imgs) CU(cudaMemcpyAsync(b->d_imgs.p, hm + o_imgs, sz_imgs, cudaMemcpyHostToDevice, b->stream));
     if (sz_ts) CU(cudaMemcpyAsync(b->d_tsets.p, hm + o_ts, sz_ts, cudaMemcpyHostToDevice, b->stream));
     if (sz_qs) CU(cudaMemcpyAsync(b->d_qsets.p, hm + o_qs, sz_qs, cudaMemcpyHostToDevice, b->stream));
     if (sz_wk) CU(cudaMemcpyAsync(b->d_work.p, hm + o_wk, sz_wk, cudaMemcpyHostToDevice, b->stream));
     if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
+    if (sz_ss) CU(cudaMemcpyAsync(b->d_ss.p, hm + o_ss, sz_ss, cudaMemcpyHostToDevice, b->stream));
+    if (sz_sw) CU(cudaMemcpyAsync(b->d_sswork.p, hm + o_sw, sz_sw, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemsetAsync(b->d_status.p, 0, sizeof(int32_t) * (size_t)(n + 1), b->stream));
 
     b->uploaded = true;
@@ -486,6 +546,59 @@ extern "C" int hjd_batch_set_overlap(hjd_batch* b, int on)
     return HJD_OK;
 }
 
+// Kernel 1b for all restart-free images of the batch (see selfsync.cu).  Runs on `st`; the
+// synchronisation rounds need the host to look at a flag, so this call blocks on the stream.
+static int run_selfsync(hjd_batch* b, cudaStream_t st)
+{
+    if (b->ss.empty()) return HJD_OK;
+    const uint8_t* arena = (const uint8_t*)b->d_arena.p;
+    const HjdImageDesc* imgs = (const HjdImageDesc*)b->d_imgs.p;
+    const HjdTableSet* tsets = (const HjdTableSet*)b->d_tsets.p;
+    const HjdSsImage* ss = (const HjdSsImage*)b->d_ss.p;
+    const HjdSsWork* work = (const HjdSsWork*)b->d_sswork.p;
+    const int n_ss = (int)b->ss.size(), n_work = (int)b->sswork.size();
+    uint8_t* dst = (uint8_t*)b->d_destuff.p;
+    uint32_t* dlen = (uint32_t*)b->d_dlen.p;
+    uint64_t* E[2] = {(uint64_t*)b->d_ssE0.p, (uint64_t*)b->d_ssE1.p};
+    uint64_t* X = (uint64_t*)b->d_ssX.p;
+    uint32_t* nb = (uint32_t*)b->d_ssnb.p;
+    int* flag = (int*)b->d_flag.p;
+    int* hflag = (int*)b->h_flag.p;
+
+    CU(hjd_launch_destuff(arena, imgs, ss, n_ss, b->ss_chunks, (uint32_t*)b->d_counts.p, (uint32_t*)b->d_scantmp.p,
+                          dst, dlen, st));
+    b->launches += 2 + (b->ss_chunks + 1 > 2048 ? 3 : 1);
+    // the coefficient regions are written sparsely: zero them first
+    for (const HjdSsImage& si : b->ss) {
+        const HjdImageDesc& d = b->imgs[si.img];
+        CU(cudaMemsetAsync((uint8_t*)b->d_coef.p + d.block_base * 128, 0, d.n_blocks * 128, st));
+    }
+    CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 1, E[1], E[0], X, nb, flag, st));
+    b->launches += 1;
+    const int max_rounds = (int)(b->ss_subs / 32) + 8;
+    int r = 1;
+    for (;; r++) {
+        if (r > max_rounds) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
+        CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 0, E[(r - 1) & 1], E[r & 1], X, nb, flag, st));
+        b->launches += 1;
+        CU(cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*hflag == 0) break;
+    }
+    b->ss_rounds = r + 1;
+    CU(hjd_scan_u32(nb, b->ss_subs + 1, (uint32_t*)b->d_scantmp.p, st));          // nb[] becomes first_block[]
+    CU(hjd_launch_ss_write(imgs, tsets, ss, work, n_work, dst, dlen, X, nb, (int16_t*)b->d_coef.p,
+                           (int32_t*)b->d_status.p, st));
+    uint32_t* sums = (uint32_t*)b->d_dcsums.p;
+    CU(hjd_launch_dc_sums(imgs, ss, n_ss, b->ss_mcus, (const int16_t*)b->d_coef.p, sums, st));
+    CU(hjd_scan_u32(sums, 3 * b->ss_mcus + 1, (uint32_t*)b->d_scantmp.p, st));
+    CU(hjd_launch_dc_apply(imgs, ss, n_ss, b->ss_mcus, sums, (int16_t*)b->d_coef.p, st));
+    b->launches += 3 + 2 * 3;
+    return HJD_OK;
+}
+
 // Kernels of one chunk on one stream.  ev != nullptr: record stage boundaries (serial mode only).
 static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent_t* ev)
 {
@@ -497,7 +610,11 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
         CU(hjd_launch_marker_scan(arena, imgs, (uint32_t*)b->d_istart.p, status, c.img0, n, st));
         b->launches += 1;
     }
-    if (ev) CU(cudaEventRecord(ev[1], st));
+    if (ev) {
+        CU(cudaEventRecord(ev[1], st));
+        int rc = run_selfsync(b, st);          // serial mode: counted in the entropy stage
+        if (rc) return rc;
+    }
     if (c.work1 > c.work0) {
         CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
                                       (const HjdEntropyWork*)b->d_work.p + c.work0, (int)(c.work1 - c.work0),
@@ -549,6 +666,15 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
         return HJD_OK;
     }
     for (int k = 1; k <= 3; k++) CU(cudaEventRecord(b->ev[k], main));     // no per-stage times when chunks overlap
+    if (!b->ss.empty()) {
+        // restart-free images need their bytes before the host-driven sync rounds: copy first
+        if (h2d) {
+            for (const Chunk& c : b->chunks) { int rc = copy_files(b, c, main); if (rc) return rc; }
+            h2d = false;
+        }
+        int rc = run_selfsync(b, main);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(b->ev_fork, main));
     for (int s = 0; s < HJD_NSTREAMS; s++) CU(cudaStreamWaitEvent(b->aux[s], b->ev_fork, 0));
     for (size_t k = 0; k < b->chunks.size(); k++) {
@@ -589,6 +715,7 @@ extern "C" int hjd_batch_sync(hjd_batch* b)
 }
 
 extern "C" int hjd_batch_num_images(const hjd_batch* b) { return b ? (int)b->imgs.size() : 0; }
+extern "C" int hjd_batch_selfsync_rounds(const hjd_batch* b) { return b ? b->ss_rounds : 0; }
 
 extern "C" int hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* o)
 {

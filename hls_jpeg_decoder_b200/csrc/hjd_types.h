@@ -66,6 +66,32 @@ struct HjdEntropyWork {
     uint32_t table_set;
 };
 
+// ---- self-synchronising path (restart-free scans) -------------------------------------------
+#define HJD_SS_SUB_BYTES   128          // sub-sequence length in (de-stuffed) bytes = 1024 bits
+#define HJD_SS_MIN_BYTES   1024         // restart-free scans shorter than this stay on the 1-thread path
+#define HJD_SS_SLACK       256          // zeroed bytes after every de-stuffed stream
+#define HJD_SS_THREADS     128
+
+// One per image decoded by the self-synchronising kernels; all index spaces below are global
+// over the batch (sub-sequences, 16-byte de-stuffing chunks, MCUs).
+struct HjdSsImage {
+    uint32_t img;          // image index in the batch
+    uint32_t sub_base;     // first sub-sequence
+    uint32_t n_subs;
+    uint32_t chunk_base;   // first 16-byte chunk of the (16-byte aligned) stuffed scan
+    uint32_t n_chunks;
+    uint32_t mcu_base;     // first MCU (DC prefix pass)
+    uint32_t lead;         // bytes between the aligned chunk origin and the first scan byte
+    uint32_t pad;
+    uint64_t dst_off;      // offset of the de-stuffed stream in the de-stuff buffer
+};
+
+// One CTA of the sync / write kernels: HJD_SS_THREADS consecutive sub-sequences of one image.
+struct HjdSsWork {
+    uint32_t ss;           // index into the HjdSsImage array
+    uint32_t first_sub;    // local index of the CTA's first sub-sequence
+};
+
 // Per-image status bits written by kernels (mirrors HJD_IMG_WARN_* in include/hjd.h).
 #define HJD_ST_BAD_CODE     1
 #define HJD_ST_COEF_RANGE   2

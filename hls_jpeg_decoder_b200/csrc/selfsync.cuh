@@ -1,0 +1,36 @@
+// csrc/selfsync.cuh -- kernel 1b: speculative self-synchronising Huffman decode of restart-free scans.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hjd_types.h"
+
+// Device-wide exclusive prefix sum of n uint32 (in place in `data`); tmp holds >= n/2048 + 2 words.
+cudaError_t hjd_scan_u32(uint32_t* data, uint32_t n, uint32_t* tmp, cudaStream_t st);
+
+// De-stuffing pre-pass (FillNBits' FF00 rule, loadjpg.cpp:475-478, applied once, in parallel):
+// counts[] (n_chunks_total + 1 words) is scratch; dst receives the compacted streams, dlen[ss] their lengths.
+cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss,
+                               uint32_t n_chunks_total, uint32_t* counts, uint32_t* scan_tmp,
+                               uint8_t* dst, uint32_t* dlen, cudaStream_t st);
+
+// One synchronisation round over all sub-sequences (first = 1: speculative decode from the fixed
+// bit offsets).  e_in/e_out: exit states (double buffered), x: entry state each exit was computed
+// from, nb: blocks completed inside each sub-sequence, changed: set to 1 when any exit state moved.
+cudaError_t hjd_launch_ss_round(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                                const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                                int first, const uint64_t* e_in, uint64_t* e_out, uint64_t* x, uint32_t* nb,
+                                int* changed, cudaStream_t st);
+
+// Final pass: decode every sub-sequence from its (now correct) entry state and write the
+// coefficients (DC as differences) at block offsets first_block[] (exclusive scan of nb[]).
+cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                                const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                                const uint64_t* x, const uint32_t* first_block, int16_t* coef, int32_t* status,
+                                cudaStream_t st);
+
+// DC pass: per-MCU, per-component sums of the DC differences -> sums[3][n_mcus_total].
+cudaError_t hjd_launch_dc_sums(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, uint32_t n_mcus_total,
+                               const int16_t* coef, uint32_t* sums, cudaStream_t st);
+// ... and, after an exclusive scan of sums[], the un-differenced DC values written back.
+cudaError_t hjd_launch_dc_apply(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, uint32_t n_mcus_total,
+                                const uint32_t* prefix, int16_t* coef, cudaStream_t st);

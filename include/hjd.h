@@ -62,6 +62,7 @@ extern "C" {
 #define HJD_FLAG_KEEP_PLANES   1u   /* (default behaviour; kept for compatibility) Y/Cb/Cr planes stay in HBM */
 #define HJD_FLAG_HOST_SCAN     2u   /* find RSTn markers on the host instead of the GPU pre-pass */
 #define HJD_FLAG_FUSED         4u   /* kernels 2+3 fused: planes live in shared memory only (no plane tap) */
+#define HJD_FLAG_NO_SELFSYNC   8u   /* restart-free scans: one thread per scan (kernel 1a) instead of kernel 1b */
 
 typedef struct hjd_batch hjd_batch;
 
@@ -135,6 +136,8 @@ int  hjd_batch_sync(hjd_batch* b);
  * (testing / tuning).  Takes effect at the next upload. */
 int  hjd_batch_set_overlap(hjd_batch* b, int on);
 
+/* Synchronisation rounds the self-synchronising kernel (restart-free scans) needed in the last decode. */
+int  hjd_batch_selfsync_rounds(const hjd_batch* b);
 int  hjd_batch_num_images(const hjd_batch* b);
 int  hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* out);
 int  hjd_batch_get_status(hjd_batch* b, int32_t* status /* n */);   /* syncs */

@@ -250,3 +250,45 @@ def test_chunked_overlapped_execution_matches_serial(hjd, port):
             n = want[i].size
             assert np.array_equal(out[int(off):int(off) + n].reshape(want[i].shape), want[i])
         arena.close()
+
+
+def test_selfsync_matches_single_thread_path(hjd, port):
+    """Restart-free scans: kernel 1b (speculative self-synchronising decode) against kernel 1a run
+    with one thread per scan (HJD_FLAG_NO_SELFSYNC) and against the oracle."""
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    files = [encode_jpeg(synth_rgb(320, 200, 41), 85, "4:4:4"),
+             encode_jpeg(synth_rgb(333, 217, 42), 60, "4:2:0"),
+             encode_jpeg(synth_rgb(256, 256, 43), 95, "4:2:2", optimize=True),
+             encode_jpeg(synth_rgb(200, 300, 44), 75, gray=True),
+             encode_jpeg(cases.noise_rgb(160, 160, 45), 100, "4:4:4"),
+             encode_jpeg(cases.flat_rgb(512, 512, 90), 85, "4:2:0"),
+             encode_jpeg(synth_rgb(300, 200, 46), 85, "4:2:0", restart_blocks=8)]     # one restart image in the mix
+    with hjd.BatchDecoder(0) as d1, hjd.BatchDecoder(0, hjd.FLAG_NO_SELFSYNC) as d2:
+        for d in (d1, d2):
+            d.upload(files)
+            d.decode()
+            assert (d.status() == 0).all(), d.status()
+        assert d1.selfsync_rounds >= 2 and d2.selfsync_rounds == 0
+        c1, c2 = d1.coefficients(), d2.coefficients()
+        assert np.array_equal(c1, c2)
+        for i, f in enumerate(files):
+            o = port.decode(f)
+            assert np.array_equal(d1.image_coefficients(i, c1), o["coef"]), i
+            assert np.array_equal(d1.rgb(i), o["rgb"]), i
+
+
+def test_selfsync_large_scan(hjd, port):
+    """Config 4 geometry scaled down: one 2048x2048 4:4:4 restart-free image (196,608 blocks),
+    coefficients bit-exact against the oracle's entropy stage, RGB against the full oracle."""
+    from tools.gen_jpegs import make_c4
+    jpg = make_c4(2048, seed=4)
+    with hjd.BatchDecoder(0) as d:
+        d.upload([jpg])
+        d.decode()
+        assert d.status()[0] == 0
+        inf = d.info(0)
+        assert (inf.restart_interval, inf.n_intervals, inf.n_blocks) == (0, 0, 196608)
+        o = port.decode(jpg)
+        assert np.array_equal(d.coefficients(), o["coef"])
+        assert np.array_equal(d.rgb(0), o["rgb"])
+        assert d.selfsync_rounds <= 6, d.selfsync_rounds
