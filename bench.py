@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-W, H = 1920, 1080
+W, H = 1920, 1080     # config 2 geometry (the CPU arm always decodes config-2 images)
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -35,7 +35,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=1024, help="images per GPU (config 2: 1024)")
+    ap.add_argument("--images", type=int, default=0, help="images per GPU (default: 1024 for c2, 1 for c4, 8192 for c5)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="BASELINE.json workload: c2 = 1080p 4:2:0 Ri=8 batch (headline), c4 = one 8192x8192 4:4:4 "
+                         "restart-free image, c5 = 256x256 gray/4:2:0 thumbnails")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank decodes its own batch; strong: one batch sharded over the ranks (config 3)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -57,15 +62,23 @@ def measured_peak():
 # ---------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------
-def load_images(n: int, rank: int, world: int) -> list[bytes]:
-    """Config-2 images i = 0..n-1 (seeded, tools/gen_jpegs.make_c2), cached on local disk so that
+WORKLOADS = {
+    "c2": dict(n=1024, w=1920, h=1080, desc="synthetic 1920x1080 4:2:0 baseline JPEGs, q85, restart interval 8 MCUs (BASELINE.json configs[1])"),
+    "c4": dict(n=1, w=8192, h=8192, desc="one synthetic 8192x8192 4:4:4 baseline JPEG, q85, no restart markers: self-synchronising path (BASELINE.json configs[3])"),
+    "c5": dict(n=8192, w=256, h=256, desc="synthetic 256x256 thumbnails, even = grayscale, odd = 4:2:0, q75, restart interval 8 MCUs (BASELINE.json configs[4], per-GPU share)"),
+}
+
+
+def load_images(n: int, rank: int, world: int, config: str = "c2", scaling: str = "weak") -> list[bytes]:
+    """Seeded images of one BASELINE.json workload (tools/gen_jpegs), cached on local disk so that
     the ranks of one run (and the reference arm) generate them only once."""
     from tools import gen_jpegs
-    cache = f"/tmp/hjd_bench_c2_{W}x{H}_{n}.bin"
+    wl = WORKLOADS[config]
+    cache = f"/tmp/hjd_bench_{config}_{wl['w']}x{wl['h']}_{n}.bin"
     idx = cache + ".idx"
     if not os.path.exists(idx):
         if rank == 0:
-            files = gen_jpegs.make_batch("c2", n)
+            files = [gen_jpegs.make_c4(wl["w"], 4 + i) for i in range(n)] if config == "c4" else gen_jpegs.make_batch(config, n)
             tmp = cache + f".tmp{os.getpid()}"
             with open(tmp, "wb") as fh:
                 for f in files:
@@ -86,7 +99,12 @@ def load_images(n: int, rank: int, world: int) -> list[bytes]:
     for s in sizes:
         files.append(blob[o:o + s])
         o += s
-    # every rank owns a different rotation of the same seeded set (weak scaling, independent shards)
+    if scaling == "strong":
+        # config 3: ONE batch cut into contiguous image ranges balanced by compressed bytes
+        from hls_jpeg_decoder_b200.sharding import shard_range
+        lo, hi = shard_range(sizes, rank, world)
+        return files[lo:hi]
+    # weak: every rank owns a different rotation of the same seeded set (independent shards)
     k = (rank * 131) % max(len(files), 1)
     return files[k:] + files[:k]
 
@@ -196,7 +214,7 @@ class CpuReference:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    files = load_images(args.images, 0, 1)
+    files = load_images(args.images or WORKLOADS["c2"]["n"], 0, 1)
     ref = CpuReference(files, per_core=1)
     for _ in range(args.warmup):
         ref.step()
@@ -238,7 +256,9 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    files = load_images(args.images, rank, world)
+    wl = WORKLOADS[args.config]
+    n_req = args.images or wl["n"]
+    files = load_images(n_req, rank, world, args.config, args.scaling)
     n = len(files)
     arena = hjd.PinnedArena(files)
     dec = hjd.BatchDecoder(local_rank)
@@ -282,10 +302,13 @@ def run_ours(args, rank, local_rank, world):
         launches = t["launches"]
 
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(pixels), float(scan_bytes), float(alg_bytes), float(n)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_max = float(t_ms.item())
-    value = world * pixels / 1e6 * args.steps / (ms_max / 1e3)
+    job_pixels, job_scan, job_alg, job_images = (float(v) for v in tot.tolist())
+    value = job_pixels / 1e6 * args.steps / (ms_max / 1e3)
 
     # end to end through the C ABI with host buffers (pinned in, pinned out), copies inside the timed region
     e2e = None
@@ -306,7 +329,7 @@ def run_ours(args, rank, local_rank, world):
         t_e = torch.tensor([te], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * pixels / 1e6 * args.e2e_steps / float(t_e.item()), 1), "unit": "MP/s",
+        e2e = {"value": round(job_pixels / 1e6 * args.e2e_steps / float(t_e.item()), 1), "unit": "MP/s",
                "h2d_bytes_per_step": int(arena.bytes), "d2h_bytes_per_step": int(need), "steps": args.e2e_steps}
         hjd.lib().hjd_host_free(out_ptr)
 
@@ -318,14 +341,14 @@ def run_ours(args, rank, local_rank, world):
         whole = alg_bytes / (ms_max / args.steps / 1e3) / 1e9
         line = {"metric": "decoded_MP_per_s", "value": round(value, 1), "unit": "MP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 4),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"batch of {n} synthetic {W}x{H} 4:2:0 baseline JPEGs per GPU, q85, restart "
-                                       f"interval 8 MCUs (BASELINE.json configs[1]); inputs resident in HBM",
-                           "images_per_gpu": n, "scan_bytes_per_image": scan_bytes // n,
-                           "l2_policy": "per-step working set (coefficient + plane + RGB slabs, >10 GB) far exceeds the 126 MB L2",
-                           "parallelism": f"{world} independent shards, no collective"},
-                "compressed_GB_per_s": round(world * scan_bytes * args.steps / (ms_max / 1e3) / 1e9, 2),
+                "config": {"workload": f"{int(job_images)} x {wl['desc']}; inputs resident in HBM",
+                           "images_per_gpu": n, "scan_bytes_per_image": scan_bytes // max(n, 1),
+                           "l2_policy": f"per-step working set (coefficient + plane + RGB slabs, {(dec.coef_bytes + 2 * dec.rgb_bytes) / 1e9:.2f} GB on rank 0) "
+                                        "against a 126 MB L2; every step rewrites all of it",
+                           "parallelism": f"{world} independent shards ({args.scaling} scaling), no collective"},
+                "compressed_GB_per_s": round(job_scan * args.steps / (ms_max / 1e3) / 1e9, 2),
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1),
                              "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
@@ -335,7 +358,7 @@ def run_ours(args, rank, local_rank, world):
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            ref = CpuReference(files, per_core=1)
+            ref = CpuReference(load_images(WORKLOADS["c2"]["n"], 0, 1) if args.config != "c2" else files, per_core=1)
             ref.step()
             t = ref.step()
             line["cpu_baseline"] = {"value": round(len(ref.sample) * W * H / 1e6 / t, 3), "unit": "MP/s",

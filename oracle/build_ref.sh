@@ -47,3 +47,13 @@ build_variant big 8192 8192 64000
 # ignored oracle/_ref/ so that GPU-box tests can read it without touching /root/reference.
 cp -f "$REF/data/Lenna.jpg" "$OUT/data/Lenna.jpg"
 echo "build_ref: done"
+
+# Drop-in demonstration at the HLS-top boundary: the reference's UNCHANGED src/main.cpp and
+# src/openjpg.cpp, linked against this repository's JpegDecodeHW (csrc/ref_shim_hw.cpp + libhjd.so)
+# instead of the reference's src/loadjpg.cpp.  tests/test_gpu_dropin.py runs it on the GPU box.
+LIB_DIR="$HERE/../hls_jpeg_decoder_b200"
+if [ -f "$LIB_DIR/libhjd.so" ]; then
+    $CXX -O2 -w -I"$REF/src" "$REF/src/main.cpp" "$REF/src/openjpg.cpp" "$LIB_DIR/csrc/ref_shim_hw.cpp" \
+        -L"$LIB_DIR" -lhjd -Wl,-rpath,'$ORIGIN/../../hls_jpeg_decoder_b200' -o "$OUT/ref_main_on_gpu"
+    echo "build_ref: built $OUT/ref_main_on_gpu (reference main.cpp + openjpg.cpp on the GPU decode core)"
+fi
