@@ -35,6 +35,9 @@ struct HjdTableSet {
 // Component 1 (Cb) already carries Cr's table: the reference dequantises Cb with Cr's (loadjpg.cpp:984).
 struct HjdQuantSet {
     uint16_t q[3][64];
+    // the same tables packed for DP2A: word i = q[2i] | q[2i+1] << 24 (bytes 1, 2 zero), so that
+    // dp2a_lo/hi(coefficient pair, word) = coef[2i]*q[2i] resp. coef[2i+1]*q[2i+1] with no unpacking
+    uint32_t qp[3][32];
 };
 
 struct HjdImageDesc {

@@ -213,6 +213,8 @@ void hjd_build_quant_set(const HjdParsed& p, HjdQuantSet* out)
         // loadjpg.cpp:984 dequantises Cb with Cr's table; identical whenever both name one table.
         int src = (p.ncomp == 3 && c == 1) ? 2 : c;
         for (int k = 0; k < 64; k++) out->q[c][k] = p.qt[p.tq[src]][k];
+        for (int k = 0; k < 32; k++)
+            out->qp[c][k] = (uint32_t)p.qt[p.tq[src]][2 * k] | ((uint32_t)p.qt[p.tq[src]][2 * k + 1] << 24);
     }
 }
 

@@ -386,7 +386,11 @@ __device__ __forceinline__ int hjd_finish_sample(float sum)
     return min(max(iv, 0), 255);               // Clamp, loadjpg.cpp:83-91
 }
 
-// Dequantise one block held as 8 x uint4 (zig-zag order) into bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)).
+// a = two signed 16-bit lanes, b = four unsigned bytes: lo -> a.lo*b0 + a.hi*b1, hi -> a.lo*b2 + a.hi*b3
+__device__ __forceinline__ int hjd_dp2a_lo_su(uint32_t a, uint32_t b) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
+__device__ __forceinline__ int hjd_dp2a_hi_su(uint32_t a, uint32_t b) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
+
+// q: HjdQuantSet::qp (byte-packed pairs).  Dequantise one block held as 8 x uint4 (zig-zag order) into bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)).
 // Returns A_ac = sum over AC terms of |bp| ; *a_dc = |bp[0]|.
 __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4 q[8], float bp[64], float* a_dc)
 {
@@ -396,9 +400,10 @@ __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4
     float a_ac = 0.f;
 #define HJD_DQ(P, N)                                                                           \
     {                                                                                          \
-        const int cv = (int)(short)((cw[(P) >> 1] >> (((P) & 1) * 16)) & 0xFFFFu);             \
-        const int qv = (int)((qw[(P) >> 1] >> (((P) & 1) * 16)) & 0xFFFFu);                    \
-        const float f = (float)(int)(short)(cv * qv);       /* loadjpg.cpp:150, product exact */ \
+        /* coef*q straight from the packed pair (loadjpg.cpp:150; the product is exact) */      \
+        const int prod = ((P) & 1) ? hjd_dp2a_hi_su(cw[(P) >> 1], qw[(P) >> 1])                \
+                                   : hjd_dp2a_lo_su(cw[(P) >> 1], qw[(P) >> 1]);               \
+        const float f = (float)(int)(short)prod;            /* stored to short */              \
         const float ccw = ((N) == 0) ? cc00 : ((((N) & 7) == 0 || ((N) >> 3) == 0) ? cc0 : 1.0f); \
         const float b = __fmul_rn(ccw, f);                  /* (C(u)*C(v)) * block[u][v] */    \
         bp[(N)] = b;                                                                           \
@@ -407,6 +412,14 @@ __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4
     HJD_ZZ_LIST(HJD_DQ)
 #undef HJD_DQ
     return a_ac;
+}
+
+// d = {sat_u8(a), sat_u8(b)} in the low half-word, c's low half-word in the high one: clamp + pack.
+__device__ __forceinline__ uint32_t hjd_pack_sat_u8(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 // Exact re-evaluation of sample (x, y) in the reference's order.  tx/ty: rows of the cos table.
@@ -453,25 +466,36 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
     // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples:
     // |h - rint(h)| <= win  <=  an integer (truncation boundary) lies within the error window of h;
     // everywhere else trunc(h) is provably the reference's value.
+    // With A < 1e5 neither short wrap of the reference (loadjpg.cpp:136-137) can trigger (|h| <= A/4), so
+    // the sample is sat_u8(trunc(h) + 128), and the clamp comes free with the byte packing
+    // (cvt.pack.sat.u8.s32).  Absurd blocks (A >= 1e5) take the exact path for every sample.
     uint32_t row_lo[8], row_hi[8];
 #pragma unroll
     for (int y = 0; y < 8; y++) { row_lo[y] = 0; row_hi[y] = 0; }
     uint32_t near_lo = 0, near_hi = 0;             // bit (8y + x)
 #pragma unroll
-    for (int x = 0; x < 8; x++)
+    for (int xq = 0; xq < 4; xq++) {
+        const int xp = xq ^ 1;                     // pairs (2,3) (0,1) (6,7) (4,5): high half-word first
 #pragma unroll
         for (int y = 0; y < 8; y++) {
-            float acc = r[x];                      // v = 0, cos[y][0] == 1
+            int iv[2];
 #pragma unroll
-            for (int v = 1; v < 8; v++) acc = fmaf(r[8 * v + x], c_cos[y * 8 + v], acc);
-            const float h = 0.25f * acc;
-            const float n = rintf(h);
-            const bool nearint = (fabsf(h - n) <= win) && (n != 0.f);   // (-1, 1) truncates to 0: no boundary at 0
-            const uint32_t pix = (uint32_t)hjd_finish_sample(acc);
-            if (x < 4) row_lo[y] |= pix << (8 * x); else row_hi[y] |= pix << (8 * (x - 4));
-            if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
-            else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + x); }
+            for (int e = 0; e < 2; e++) {
+                const int x = 2 * xp + e;
+                float acc = r[x];                  // v = 0, cos[y][0] == 1
+#pragma unroll
+                for (int v = 1; v < 8; v++) acc = fmaf(r[8 * v + x], c_cos[y * 8 + v], acc);
+                const float h = 0.25f * acc;
+                const bool nearint = fabsf(h - rintf(h)) <= win;
+                iv[e] = __float2int_rz(h) + 128;   // (int)(0.25*sum) + 128, loadjpg.cpp:123,137
+                if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
+                else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + x); }
+            }
+            if (xp < 2) row_lo[y] = hjd_pack_sat_u8(iv[1], iv[0], row_lo[y]);
+            else        row_hi[y] = hjd_pack_sat_u8(iv[1], iv[0], row_hi[y]);
         }
+    }
+    if (a_ac + a_dc >= 1.0e5f) { near_lo = 0xFFFFFFFFu; near_hi = 0xFFFFFFFFu; }
 
 #pragma unroll
     for (int y = 0; y < 8; y++) *(uint2*)(dst + (size_t)y * pitch) = make_uint2(row_lo[y], row_hi[y]);
@@ -510,7 +534,7 @@ hjd_k_idct_planes(const int16_t* __restrict__ coef, const HjdImageDesc* __restri
         comp = (bi == ny) ? 1 : 2; pitch = d->c_pitch; poff = comp == 1 ? d->cb_off : d->cr_off;
         bx = mx; by = my;
     }
-    hjd_idct_block((const uint4*)(coef + (d->block_base + b) * 64), (const uint4*)(qsets[d->quant_set].q[comp]),
+    hjd_idct_block((const uint4*)(coef + (d->block_base + b) * 64), (const uint4*)(qsets[d->quant_set].qp[comp]),
                    s_cos, planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8, pitch);
 }
 
@@ -704,7 +728,7 @@ hjd_k_idct_color(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
         if (bi < ny) { comp = 0; pitch = yw; dst = tY + (bi / hf) * 8 * yw + (mcu * hf + bi % hf) * 8; }
         else { comp = (bi == ny) ? 1 : 2; pitch = cw; dst = (comp == 1 ? tCb : tCr) + mcu * 8; }
         const uint64_t blk = d->block_base + ((uint64_t)my * d->mcus_x + mcu0) * bpm + t;
-        hjd_idct_block((const uint4*)(coef + blk * 64), (const uint4*)(qsets[d->quant_set].q[comp]), s_cos, dst, pitch);
+        hjd_idct_block((const uint4*)(coef + blk * 64), (const uint4*)(qsets[d->quant_set].qp[comp]), s_cos, dst, pitch);
     }
     __syncthreads();
 
