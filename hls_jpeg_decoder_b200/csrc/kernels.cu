@@ -19,12 +19,17 @@
 // constants
 // ------------------------------------------------------------------------------------------
 __constant__ float c_cos[64];     // c_cos[p*8+k] = cosf(((2p+1)*k*3.14f)/16)  (host libm, loadjpg.cpp:120)
+__constant__ float2 c_cos2[64];  // c_cos2[p*8+k] = (c_cos[p*8+k], c_cos[p*8+k]): FFMA2 operand for two rows at once
 __constant__ float c_cc0;         // C(0)*C(k>0) = 1/sqrtf(2)                    (loadjpg.cpp:96-102)
 __constant__ float c_cc00;        // C(0)*C(0) = fl(0.70710677^2) = 0.49999997
 
 cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00)
 {
     cudaError_t e = cudaMemcpyToSymbol(c_cos, cos_tab, 64 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    float2 dup[64];
+    for (int i = 0; i < 64; i++) dup[i] = make_float2(cos_tab[i], cos_tab[i]);
+    e = cudaMemcpyToSymbol(c_cos2, dup, sizeof dup);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_cc0, &cc0, sizeof(float));
     if (e != cudaSuccess) return e;
@@ -372,7 +377,8 @@ cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc*
 // next to an integer.  This kernel computes the separable form (16 FMA per sample) and proves,
 // per sample, that truncation cannot differ: with A = sum |C(u)C(v)*coef| the two evaluations
 // differ by at most (65+14) * 2^-24 * A (standard rounding-error bounds for a 64-term recursive
-// sum of doubly-rounded products, and for two 8-term FMA chains), i.e. < 20 * 2^-24 * A on the
+// sum of doubly-rounded products, and for two 8-term FMA chains; the packed even/odd split of the
+// second pass is within the same bound), i.e. < 20 * 2^-24 * A on the
 // 0.25*sum scale.  Samples closer than 24 * 2^-24 * A to a non-zero integer (well under 1 %) are
 // re-evaluated in the reference's exact order (u outer, v inner, products left to right, no FMA).
 // Blocks with only a DC term are exact in both forms (cos(0) = 1) and are never re-evaluated.
@@ -390,9 +396,10 @@ __device__ __forceinline__ int hjd_finish_sample(float sum)
 __device__ __forceinline__ int hjd_dp2a_lo_su(uint32_t a, uint32_t b) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
 __device__ __forceinline__ int hjd_dp2a_hi_su(uint32_t a, uint32_t b) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
 
-// q: HjdQuantSet::qp (byte-packed pairs).  Dequantise one block held as 8 x uint4 (zig-zag order) into bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)).
+// q: HjdQuantSet::qp (byte-packed pairs).  Dequantise one block held as 8 x uint4 (zig-zag order) into
+// bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)), stored as row pairs: bp2[(v>>1)*8+u] = (bp[8v+u], bp[8(v+1)+u]), v even.
 // Returns A_ac = sum over AC terms of |bp| ; *a_dc = |bp[0]|.
-__device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4 q[8], float bp[64], float* a_dc)
+__device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4 q[8], float2 bp2[32], float* a_dc)
 {
     const float cc0 = c_cc0, cc00 = c_cc00;
     const uint32_t* cw = (const uint32_t*)c;
@@ -406,7 +413,8 @@ __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4
         const float f = (float)(int)(short)prod;            /* stored to short */              \
         const float ccw = ((N) == 0) ? cc00 : ((((N) & 7) == 0 || ((N) >> 3) == 0) ? cc0 : 1.0f); \
         const float b = __fmul_rn(ccw, f);                  /* (C(u)*C(v)) * block[u][v] */    \
-        bp[(N)] = b;                                                                           \
+        if (((N) >> 3) & 1) bp2[((N) >> 4) * 8 + ((N) & 7)].y = b;                              \
+        else                bp2[((N) >> 4) * 8 + ((N) & 7)].x = b;                              \
         if ((N) == 0) *a_dc = fabsf(b); else a_ac += fabsf(b);                                 \
     }
     HJD_ZZ_LIST(HJD_DQ)
@@ -423,7 +431,7 @@ __device__ __forceinline__ uint32_t hjd_pack_sat_u8(int a, int b, uint32_t c)
 }
 
 // Exact re-evaluation of sample (x, y) in the reference's order.  tx/ty: rows of the cos table.
-__device__ __forceinline__ float hjd_exact_sum(const float bp[64], const float* tx, const float* ty)
+__device__ __forceinline__ float hjd_exact_sum(const float2 bp2[32], const float* tx, const float* ty)
 {
     float sum = 0.f;
 #pragma unroll
@@ -431,7 +439,7 @@ __device__ __forceinline__ float hjd_exact_sum(const float bp[64], const float* 
         const float cxu = tx[u];
 #pragma unroll
         for (int v = 0; v < 8; v++)
-            sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(bp[8 * v + u], cxu), ty[v]));
+            sum = __fadd_rn(sum, __fmul_rn(__fmul_rn((v & 1) ? bp2[(v >> 1) * 8 + u].y : bp2[(v >> 1) * 8 + u].x, cxu), ty[v]));
     }
     return sum;
 }
@@ -446,23 +454,26 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
 #pragma unroll
     for (int i = 0; i < 8; i++) { c[i] = cp[i]; q[i] = __ldg(qp + i); }
 
-    float bp[64];
+    float2 bp2[32];
     float a_dc;
-    const float a_ac = hjd_dequant_block(c, q, bp, &a_dc);
+    const float a_ac = hjd_dequant_block(c, q, bp2, &a_dc);
     // re-evaluation window on the 0.25*sum scale: 24 * 2^-24 * A; DC-only blocks are exact (no window)
     const float win = (a_ac == 0.f) ? -1.f : (a_ac + a_dc) * 1.430511474609375e-06f;
 
-    // pass 1 (horizontal frequency u -> position x): r[8v+x] = sum_u bp[8v+u] * cos[x][u]
-    float r[64];
+    // Packed FP32x2 FMAs (Blackwell FFMA2) halve the issue slots of this issue-bound kernel.
+    // pass 1 (horizontal frequency u -> position x), two coefficient rows per instruction:
+    //   r2[vp*8+x] = (r[2vp][x], r[2vp+1][x]),  r[v][x] = sum_u bp[8v+u] * cos[x][u]
+    float2 r2[32];
 #pragma unroll
-    for (int v = 0; v < 8; v++)
+    for (int vp = 0; vp < 4; vp++)
 #pragma unroll
         for (int x = 0; x < 8; x++) {
-            float acc = bp[8 * v];                 // cos[x][0] == 1
+            float2 acc = bp2[vp * 8];              // cos[x][0] == 1
 #pragma unroll
-            for (int u = 1; u < 8; u++) acc = fmaf(bp[8 * v + u], c_cos[x * 8 + u], acc);
-            r[8 * v + x] = acc;
+            for (int u = 1; u < 8; u++) acc = __ffma2_rn(bp2[vp * 8 + u], c_cos2[x * 8 + u], acc);
+            r2[vp * 8 + x] = acc;
         }
+    const float2* cosp = (const float2*)c_cos;     // cosp[y*4+vp] = (cos[y][2vp], cos[y][2vp+1])
     // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples:
     // |h - rint(h)| <= win  <=  an integer (truncation boundary) lies within the error window of h;
     // everywhere else trunc(h) is provably the reference's value.
@@ -482,10 +493,11 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int x = 2 * xp + e;
-                float acc = r[x];                  // v = 0, cos[y][0] == 1
+                // pass 2: even and odd vertical frequencies accumulate in the two halves
+                float2 a2 = __fmul2_rn(r2[x], cosp[y * 4]);          // (r[0][x] * 1, r[1][x] * cos[y][1])
 #pragma unroll
-                for (int v = 1; v < 8; v++) acc = fmaf(r[8 * v + x], c_cos[y * 8 + v], acc);
-                const float h = 0.25f * acc;
+                for (int vp = 1; vp < 4; vp++) a2 = __ffma2_rn(r2[vp * 8 + x], cosp[y * 4 + vp], a2);
+                const float h = 0.25f * (a2.x + a2.y);
                 const bool nearint = fabsf(h - rintf(h)) <= win;
                 iv[e] = __float2int_rz(h) + 128;   // (int)(0.25*sum) + 128, loadjpg.cpp:123,137
                 if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
@@ -506,12 +518,12 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
         if (near_lo) { pos = __ffs(near_lo) - 1; near_lo &= near_lo - 1; }
         else         { pos = 32 + __ffs(near_hi) - 1; near_hi &= near_hi - 1; }
         const int y = pos >> 3, x = pos & 7;
-        const float sum = hjd_exact_sum(bp, s_cos + x * 8, s_cos + y * 8);
+        const float sum = hjd_exact_sum(bp2, s_cos + x * 8, s_cos + y * 8);
         dst[(size_t)y * pitch + x] = (uint8_t)hjd_finish_sample(sum);
     }
 }
 
-__global__ void __launch_bounds__(HJD_IDCT_THREADS)
+__global__ void __launch_bounds__(HJD_IDCT_THREADS, 4)
 hjd_k_idct_planes(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
                   const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ planes, int img_base)
 {
@@ -559,19 +571,14 @@ cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs
 // (loadjpg.cpp:873-879 with the swapped argument names of the call at 918 resolved).
 // Chroma is replicated, nearest neighbour (loadjpg.cpp:911-912).
 
-// No integer<->float conversion instructions (a quarter-rate-or-worse pipe that bounded the first
-// version of this kernel): a byte b becomes the float 2^23 + b by dropping it into the mantissa of
-// 0x4B000000 (PRMT), and trunc+clamp of a result c in [0, 255] is the low mantissa byte of
-// c + 2^23 rounded DOWN.  Clamping before flooring equals the reference's truncate-then-clamp.
+// The kernel is issue-bound before it is HBM-bound, so every pixel uses the fewest instructions
+// that still reproduce the reference bit for bit: byte -> float is one I2F with a byte selector,
+// truncation toward zero is one F2I.TRUNC, and the clamp to [0, 255] comes free with the byte
+// packing (cvt.pack.sat.u8.s32 packs and saturates two values per instruction).
 template <int SEL>
-__device__ __forceinline__ float hjd_byte_biased(uint32_t word)     // 2^23 + byte SEL of word, exactly
+__device__ __forceinline__ float hjd_byte_to_float(uint32_t word)
 {
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | SEL));
-}
-
-__device__ __forceinline__ uint32_t hjd_trunc_clamp_bits(float v)   // low byte = clamp((int)v, 0, 255)
-{
-    return __float_as_uint(__fadd_rd(fminf(fmaxf(v, 0.f), 255.f), 8388608.0f));
+    return (float)((word >> (8 * SEL)) & 255u);
 }
 
 // 16 pixels -> 48 packed bytes.  HS = log2(horizontal luma factor): chroma sample i >> HS.
@@ -579,21 +586,21 @@ template <int HS>
 __device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_t cbw[4], const uint32_t crw[4],
                                              uint32_t out[12])
 {
-    uint32_t ch[48];                      // per output byte: a word whose low byte is the value
+    int ch[48];                           // R, G, B of the 16 pixels before clamping
     float rr = 0.f, g1 = 0.f, g2 = 0.f, bb = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         if (HS == 0 || (i & 1) == 0) {
             const int ci = i >> HS;
-            float cb, cr;                 // (Cb - 128), (Cr - 128), exact
+            float cb, cr;
             switch (ci & 3) {
-                case 0: cb = hjd_byte_biased<0>(cbw[ci >> 2]); cr = hjd_byte_biased<0>(crw[ci >> 2]); break;
-                case 1: cb = hjd_byte_biased<1>(cbw[ci >> 2]); cr = hjd_byte_biased<1>(crw[ci >> 2]); break;
-                case 2: cb = hjd_byte_biased<2>(cbw[ci >> 2]); cr = hjd_byte_biased<2>(crw[ci >> 2]); break;
-                default: cb = hjd_byte_biased<3>(cbw[ci >> 2]); cr = hjd_byte_biased<3>(crw[ci >> 2]); break;
+                case 0: cb = hjd_byte_to_float<0>(cbw[ci >> 2]); cr = hjd_byte_to_float<0>(crw[ci >> 2]); break;
+                case 1: cb = hjd_byte_to_float<1>(cbw[ci >> 2]); cr = hjd_byte_to_float<1>(crw[ci >> 2]); break;
+                case 2: cb = hjd_byte_to_float<2>(cbw[ci >> 2]); cr = hjd_byte_to_float<2>(crw[ci >> 2]); break;
+                default: cb = hjd_byte_to_float<3>(cbw[ci >> 2]); cr = hjd_byte_to_float<3>(crw[ci >> 2]); break;
             }
-            cb = __fadd_rn(cb, -8388736.0f);
-            cr = __fadd_rn(cr, -8388736.0f);
+            cb = __fadd_rn(cb, -128.0f);  // (float)(Cb - 128), exact
+            cr = __fadd_rn(cr, -128.0f);
             rr = __fmul_rn(1.402f, cr);
             g1 = __fmul_rn(0.34414f, cb);
             g2 = __fmul_rn(0.71414f, cr);
@@ -601,23 +608,19 @@ __device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_
         }
         float fy;
         switch (i & 3) {
-            case 0: fy = hjd_byte_biased<0>(yw[i >> 2]); break;
-            case 1: fy = hjd_byte_biased<1>(yw[i >> 2]); break;
-            case 2: fy = hjd_byte_biased<2>(yw[i >> 2]); break;
-            default: fy = hjd_byte_biased<3>(yw[i >> 2]); break;
+            case 0: fy = hjd_byte_to_float<0>(yw[i >> 2]); break;
+            case 1: fy = hjd_byte_to_float<1>(yw[i >> 2]); break;
+            case 2: fy = hjd_byte_to_float<2>(yw[i >> 2]); break;
+            default: fy = hjd_byte_to_float<3>(yw[i >> 2]); break;
         }
-        fy = __fadd_rn(fy, -8388608.0f);
-        // loadjpg.cpp:873-879 with the argument swap of the call at 918 resolved
-        ch[3 * i]     = hjd_trunc_clamp_bits(__fadd_rn(fy, rr));
-        ch[3 * i + 1] = hjd_trunc_clamp_bits(__fsub_rn(__fsub_rn(fy, g1), g2));
-        ch[3 * i + 2] = hjd_trunc_clamp_bits(__fadd_rn(fy, bb));
+        // loadjpg.cpp:873-879 with the argument swap of the call at 918 resolved; (int) truncates
+        ch[3 * i]     = __float2int_rz(__fadd_rn(fy, rr));
+        ch[3 * i + 1] = __float2int_rz(__fsub_rn(__fsub_rn(fy, g1), g2));
+        ch[3 * i + 2] = __float2int_rz(__fadd_rn(fy, bb));
     }
 #pragma unroll
-    for (int w = 0; w < 12; w++) {
-        const uint32_t lo = __byte_perm(ch[4 * w], ch[4 * w + 1], 0x0040);
-        const uint32_t hi = __byte_perm(ch[4 * w + 2], ch[4 * w + 3], 0x0040);
-        out[w] = __byte_perm(lo, hi, 0x5410);
-    }
+    for (int w = 0; w < 12; w++)          // Clamp (loadjpg.cpp:83-91) + pack, two values per instruction
+        out[w] = hjd_pack_sat_u8(ch[4 * w + 1], ch[4 * w], hjd_pack_sat_u8(ch[4 * w + 3], ch[4 * w + 2], 0u));
 }
 
 __global__ void __launch_bounds__(HJD_COLOR_THREADS)
