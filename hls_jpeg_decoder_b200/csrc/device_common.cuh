@@ -4,13 +4,23 @@
 #include "hjd_types.h"
 
 // Byte offsets inside HjdHuffTable (lut, limit, delta, vals) for 32-bit shared-window addressing.
-#define HJD_TAB_LIMIT_OFF (HJD_LUT_SIZE * 2)
-#define HJD_TAB_DELTA_OFF (HJD_LUT_SIZE * 2 + 68)
-#define HJD_TAB_VALS_OFF  (HJD_LUT_SIZE * 2 + 136)
+#define HJD_TAB_LIMIT_OFF (HJD_LUT_SIZE * 4)
+#define HJD_TAB_DELTA_OFF (HJD_LUT_SIZE * 4 + 68)
+#define HJD_TAB_VALS_OFF  (HJD_LUT_SIZE * 4 + 136)
+
+// Meaning of a decoded symbol (see HjdHuffTable); also used by the host when it fills the LUT.
+__host__ __device__ __forceinline__ uint32_t hjd_sym_fields(uint32_t len, uint32_t sym, bool is_ac)
+{
+    const uint32_t size = sym & 15u, run = sym >> 4;
+    if (!is_ac) return HJD_SYM_FIELDS(len, size, 1, 1);                       // DC: loadjpg.cpp:616-667
+    if (size) return HJD_SYM_FIELDS(len, size, run + 1, 1);                   // loadjpg.cpp:778-806
+    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0), 0);   // EOB / ZRL / ignored, 771-775
+}
 
 __device__ __forceinline__ uint32_t hjd_lds_u16(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t hjd_lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t hjd_lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t hjd_lds_u16_sync(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void hjd_sts_u16_sync(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v) : "memory"); }
 __device__ __forceinline__ void hjd_sts_v2_sync(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ uint2 hjd_lds_v2_sync(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
@@ -20,3 +30,15 @@ __device__ __forceinline__ void hjd_sts_zero16_sync(uint32_t a) { asm volatile("
 __device__ __forceinline__ uint32_t hjd_shr(uint32_t v, uint32_t n) { uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ uint32_t hjd_shl(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 
+
+// Slow path of the symbol lookup: codes longer than the first-level table.  t = shared-window address
+// of the table, peek16 = next 16 bits.  Returns the symbol fields, or 0 when no code matches.
+__device__ __forceinline__ uint32_t hjd_long_code(uint32_t t, uint32_t peek16, bool is_ac)
+{
+    uint32_t len = HJD_LUT_BITS + 1;
+    while (len <= 16 && peek16 >= hjd_lds_u32(t + HJD_TAB_LIMIT_OFF + len * 4)) len++;
+    if (len > 16) return 0;
+    const uint32_t dl = hjd_lds_u32(t + HJD_TAB_DELTA_OFF + len * 4);
+    const uint32_t sym = hjd_lds_u8(t + HJD_TAB_VALS_OFF + (((peek16 >> (16 - len)) + dl) & 255u));
+    return hjd_sym_fields(len, sym, is_ac);
+}

@@ -156,7 +156,16 @@ int hjd_parse_jpeg(const uint8_t* buf, size_t size, HjdParsed* o)
     return o->status = HJD_IMG_OK;
 }
 
-bool hjd_build_huff_table(const HjdRawHuff& raw, HjdHuffTable* t)
+static uint32_t sym_fields(uint32_t len, uint32_t sym, bool is_ac)
+{
+    // keep in sync with hjd_sym_fields() in device_common.cuh (ProcessHuffmanBlock's run/size logic)
+    const uint32_t size = sym & 15u, run = sym >> 4;
+    if (!is_ac) return HJD_SYM_FIELDS(len, size, 1, 1);
+    if (size) return HJD_SYM_FIELDS(len, size, run + 1, 1);
+    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0), 0);
+}
+
+bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)
 {
     memset(t, 0, sizeof *t);
     memcpy(t->vals, raw.vals, 256);
@@ -171,7 +180,7 @@ bool hjd_build_huff_table(const HjdRawHuff& raw, HjdHuffTable* t)
         if (L <= HJD_LUT_BITS) {
             for (int k = 0; k < cnt; k++) {
                 uint32_t first = (code + (uint32_t)k) << (HJD_LUT_BITS - L);
-                uint16_t e = (uint16_t)((L << 8) | raw.vals[valptr + k]);
+                const uint32_t e = sym_fields((uint32_t)L, raw.vals[valptr + k], is_ac);
                 for (uint32_t j = 0; j < (1u << (HJD_LUT_BITS - L)); j++) t->lut[first + j] = e;
             }
         }
@@ -192,11 +201,11 @@ int hjd_build_table_set(const HjdParsed& p, HjdTableSet* out)
     int n = 0;
     for (int c = 0; c < p.ncomp; c++) {
         if (slot_dc[p.td[c]] < 0) {
-            if (!hjd_build_huff_table(p.dc[p.td[c]], &out->tab[n])) return HJD_IMG_ERR_BAD_TABLE;
+            if (!hjd_build_huff_table(p.dc[p.td[c]], false, &out->tab[n])) return HJD_IMG_ERR_BAD_TABLE;
             slot_dc[p.td[c]] = n++;
         }
         if (slot_ac[p.ta[c]] < 0) {
-            if (!hjd_build_huff_table(p.ac[p.ta[c]], &out->tab[n])) return HJD_IMG_ERR_BAD_TABLE;
+            if (!hjd_build_huff_table(p.ac[p.ta[c]], true, &out->tab[n])) return HJD_IMG_ERR_BAD_TABLE;
             slot_ac[p.ta[c]] = n++;
         }
         out->dc_of_comp[c] = (uint8_t)slot_dc[p.td[c]];

@@ -35,7 +35,7 @@ struct HjdParsed {
 int hjd_parse_jpeg(const uint8_t* buf, size_t size, HjdParsed* out);
 
 // Flattened lookup table from BITS/HUFFVAL.  Returns false if the code is over-subscribed.
-bool hjd_build_huff_table(const HjdRawHuff& raw, HjdHuffTable* out);
+bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* out);
 
 // Resolve the per-component tables of a parsed image into a device table set / quant set.
 // Returns HJD_IMG_OK or HJD_IMG_ERR_BAD_TABLE.

@@ -198,7 +198,7 @@ __device__ __forceinline__ void br_refill(BitReader& r)
     if (avail == 0 && r.nbits <= 32) { r.nbits += 32; r.padbits += 32; }     // past the interval: zero padding
 }
 
-__global__ void __launch_bounds__(HJD_ENT_THREADS)
+__global__ void __launch_bounds__(HJD_ENT_THREADS, 7)
 hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
                       const HjdTableSet* __restrict__ tsets, const uint32_t* __restrict__ interval_start,
                       const HjdEntropyWork* __restrict__ work, int16_t* __restrict__ coef,
@@ -282,39 +282,29 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                     }
                     const uint32_t is_ac = (uint32_t)min(k, 1);
                     const uint32_t t = t0 + is_ac * kTabBytes;
-                    const uint32_t e = hjd_lds_u16(t + ((br.hi >> (32 - HJD_LUT_BITS)) << 1));
-                    uint32_t len = e >> 8, sym = e & 255u;
-                    if (len == 0) {                      // code longer than the first-level table
-                        const uint32_t peek = br.hi >> 16;
-                        len = HJD_LUT_BITS + 1;
-                        while (len <= 16 && peek >= hjd_lds_u32(t + HJD_LUT_SIZE * 2 + len * 4)) len++;
-                        if (len > 16) { dead = true; flags |= HJD_ST_BAD_CODE; len = 0; sym = 0; }
-                        else {
-                            const uint32_t dl = hjd_lds_u32(t + HJD_LUT_SIZE * 2 + 68 + len * 4);
-                            sym = hjd_lds_u8(t + HJD_LUT_SIZE * 2 + 136 + (((peek >> (16 - len)) + dl) & 255u));
-                        }
+                    // the entry says what the symbol means: code length, value bits, zig-zag advance, store or not
+                    uint32_t e = hjd_lds_u32(t + ((br.hi >> (32 - HJD_LUT_BITS)) << 2));
+                    if ((e & 31u) == 0) {                // code longer than the first-level table
+                        e = hjd_long_code(t, br.hi >> 16, is_ac != 0);
+                        if (e == 0) { dead = true; flags |= HJD_ST_BAD_CODE; }
                     }
-                    const uint32_t size = sym & 15u;
-                    const uint32_t run = is_ac ? (sym >> 4) : 0u;
+                    const uint32_t len = e & 31u, size = (e >> 5) & 15u, kadv = (e >> 9) & 127u;
                     // value bits follow the code
                     const uint32_t after = __funnelshift_l(br.lo, br.hi, len);            // window << len, top word
                     const uint32_t v = hjd_shr(after, 32u - size);                         // 0 for size 0
                     // DetermineSign (loadjpg.cpp:396-409): leading 0 bit -> v - (2^size - 1)
                     const int neg = ~((int)after >> 31);                                   // all ones if negative
-                    int val = (int)v + (neg & (int)(hjd_shl(0xFFFFFFFFu, size) + 1u));
+                    const int val = (int)v + (neg & (int)(hjd_shl(0xFFFFFFFFu, size) + 1u));
                     const uint32_t used = len + size;                                      // <= 31
                     br.hi = __funnelshift_l(br.lo, br.hi, used);
                     br.lo <<= used;
                     br.nbits -= (int)used;
-                    if (!is_ac) { p0 = (int)(short)(p0 + val); val = p0; }                 // loadjpg.cpp:616-667
-                    const bool store = (!is_ac) || (size != 0u);
-                    const uint32_t kpos = (uint32_t)k + run;                               // loadjpg.cpp:778
-                    if (store) {
+                    const uint32_t kpos = (uint32_t)k + kadv - 1u;                         // loadjpg.cpp:778, 806
+                    if (e & 0x10000u) {                                                    // DC (as a difference) or AC value
                         if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)val);
                         else flags |= HJD_ST_COEF_RANGE;                                   // loadjpg.cpp:780-783
                     }
-                    // EOB ends the block, ZRL skips 16, any other size-0 symbol is ignored (loadjpg.cpp:771-775)
-                    k = store ? (int)kpos + 1 : (run == 0u ? 64 : (run == 15u ? k + 16 : k));
+                    k += (int)kadv;                      // EOB: +64, ZRL: +16 (loadjpg.cpp:771-775)
                     done_block = (k >= 64) || dead;
                 }
             }
@@ -322,6 +312,10 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
         // ---- block hand-over ---------------------------------------------------------------
         uint32_t flush_blk = 0;
         if (done_block) {
+            if (!dead) {                                  // DCT[0] = data + prevDC in int16 (loadjpg.cpp:664-665)
+                p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
+                hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
+            }
             flush_blk = gblk++;
             blocks_left--;
             k = 0;
@@ -332,19 +326,22 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
             }
             if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
         }
-        // ---- cooperative flush of the finished blocks --------------------------------------
+        // ---- cooperative flush of the finished blocks, four per step --------------------------
         const uint32_t m = __ballot_sync(0xffffffffu, done_block);
         if (m) {
             if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane);
             __syncwarp();
             const int n_done = __popc(m);
             const uint32_t chunk = (uint32_t)lane & 7u;
-            for (int idx = lane >> 3; idx < n_done; idx += 4) {
-                const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);          // {block, owner lane}
-                const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
-                const uint4 w = hjd_lds_v4_sync(src);
-                hjd_sts_zero16_sync(src);
-                ((uint4*)coef)[(size_t)ent.x * 8 + chunk] = w;
+            for (int base = 0; base < n_done; base += 4) {                                  // warp-uniform trip count
+                const int idx = base + (lane >> 3);
+                if (idx < n_done) {
+                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);      // {block, owner lane}
+                    const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
+                    const uint4 w = hjd_lds_v4_sync(src);
+                    hjd_sts_zero16_sync(src);
+                    ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
+                }
             }
             __syncwarp();
         }

@@ -257,20 +257,13 @@ __device__ __forceinline__ uint64_t ss_decode(const SsCtx& cx, uint64_t state, u
         }
         const uint32_t is_ac = (uint32_t)min(k, 1);
         const uint32_t t = tbase + is_ac * kTabBytes;
-        const uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
-        uint32_t len = e >> 8, sym = e & 255u;
-        if (len == 0) {
-            const uint32_t peek = hi >> 16;
-            len = HJD_LUT_BITS + 1;
-            while (len <= 16 && peek >= hjd_lds_u32(t + HJD_TAB_LIMIT_OFF + len * 4)) len++;
-            if (len > 16) { len = 1; sym = 0; *flags |= HJD_ST_BAD_CODE; }
-            else {
-                const uint32_t dl = hjd_lds_u32(t + HJD_TAB_DELTA_OFF + len * 4);
-                sym = hjd_lds_u8(t + HJD_TAB_VALS_OFF + (((peek >> (16 - len)) + dl) & 255u));
-            }
+        uint32_t e = hjd_lds_u32(t + ((hi >> (32 - HJD_LUT_BITS)) << 2));
+        if ((e & 31u) == 0) {
+            e = hjd_long_code(t, hi >> 16, is_ac != 0);
+            if (e == 0) { e = hjd_sym_fields(1, 0, is_ac != 0); *flags |= HJD_ST_BAD_CODE; }   // consume one bit
         }
-        const uint32_t size = sym & 15u;
-        const uint32_t run = is_ac ? (sym >> 4) : 0u;
+        const uint32_t len = e & 31u, size = (e >> 5) & 15u, kadv = (e >> 9) & 127u;
+        const bool store = (e >> 16) & 1u;
         const uint32_t after = __funnelshift_l(lo, hi, len);
         const uint32_t v = hjd_shr(after, 32u - size);
         const int neg = ~((int)after >> 31);
@@ -280,13 +273,12 @@ __device__ __forceinline__ uint64_t ss_decode(const SsCtx& cx, uint64_t state, u
         lo <<= used;
         nbits -= (int)used;
         p += used;
-        const bool store = (!is_ac) || (size != 0u);
-        const uint32_t kpos = (uint32_t)k + run;
+        const uint32_t kpos = (uint32_t)k + kadv - 1u;
         if (WRITE && store) {
             if (kpos <= 63u) coef_img[(size_t)(blk0 + nb) * 64 + kpos] = (int16_t)val;   // DC: the difference
             else *flags |= HJD_ST_COEF_RANGE;
         }
-        k = store ? (int)kpos + 1 : (run == 0u ? 64 : (run == 15u ? k + 16 : k));
+        k += (int)kadv;
         if (k >= 64) {
             nb++;
             k = 0;
