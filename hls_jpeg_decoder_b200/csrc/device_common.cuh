@@ -4,17 +4,17 @@
 #include "hjd_types.h"
 
 // Byte offsets inside HjdHuffTable (lut, limit, delta, vals) for 32-bit shared-window addressing.
-#define HJD_TAB_LIMIT_OFF (HJD_LUT_SIZE * 4)
-#define HJD_TAB_DELTA_OFF (HJD_LUT_SIZE * 4 + 68)
-#define HJD_TAB_VALS_OFF  (HJD_LUT_SIZE * 4 + 136)
+#define HJD_TAB_LIMIT_OFF (HJD_LUT_SIZE * 2)
+#define HJD_TAB_DELTA_OFF (HJD_LUT_SIZE * 2 + 68)
+#define HJD_TAB_VALS_OFF  (HJD_LUT_SIZE * 2 + 136)
 
 // Meaning of a decoded symbol (see HjdHuffTable); also used by the host when it fills the LUT.
 __host__ __device__ __forceinline__ uint32_t hjd_sym_fields(uint32_t len, uint32_t sym, bool is_ac)
 {
     const uint32_t size = sym & 15u, run = sym >> 4;
-    if (!is_ac) return HJD_SYM_FIELDS(len, size, 1, 1);                       // DC: loadjpg.cpp:616-667
-    if (size) return HJD_SYM_FIELDS(len, size, run + 1, 1);                   // loadjpg.cpp:778-806
-    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0), 0);   // EOB / ZRL / ignored, 771-775
+    if (!is_ac) return HJD_SYM_FIELDS(len, size, 1);                          // DC: loadjpg.cpp:616-667
+    if (size) return HJD_SYM_FIELDS(len, size, run + 1);                      // loadjpg.cpp:778-806
+    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0));      // EOB / ZRL / ignored, 771-775
 }
 
 __device__ __forceinline__ uint32_t hjd_lds_u16(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }

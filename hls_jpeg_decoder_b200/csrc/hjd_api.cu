@@ -123,6 +123,7 @@ struct hjd_batch {
     uint64_t total_blocks = 0, rgb_bytes = 0, plane_bytes = 0, scan_bytes = 0, pixels = 0, arena_bytes = 0;
     uint32_t total_intervals = 0, max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0;
     size_t fused_smem = 0;
+    int max_tabs = 1;
     bool any_parse_error = false;
     bool uploaded = false, decoded = false;
     int launches = 0;
@@ -240,6 +241,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
     b->total_intervals = b->max_blocks = b->max_w = b->max_h = b->max_strips = 0;
     b->fused_smem = 0;
+    b->max_tabs = 1;
     b->any_parse_error = false;
     b->uploaded = b->decoded = false;
 
@@ -262,7 +264,10 @@ static int upload_common(hjd_batch* b, bool chunked)
             else {
                 HjdTableSet ts;
                 st = hjd_build_table_set(ps, &ts);
-                if (st == HJD_IMG_OK) { tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_of[tk] = tset; }
+                if (st == HJD_IMG_OK) {
+                    tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_of[tk] = tset;
+                    if (ts.n_tabs > b->max_tabs) b->max_tabs = ts.n_tabs;
+                }
             }
         }
         if (st == HJD_IMG_OK) {
@@ -618,7 +623,7 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
     if (c.work1 > c.work0) {
         CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
                                       (const HjdEntropyWork*)b->d_work.p + c.work0, (int)(c.work1 - c.work0),
-                                      (int16_t*)b->d_coef.p, status, st));
+                                      b->max_tabs, (int16_t*)b->d_coef.p, status, st));
         b->launches += 1;
     }
     if (ev) CU(cudaEventRecord(ev[2], st));

@@ -6,7 +6,7 @@
 #pragma once
 #include <stdint.h>
 
-#define HJD_LUT_BITS    9                     // first-level Huffman lookup width
+#define HJD_LUT_BITS    10                    // first-level Huffman lookup width
 #define HJD_LUT_SIZE    (1 << HJD_LUT_BITS)
 #define HJD_MAX_TABLES  6                     // (DC, AC) x 3 components, de-duplicated per set
 
@@ -14,14 +14,15 @@
 // codes GenHuffCodes produces, openjpg.cpp:48-66).  A first-level entry already holds what the
 // symbol MEANS for the decode loop (ProcessHuffmanBlock's run/size logic, loadjpg.cpp:616-627, 768-808),
 // so the kernels do no per-symbol case analysis:
-//   lut[peek >> (16 - LUT_BITS)] = len | size << 5 | kadv << 9 | store << 16    (0: code longer than LUT_BITS)
-//     len   code length; size = number of value bits that follow
+//   lut[peek >> (16 - LUT_BITS)] = len | size << 5 | kadv << 9      (16 bits; 0: code longer than LUT_BITS)
+//     len   code length (1..16); size = number of value bits that follow (0..15)
 //     kadv  advance of the zig-zag index: DC 1; AC run+1; EOB 64; ZRL 16; other size-0 symbols 0 (ignored)
-//     store 1 if a coefficient is written at (k + kadv - 1): every DC symbol, AC symbols with size != 0
+//   A coefficient is written at (k + kadv - 1) iff size != 0: a DC symbol with size 0 adds nothing to
+//   the predictor, and the output block is zero-filled beforehand.
 //   longer codes: the first L in (LUT_BITS, 16] with peek16 < limit[L]; symbol = vals[(peek16 >> (16-L)) + delta[L]]
-#define HJD_SYM_FIELDS(len, size, kadv, store) ((uint32_t)(len) | (uint32_t)(size) << 5 | (uint32_t)(kadv) << 9 | (uint32_t)(store) << 16)
+#define HJD_SYM_FIELDS(len, size, kadv) ((uint32_t)(len) | (uint32_t)(size) << 5 | (uint32_t)(kadv) << 9)
 struct HjdHuffTable {
-    uint32_t lut[HJD_LUT_SIZE];
+    uint16_t lut[HJD_LUT_SIZE];
     uint32_t limit[17];      // exclusive upper bound of left-aligned codes of length <= L (0x10000 possible)
     int32_t  delta[17];      // valptr[L] - mincode[L]
     uint8_t  vals[256];

@@ -160,9 +160,9 @@ static uint32_t sym_fields(uint32_t len, uint32_t sym, bool is_ac)
 {
     // keep in sync with hjd_sym_fields() in device_common.cuh (ProcessHuffmanBlock's run/size logic)
     const uint32_t size = sym & 15u, run = sym >> 4;
-    if (!is_ac) return HJD_SYM_FIELDS(len, size, 1, 1);
-    if (size) return HJD_SYM_FIELDS(len, size, run + 1, 1);
-    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0), 0);
+    if (!is_ac) return HJD_SYM_FIELDS(len, size, 1);
+    if (size) return HJD_SYM_FIELDS(len, size, run + 1);
+    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0));
 }
 
 bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)
@@ -180,7 +180,7 @@ bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)
         if (L <= HJD_LUT_BITS) {
             for (int k = 0; k < cnt; k++) {
                 uint32_t first = (code + (uint32_t)k) << (HJD_LUT_BITS - L);
-                const uint32_t e = sym_fields((uint32_t)L, raw.vals[valptr + k], is_ac);
+                const uint16_t e = (uint16_t)sym_fields((uint32_t)L, raw.vals[valptr + k], is_ac);
                 for (uint32_t j = 0; j < (1u << (HJD_LUT_BITS - L)); j++) t->lut[first + j] = e;
             }
         }

@@ -170,19 +170,37 @@ struct BitReader {
     uint32_t hi, lo;       // MSB-aligned 64-bit window (hi:lo)
     int nbits;             // valid bits in the window
     int padbits;           // zero bits appended after `end`
+    // three aligned words prefetched one round ahead: with seven CTAs of shared memory per SM there
+    // is next to no L1 left, so every stream load is an L2 round trip that must not sit on the
+    // critical path of the symbol loop
+    const uint32_t* wptr;
+    uint32_t w0, w1, w2;
 };
+
+__device__ __forceinline__ void br_prefetch(BitReader& r)
+{
+    r.wptr = (const uint32_t*)((uintptr_t)(r.base + r.pos) & ~(uintptr_t)3);
+    r.w0 = __ldg(r.wptr);
+    r.w1 = __ldg(r.wptr + 1);
+    r.w2 = __ldg(r.wptr + 2);
+}
 
 // Append up to four bytes (as many as fit and as the interval still has).  FillNBits semantics
 // (loadjpg.cpp:446-484): the 00 stuffed after an FF data byte is dropped.  Bytes are taken up to
 // and including the first FF of the window so that the stuffed byte can be skipped without a
 // branch; a second FF in the same window is picked up by the next call.
+// CACHED: take the bytes from the prefetched words when they cover [pos, pos + 4).
+template <bool CACHED>
 __device__ __forceinline__ void br_refill(BitReader& r)
 {
     const uint32_t avail = r.end - r.pos;                       // pos never passes end
     const uintptr_t a = (uintptr_t)(r.base + r.pos);
     const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-    const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1);
-    const uint32_t x = __funnelshift_r(w0, w1, (uint32_t)(a & 3) * 8);       // 4 bytes, memory order
+    uint32_t x0, x1;
+    const uint32_t d = (uint32_t)(ap - r.wptr);                 // words between the prefetch origin and pos
+    if (CACHED && d <= 1u) { x0 = d ? r.w1 : r.w0; x1 = d ? r.w2 : r.w1; }
+    else { x0 = __ldg(ap); x1 = __ldg(ap + 1); }
+    const uint32_t x = __funnelshift_r(x0, x1, (uint32_t)(a & 3) * 8);       // 4 bytes, memory order
     const uint32_t ffm = ((~x) - 0x01010101u) & x & 0x80808080u;             // lowest set bit is exact
     const uint32_t j = (uint32_t)(__ffs((int)ffm) - 1) >> 3;                 // first FF byte; >= 4 when none
     const uint32_t room = (uint32_t)(64 - r.nbits) >> 3;
@@ -198,7 +216,7 @@ __device__ __forceinline__ void br_refill(BitReader& r)
     if (avail == 0 && r.nbits <= 32) { r.nbits += 32; r.padbits += 32; }     // past the interval: zero padding
 }
 
-__global__ void __launch_bounds__(HJD_ENT_THREADS, 7)
+__global__ void __launch_bounds__(HJD_ENT_THREADS, 6)
 hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
                       const HjdTableSet* __restrict__ tsets, const uint32_t* __restrict__ interval_start,
                       const HjdEntropyWork* __restrict__ work, int16_t* __restrict__ coef,
@@ -216,16 +234,11 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     const int tid = threadIdx.x, lane = tid & 31;
     const HjdTableSet* ts = tsets + wk.table_set;
     {
-        // component c's DC table goes to slot 2c, its AC table to slot 2c+1
-        const int ncomp_tabs = 3;
-        const int n16 = (int)(kTabBytes / 16);
-        for (int c = 0; c < ncomp_tabs; c++) {
-            const uint4* sdc = (const uint4*)&ts->tab[ts->dc_of_comp[c]];
-            const uint4* sac = (const uint4*)&ts->tab[ts->ac_of_comp[c]];
-            uint4* ddc = (uint4*)(s_raw + kSlotBytes + kListBytes + (2 * c) * kTabBytes);
-            uint4* dac = (uint4*)(s_raw + kSlotBytes + kListBytes + (2 * c + 1) * kTabBytes);
-            for (int i = tid; i < n16; i += HJD_ENT_THREADS) { ddc[i] = __ldg(sdc + i); dac[i] = __ldg(sac + i); }
-        }
+        // the distinct tables of this table set (normally 4: Cb and Cr share theirs)
+        const uint4* src = (const uint4*)ts->tab;
+        uint4* dst = (uint4*)(s_raw + kSlotBytes + kListBytes);
+        const int n16 = ts->n_tabs * (int)(kTabBytes / 16);
+        for (int i = tid; i < n16; i += HJD_ENT_THREADS) dst[i] = __ldg(src + i);
         uint4* z = (uint4*)s_raw;
         for (int i = tid; i < HJD_ENT_THREADS * 8; i += HJD_ENT_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
@@ -234,6 +247,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     // ---- per-lane interval setup -----------------------------------------------------------
     BitReader br;
     br.base = arena; br.pos = br.end = 0; br.hi = br.lo = 0; br.nbits = 0; br.padbits = 0;
+    br.wptr = (const uint32_t*)arena; br.w0 = br.w1 = br.w2 = 0;
     uint32_t blocks_left = 0, gblk = 0;
     int img = 0, bpm = 1, ny = 1;
     if ((uint32_t)tid < wk.n_intervals) {
@@ -254,8 +268,10 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
         blocks_left = n_mcu * (uint32_t)bpm;
         gblk = (uint32_t)(d->block_base + (uint64_t)first_mcu * bpm);
     }
-    // shared address of the current component's DC table (its AC table follows); rotated with p0..p2
-    uint32_t t0 = sh_tab, t1 = sh_tab + 2 * kTabBytes, t2 = sh_tab + 4 * kTabBytes;
+    // byte offsets of the current component's DC (low half) and AC (high half) table; rotated with p0..p2
+    uint32_t t0 = ts->dc_of_comp[0] * kTabBytes | (ts->ac_of_comp[0] * kTabBytes) << 16;
+    uint32_t t1 = ts->dc_of_comp[1] * kTabBytes | (ts->ac_of_comp[1] * kTabBytes) << 16;
+    uint32_t t2 = ts->dc_of_comp[2] * kTabBytes | (ts->ac_of_comp[2] * kTabBytes) << 16;
     int p0 = 0, p1 = 0, p2 = 0;        // DC predictors
     const uint32_t my_slot = sh_base + (uint32_t)tid * 128u;
     const uint32_t swz = (uint32_t)(lane & 7) << 4;      // XOR on the 16-byte chunk index
@@ -265,11 +281,13 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     int k = 0, bi = 0;                 // zig-zag index inside the block, block index inside the MCU
     int flags = 0;
     bool dead = false;                 // undecodable code or data exhausted: zero-fill the rest
+    br_prefetch(br);
 
     while (__any_sync(0xffffffffu, blocks_left > 0)) {
-        // scheduled top-up, all lanes together
-        br_refill(br);
-        if (br.nbits <= 40) br_refill(br);               // busy stretch: keep the reserve up
+        // scheduled top-up, all lanes together, from the words prefetched during the previous round
+        br_refill<true>(br);
+        if (br.nbits <= 40) br_refill<false>(br);        // busy stretch: keep the reserve up
+        br_prefetch(br);                                 // in flight while this round's symbols decode
         if (br.padbits > 512) dead = true;
         const bool live = blocks_left > 0;
         bool done_block = !live ? false : dead;
@@ -278,14 +296,14 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
             for (int rep = 0; rep < HJD_ENT_SYMS; rep++) {
                 if (!done_block) {
                     if (br.nbits < 32) {                 // rare: several very long symbols in a row
-                        br_refill(br); br_refill(br); br_refill(br); br_refill(br);
+                        br_refill<false>(br); br_refill<false>(br); br_refill<false>(br); br_refill<false>(br);
                     }
-                    const uint32_t is_ac = (uint32_t)min(k, 1);
-                    const uint32_t t = t0 + is_ac * kTabBytes;
+                    const bool is_ac = k != 0;
+                    const uint32_t t = sh_tab + (is_ac ? (t0 >> 16) : (t0 & 0xFFFFu));
                     // the entry says what the symbol means: code length, value bits, zig-zag advance, store or not
-                    uint32_t e = hjd_lds_u32(t + ((br.hi >> (32 - HJD_LUT_BITS)) << 2));
+                    uint32_t e = hjd_lds_u16(t + ((br.hi >> (32 - HJD_LUT_BITS)) << 1));
                     if ((e & 31u) == 0) {                // code longer than the first-level table
-                        e = hjd_long_code(t, br.hi >> 16, is_ac != 0);
+                        e = hjd_long_code(t, br.hi >> 16, is_ac);
                         if (e == 0) { dead = true; flags |= HJD_ST_BAD_CODE; }
                     }
                     const uint32_t len = e & 31u, size = (e >> 5) & 15u, kadv = (e >> 9) & 127u;
@@ -300,7 +318,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                     br.lo <<= used;
                     br.nbits -= (int)used;
                     const uint32_t kpos = (uint32_t)k + kadv - 1u;                         // loadjpg.cpp:778, 806
-                    if (e & 0x10000u) {                                                    // DC (as a difference) or AC value
+                    if (size) {                          // a value follows: DC difference or AC coefficient (slot is pre-zeroed)
                         if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)val);
                         else flags |= HJD_ST_COEF_RANGE;                                   // loadjpg.cpp:780-783
                     }
@@ -351,13 +369,16 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
 
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
                                        const uint32_t* interval_start, const HjdEntropyWork* work, int n_work,
-                                       int16_t* coef, int32_t* status, cudaStream_t st)
+                                       int max_tabs, int16_t* coef, int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    const size_t smem = HJD_ENT_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
+    if (max_tabs < 1) max_tabs = 1;
+    if (max_tabs > HJD_MAX_TABLES) max_tabs = HJD_MAX_TABLES;
+    const size_t smem = HJD_ENT_THREADS * (128 + 8) + (size_t)max_tabs * sizeof(HjdHuffTable);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(HJD_ENT_THREADS * (128 + 8) + HJD_MAX_TABLES * sizeof(HjdHuffTable)));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }

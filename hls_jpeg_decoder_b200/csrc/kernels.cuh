@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include "hjd_types.h"
 
-#define HJD_ENT_THREADS   128   // entropy kernel: one restart interval per thread
+#define HJD_ENT_THREADS   192   // entropy kernel: one restart interval per thread
 #define HJD_IDCT_THREADS  128   // unfused IDCT kernel: one 8x8 block per thread
 #define HJD_COLOR_THREADS 128   // unfused colour kernel: 16 pixels of one row per thread
 #define HJD_FUSED_THREADS 128   // fused IDCT+colour kernel: one strip of floor(128 / blocks_per_mcu) MCUs per CTA
@@ -19,7 +19,7 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
 // Kernel 1a: restart-interval-parallel Huffman decode -> int16 coefficients (zig-zag order).
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
                                        const uint32_t* interval_start, const HjdEntropyWork* work, int n_work,
-                                       int16_t* coef, int32_t* status, cudaStream_t st);
+                                       int max_tabs, int16_t* coef, int32_t* status, cudaStream_t st);
 
 // Kernel 2: dequantise + de-zig-zag + IDCT -> u8 planes (bit-exact with the reference's direct form).
 cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,

@@ -257,13 +257,13 @@ __device__ __forceinline__ uint64_t ss_decode(const SsCtx& cx, uint64_t state, u
         }
         const uint32_t is_ac = (uint32_t)min(k, 1);
         const uint32_t t = tbase + is_ac * kTabBytes;
-        uint32_t e = hjd_lds_u32(t + ((hi >> (32 - HJD_LUT_BITS)) << 2));
+        uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
         if ((e & 31u) == 0) {
             e = hjd_long_code(t, hi >> 16, is_ac != 0);
             if (e == 0) { e = hjd_sym_fields(1, 0, is_ac != 0); *flags |= HJD_ST_BAD_CODE; }   // consume one bit
         }
         const uint32_t len = e & 31u, size = (e >> 5) & 15u, kadv = (e >> 9) & 127u;
-        const bool store = (e >> 16) & 1u;
+        const bool store = size != 0u;              // a size-0 DC difference adds nothing; the slab is pre-zeroed
         const uint32_t after = __funnelshift_l(lo, hi, len);
         const uint32_t v = hjd_shr(after, 32u - size);
         const int neg = ~((int)after >> 31);
