@@ -338,6 +338,13 @@ def run_ours(args, rank, local_rank, world):
         dom = max(stage, key=stage.get)
         dom_ms = stage[dom]
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed ncu capture, scaled to this batch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+            if args.config == "c2":
+                traffic = int(tj["dram_bytes_per_launch"][dom.replace("_ms", "")] * n / tj["images"])
+        except Exception:
+            traffic = None
         whole = alg_bytes / (ms_max / args.steps / 1e3) / 1e9
         line = {"metric": "decoded_MP_per_s", "value": round(value, 1), "unit": "MP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 4),
@@ -351,7 +358,8 @@ def run_ours(args, rank, local_rank, world):
                 "compressed_GB_per_s": round(job_scan * args.steps / (ms_max / 1e3) / 1e9, 2),
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1),
-                             "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                             "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                             "traffic_source": "profiles/r1_final_traffic.json (ncu --set full, per launch)" if traffic else None,
                              "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
                              "whole_step_frac": round(whole / peak, 4)},
                 "clocks": clocks, "gpu_launches": launches * args.steps}

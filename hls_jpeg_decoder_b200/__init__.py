@@ -23,7 +23,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 
 import numpy as np
 
-__all__ = ["ConvertJpgFile", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
+__all__ = ["ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
            "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED", "FLAG_NO_SELFSYNC"]
 
@@ -76,6 +76,7 @@ _SIGS = {
     "hjd_get_image_size": (c_int, [c_void_p, c_int, POINTER(c_uint), POINTER(c_uint)]),
     "hjd_write_bmp24": (c_int, [c_char_p, c_uint, c_uint, c_void_p]),
     "hjd_encode_bmp24": (c_size_t, [c_uint, c_uint, c_void_p, c_void_p]),
+    "hjd_convert_jpg_files": (c_int, [POINTER(c_char_p), POINTER(c_char_p), c_int, c_int, c_int, POINTER(c_int)]),
     "hjd_batch_create": (c_void_p, [c_int, c_uint]),
     "hjd_batch_destroy": (None, [c_void_p]),
     "hjd_batch_set_stream": (c_int, [c_void_p, c_void_p]),
@@ -143,6 +144,18 @@ def _check(rc: int, what: str) -> None:
 def ConvertJpgFile(szJpgFileInName: str, szBmpFileOutName: str) -> int:
     """openjpg.cpp:593 -- load a .jpg, decode it on the GPU, write a 24-bit .bmp.  1 = ok, 0 = failure."""
     return int(lib().hjd_convert_jpg_file(os.fsencode(szJpgFileInName), os.fsencode(szBmpFileOutName)))
+
+
+def ConvertJpgFiles(jpg_in: list[str], bmp_out: list[str], device: int = 0, threads: int = 0) -> list[int]:
+    """ConvertJpgFile at batch scale: one batched decode, parallel file readers / BMP writers.
+    Returns the per-file 1/0 flags."""
+    n = len(jpg_in)
+    assert len(bmp_out) == n
+    a = (c_char_p * n)(*[os.fsencode(p) for p in jpg_in])
+    b = (c_char_p * n)(*[os.fsencode(p) for p in bmp_out])
+    ok = (c_int * n)()
+    lib().hjd_convert_jpg_files(a, b, n, device, threads, ok)
+    return list(ok)
 
 
 def DecodeJpgFileData(buf: bytes):

@@ -14,7 +14,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -978,4 +980,79 @@ extern "C" int hjd_convert_jpg_file(const char* jpg_in, const char* bmp_out)
     ok = hjd_write_bmp24(bmp_out, w, h, rgb);
     hjd_free(rgb);
     return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// batch-scale ConvertJpgFile: batched loader + one decode + parallel BMP writers
+// ------------------------------------------------------------------------------------------
+extern "C" int hjd_convert_jpg_files(const char* const* jpg_in, const char* const* bmp_out, int n, int device,
+                                     int threads, int* ok)
+{
+    if (!jpg_in || !bmp_out || n < 0) { fail(HJD_ERR_ARG, "hjd_convert_jpg_files", "bad arguments"); return 0; }
+    if (ok) for (int i = 0; i < n; i++) ok[i] = 0;
+    if (n == 0) return 0;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if (threads > n) threads = n;
+
+    // 1. sizes, then all files into one pinned arena (the batched counterpart of openjpg.cpp:603-619)
+    std::vector<int64_t> sizes((size_t)n, 0), offsets((size_t)n, 0);
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) {
+        FILE* fp = jpg_in[i] ? fopen(jpg_in[i], "rb") : nullptr;
+        if (fp) { fseek(fp, 0, SEEK_END); long len = ftell(fp); fclose(fp); if (len > 0) sizes[i] = len; }
+        offsets[i] = total;
+        total += (int64_t)align_up((uint64_t)sizes[i], 16);
+    }
+    uint8_t* arena = (uint8_t*)hjd_host_alloc((size_t)total + 16);
+    if (!arena) return 0;
+    {
+        std::atomic<int> next(0);
+        auto reader = [&]() {
+            for (int i = next++; i < n; i = next++) {
+                if (!sizes[i]) continue;
+                FILE* fp = fopen(jpg_in[i], "rb");
+                size_t got = fp ? fread(arena + offsets[i], 1, (size_t)sizes[i], fp) : 0;
+                if (fp) fclose(fp);
+                if (got != (size_t)sizes[i]) sizes[i] = 0;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) pool.emplace_back(reader);
+        for (auto& th : pool) th.join();
+    }
+
+    // 2. one batch decode with host buffers
+    int converted = 0;
+    hjd_batch* b = hjd_batch_create(device, 0);
+    uint8_t* rgb = nullptr;
+    std::vector<uint64_t> rgb_off((size_t)n, 0);
+    std::vector<int32_t> status((size_t)n, 0);
+    if (b) {
+        const uint64_t need = hjd_rgb_slab_bytes(arena, offsets.data(), sizes.data(), n);
+        rgb = (uint8_t*)hjd_host_alloc((size_t)need + 16);
+        if (rgb && hjd_batch_decode_host(b, arena, offsets.data(), sizes.data(), n, rgb, need, rgb_off.data(),
+                                         status.data(), 0) == HJD_OK) {
+            // 3. BMP encode + write in parallel (openjpg.cpp:504-570 layout)
+            std::atomic<int> next(0), done(0);
+            auto writer = [&]() {
+                for (int i = next++; i < n; i = next++) {
+                    if (status[i] < 0 || !bmp_out[i]) continue;          // rejected by the parser
+                    const HjdImageDesc& d = b->imgs[i];
+                    if (hjd_write_bmp24(bmp_out[i], d.width, d.height, rgb + rgb_off[i])) {
+                        if (ok) ok[i] = 1;
+                        done++;
+                    }
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; t++) pool.emplace_back(writer);
+            for (auto& th : pool) th.join();
+            converted = done.load();
+        }
+        hjd_batch_destroy(b);
+    }
+    if (rgb) hjd_host_free(rgb);
+    hjd_host_free(arena);
+    return converted;
 }

@@ -111,6 +111,12 @@ int  hjd_write_bmp24(const char* path, unsigned width, unsigned height, const ui
 /* Same bytes as hjd_write_bmp24 into memory; returns the BMP size (call with out = NULL to size it). */
 size_t hjd_encode_bmp24(unsigned width, unsigned height, const uint8_t* rgb, uint8_t* out);
 
+/* ConvertJpgFile at batch scale: read n .jpg files, decode them as one batch (chunked H2D / kernels /
+ * D2H overlap), write n 24-bit .bmp files with `threads` host threads (0 = all cores).
+ * ok[i] = 1 / 0 per file (may be NULL).  Returns the number of files converted. */
+int  hjd_convert_jpg_files(const char* const* jpg_in, const char* const* bmp_out, int n, int device,
+                           int threads, int* ok);
+
 /* ---- batch API: the JpegDecodeHW replacement, N independent images per call -------------- */
 hjd_batch* hjd_batch_create(int device, unsigned flags);
 void       hjd_batch_destroy(hjd_batch* b);

@@ -292,3 +292,94 @@ def test_selfsync_large_scan(hjd, port):
         assert np.array_equal(d.coefficients(), o["coef"])
         assert np.array_equal(d.rgb(0), o["rgb"])
         assert d.selfsync_rounds <= 6, d.selfsync_rounds
+
+
+def _patch_component_ids(jpg: bytes, ids):
+    """Rewrite the component identifiers in SOF0 and SOS (the reference indexes arrays with them,
+    openjpg.cpp:212-213,343-345, so it only works for 1,2,3)."""
+    b = bytearray(jpg)
+    i = 2
+    while i + 4 < len(b):
+        assert b[i] == 0xFF
+        m = b[i + 1]
+        ln = (b[i + 2] << 8) | b[i + 3]
+        if m == 0xC0:
+            for c in range(b[i + 9]):
+                b[i + 10 + 3 * c] = ids[c]
+        if m == 0xDA:
+            for c in range(b[i + 4]):
+                b[i + 5 + 2 * c] = ids[c]
+            break
+        i += 2 + ln
+    return bytes(b)
+
+
+def _move_dqt_after_sof(jpg: bytes):
+    """Reorder segments so that the DQT segments follow SOF0 (the reference copies the tables at
+    SOF time, openjpg.cpp:347-350, and would de-quantise with zeros)."""
+    segs, i = [], 2
+    while True:
+        m = jpg[i + 1]
+        ln = (jpg[i + 2] << 8) | jpg[i + 3]
+        if m == 0xDA:
+            tail = jpg[i:]
+            break
+        segs.append((m, jpg[i:i + 2 + ln]))
+        i += 2 + ln
+    dqt = [s for m, s in segs if m == 0xDB]
+    rest = [(m, s) for m, s in segs if m != 0xDB]
+    out = bytearray(jpg[:2])
+    for m, s in rest:
+        out += s
+        if m == 0xC0:
+            for q in dqt:
+                out += q
+    return bytes(out + tail)
+
+
+def test_inputs_the_reference_cannot_decode(hjd, port):
+    """component ids other than 1,2,3, DQT after SOF, extra APPn/COM segments and
+    fill bytes before markers.  The oracle port handles them by construction (components by position,
+    tables resolved at SOS); the GPU path must agree with it bit for bit."""
+    base = cases.small_cases()
+    a = _patch_component_ids(base["420_100x70_ri2"], [0, 1, 2])
+    b = _patch_component_ids(base["444_64x48_q85"], [82, 71, 66])
+    c = _move_dqt_after_sof(base["420_64x48_q85"])
+    d0 = base["422_64x48_q85"]
+    d = d0[:2] + b"\xff\xfe\x00\x07hello" + b"\xff\xff\xff\xe5\x00\x04ab" + d0[2:]      # COM, fill bytes + APP5
+    files = [a, b, c, d]
+    with hjd.BatchDecoder(0) as dec:
+        dec.upload(files)
+        dec.decode()
+        assert (dec.status() == 0).all(), dec.status()
+        coef = dec.coefficients()
+        for i, f in enumerate(files):
+            o = port.decode(f)
+            assert o["rc"] == 0
+            assert np.array_equal(dec.image_coefficients(i, coef), o["coef"]), i
+            assert np.array_equal(dec.rgb(i), o["rgb"]), i
+    # same pixels as the untouched files
+    assert np.array_equal(port.decode(a)["rgb"], port.decode(base["420_100x70_ri2"])["rgb"])
+    assert np.array_equal(port.decode(c)["rgb"], port.decode(base["420_64x48_q85"])["rgb"])
+
+
+def test_convert_jpg_files_batch(hjd, port, tmp_path):
+    """Batch-scale ConvertJpgFile: batched loader, one decode, parallel BMP writers; a missing file and
+    a non-JPEG do not stop the rest."""
+    names = ["420_100x70_ri2", "444_64x48_q85", "gray_64x64", "420_37x53_q75", "444_1x1"]
+    ins, outs = [], []
+    for n in names:
+        p = tmp_path / (n + ".jpg")
+        p.write_bytes(cases.small_cases()[n])
+        ins.append(str(p))
+        outs.append(str(tmp_path / (n + ".bmp")))
+    bad = tmp_path / "bad.jpg"
+    bad.write_bytes(b"this is not a jpeg")
+    ins += [str(bad), str(tmp_path / "missing.jpg")]
+    outs += [str(tmp_path / "bad.bmp"), str(tmp_path / "missing.bmp")]
+    ok = hjd.ConvertJpgFiles(ins, outs, threads=3)
+    assert ok == [1, 1, 1, 1, 1, 0, 0]
+    for n, o in zip(names, outs):
+        want = port.bmp24_bytes(port.decode(cases.small_cases()[n])["rgb"])
+        assert open(o, "rb").read() == want, n
+    assert not os.path.exists(outs[5]) and not os.path.exists(outs[6])
