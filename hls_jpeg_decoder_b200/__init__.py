@@ -28,7 +28,7 @@ __all__ = ["ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetIma
            "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED", "FLAG_NO_SELFSYNC"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhjd.so")
+LIB_PATH = os.environ.get("HJD_LIB_PATH") or os.path.join(_HERE, "libhjd.so")   # override: tuning builds only
 INCLUDE_PATH = os.path.join(os.path.dirname(_HERE), "include", "hjd.h")
 
 FLAG_KEEP_PLANES = 1
