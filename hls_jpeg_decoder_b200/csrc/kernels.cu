@@ -462,15 +462,28 @@ __device__ __forceinline__ float hjd_exact_sum(const float2 bp2[32], const float
     return sum;
 }
 
+__device__ __forceinline__ void hjd_ldg256(const uint4* p, uint4& a, uint4& b)
+{
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void hjd_ldg256_nc(const uint4* p, uint4& a, uint4& b)
+{
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 // One 8x8 block: dequantise, IDCT, +128, clamp; rows go to dst[y*pitch + 0..7] (planes in HBM for
 // the unfused kernel, a shared-memory tile for the fused one).  s_cos: the cos table in shared
 // memory (the exact re-evaluation indexes it dynamically).
 __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, const uint4* __restrict__ qp,
                                                const float* s_cos, uint8_t* dst, uint32_t pitch)
 {
+    // 256-bit loads (sm_100 LDG.256): a lane owns a whole 128-byte line, and every instruction of the
+    // warp touches 32 different lines, so wider loads halve the L1 wavefronts of this kernel
     uint4 c[8], q[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { c[i] = cp[i]; q[i] = __ldg(qp + i); }
+    for (int i = 0; i < 4; i++) { hjd_ldg256(cp + 2 * i, c[2 * i], c[2 * i + 1]); hjd_ldg256_nc(qp + 2 * i, q[2 * i], q[2 * i + 1]); }
 
     float2 bp2[32];
     float a_dc;
