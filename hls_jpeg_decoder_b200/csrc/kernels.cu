@@ -83,18 +83,24 @@ hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restr
         if (off < total) {
             const uint4 v = __ldg((const uint4*)(a0 + off));
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            // any FF byte in these 16?
-            uint32_t any = 0;
+            // SIMD-within-a-register byte tests (exact per byte, no carries between bytes):
+            //   ff: bytes equal to FF;  dn: bytes whose SUCCESSOR is D0..D7 (RSTn)
+            const uint32_t nb = (off + 16 < total) ? a0[off + 16] : 0u;
+            uint32_t dd[5];
 #pragma unroll
-            for (int k = 0; k < 4; k++) any |= ((~w[k]) - 0x01010101u) & w[k] & 0x80808080u;
-            if (any) {
-                const uint32_t nb = (off + 16 < total) ? a0[off + 16] : 0u;
+            for (int k = 0; k < 5; k++) {
+                const uint32_t x = ((k < 4 ? w[k] : nb) ^ 0xD0D0D0D0u) & 0xF8F8F8F8u;      // zero byte <=> D0..D7
+                dd[k] = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);           // 0x80 in those bytes
+            }
 #pragma unroll
-                for (int p = 0; p < 16; p++) {
-                    const uint32_t b  = (w[p >> 2] >> (8 * (p & 3))) & 255u;
-                    const uint32_t nx = (p == 15) ? nb : ((w[(p + 1) >> 2] >> (8 * ((p + 1) & 3))) & 255u);
-                    const bool hit = (b == 0xFFu) && ((nx & 0xF8u) == 0xD0u) && (off + p >= lead) && (off + p + 1 < total);
-                    mask |= hit ? (1u << p) : 0u;
+            for (int k = 0; k < 4; k++) {
+                const uint32_t ff = ((w[k] & 0x7F7F7F7Fu) + 0x01010101u) & w[k] & 0x80808080u;
+                uint32_t hit = ff & __funnelshift_r(dd[k], dd[k + 1], 8);                 // FF followed by RSTn
+                while (hit) {                                                             // rare: ~1 marker per 365 bytes
+                    const int bit = __ffs((int)hit) - 1;
+                    hit &= hit - 1;
+                    const uint32_t p = 4u * k + ((uint32_t)bit >> 3);
+                    if (off + p >= lead && off + p + 1 < total) mask |= 1u << p;
                 }
             }
         }
