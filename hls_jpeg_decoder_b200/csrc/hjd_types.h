@@ -8,6 +8,7 @@
 
 #define HJD_LUT_BITS    10                    // first-level Huffman lookup width
 #define HJD_LUT_SIZE    (1 << HJD_LUT_BITS)
+#define HJD_MAX_PIXELS  (1ull << 28)          // 16384 x 16384: larger frames are rejected (a corrupt SOF must not allocate 13 GB)
 #define HJD_MAX_TABLES  6                     // (DC, AC) x 3 components, de-duplicated per set
 
 // One flattened Huffman table (built on the host from BITS/HUFFVAL, i.e. the same canonical

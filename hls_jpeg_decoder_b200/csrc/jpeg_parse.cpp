@@ -101,6 +101,7 @@ int hjd_parse_jpeg(const uint8_t* buf, size_t size, HjdParsed* o)
             if (prec != 8 || (o->ncomp != 1 && o->ncomp != 3)) return o->status = HJD_IMG_ERR_UNSUPPORTED;
             if (len < 8 + 3 * o->ncomp) return o->status = HJD_IMG_ERR_TRUNCATED;
             if (o->width == 0 || o->height == 0) return o->status = HJD_IMG_ERR_UNSUPPORTED;
+            if ((uint64_t)o->width * o->height > HJD_MAX_PIXELS) return o->status = HJD_IMG_ERR_UNSUPPORTED;
             for (int c = 0; c < o->ncomp; c++) {
                 cid[c] = r.u8();
                 uint8_t s = r.u8();

@@ -25,6 +25,18 @@ def gradient_rgb(w, h):
     return img.astype(np.uint8)
 
 
+def encode_jpeg_cv(rgb, quality=85, sampling="440", restart=0):
+    """OpenCV / libjpeg-turbo encoder: the only one here that writes 4:4:0 (luma 1x2) files."""
+    import cv2
+    params = [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+              getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)]
+    if restart:
+        params += [cv2.IMWRITE_JPEG_RST_INTERVAL, restart]
+    ok, buf = cv2.imencode(".jpg", np.ascontiguousarray(rgb[:, :, ::-1]), params)
+    assert ok
+    return buf.tobytes()
+
+
 def small_cases():
     """name -> jpeg bytes; every sampling mode, odd sizes, restart intervals, table kinds, qualities."""
     c = {}
@@ -39,6 +51,8 @@ def small_cases():
     c["422_100x70_ri3"] = encode_jpeg(synth_rgb(100, 70, 9), 60, "4:2:2", restart_blocks=3)
     c["444_100x70_ri8"] = encode_jpeg(synth_rgb(100, 70, 10), 85, "4:4:4", restart_blocks=8)
     c["420_100x70_ri1000"] = encode_jpeg(synth_rgb(100, 70, 11), 85, "4:2:0", restart_blocks=1000)
+    c["440_100x70_q85"] = encode_jpeg_cv(synth_rgb(100, 70, 21), 85, "440")
+    c["440_61x35_ri3"] = encode_jpeg_cv(synth_rgb(61, 35, 22), 70, "440", restart=3)
     c["gray_64x64"] = encode_jpeg(synth_rgb(64, 64, 12), 75, gray=True)
     c["gray_33x9_ri4"] = encode_jpeg(synth_rgb(33, 9, 13), 75, gray=True, restart_blocks=4)
     c["420_opt_96x96"] = encode_jpeg(synth_rgb(96, 96, 14), 85, "4:2:0", optimize=True)

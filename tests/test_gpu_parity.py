@@ -383,3 +383,41 @@ def test_convert_jpg_files_batch(hjd, port, tmp_path):
         want = port.bmp24_bytes(port.decode(cases.small_cases()[n])["rgb"])
         assert open(o, "rb").read() == want, n
     assert not os.path.exists(outs[5]) and not os.path.exists(outs[6])
+
+
+@pytest.mark.timeout(600)
+def test_fuzzed_files_never_hang_or_crash(hjd):
+    """Random byte corruption anywhere in valid files (headers, tables, entropy data, markers):
+    every call returns, every loop is bounded, good neighbours in the batch are untouched."""
+    rng = np.random.default_rng(99)
+    base = cases.small_cases()
+    names = ["420_100x70_ri2", "444_64x48_q85", "gray_33x9_ri4", "420_opt_96x96", "422_100x70_ri3", "444_opt_ri5",
+             "440_61x35_ri3", "420_noise_q100"]
+    good = base["420_64x48_q85"]
+    with hjd.BatchDecoder(0) as d:
+        d.upload([good])
+        d.decode()
+        want = d.rgb(0).copy()
+        for rounds in range(12):
+            files = [good]
+            for n in names:
+                b = bytearray(base[n])
+                k = int(rng.integers(1, 12))
+                for _ in range(k):
+                    pos = int(rng.integers(2, len(b)))
+                    mode = int(rng.integers(0, 4))
+                    if mode == 0:
+                        b[pos] = int(rng.integers(0, 256))
+                    elif mode == 1:
+                        b[pos] = 0xFF
+                    elif mode == 2 and pos + 1 < len(b):
+                        b[pos], b[pos + 1] = 0xFF, int(rng.integers(0xD0, 0xDA))
+                    else:
+                        del b[pos:pos + int(rng.integers(1, 40))]
+                files.append(bytes(b))
+            files.append(good)
+            d.upload(files)
+            d.decode()
+            st = d.status()
+            assert st[0] == 0 and st[-1] == 0
+            assert np.array_equal(d.rgb(0), want) and np.array_equal(d.rgb(len(files) - 1), want)
