@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = ["ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED", "FLAG_NO_SELFSYNC"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HJD_LIB_PATH") or os.path.join(_HERE, "libhjd.so")   # override: tuning builds only
@@ -35,6 +35,7 @@ FLAG_KEEP_PLANES = 1
 FLAG_HOST_SCAN = 2
 FLAG_FUSED = 4
 FLAG_NO_SELFSYNC = 8
+FLAG_FUSED_MCU = 16
 
 IMG_WARN_BAD_CODE, IMG_WARN_COEF_RANGE, IMG_WARN_OVERRUN, IMG_WARN_RESTART = 1, 2, 4, 8
 

@@ -88,7 +88,7 @@ struct Chunk {
     uint32_t work0 = 0, work1 = 0;
     uint64_t arena_lo = 0, arena_hi = 0;      // device arena byte range holding these files
     uint64_t rgb_lo = 0, rgb_hi = 0;
-    uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0;
+    uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0, max_mcus = 0;
     uint64_t blocks = 0;
 };
 
@@ -393,6 +393,7 @@ static int upload_common(hjd_batch* b, bool chunked)
                 if (files[i].dev_off + (uint64_t)files[i].size > c.arena_hi) c.arena_hi = files[i].dev_off + (uint64_t)files[i].size;
             }
             if (d.n_blocks > c.max_blocks) c.max_blocks = (uint32_t)d.n_blocks;
+            if (d.n_mcus > c.max_mcus) c.max_mcus = d.n_mcus;
             if (d.width > c.max_w) c.max_w = d.width;
             if (d.height > c.max_h) c.max_h = d.height;
             if (d.blocks_per_mcu) {
@@ -426,7 +427,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_coef.ensure(b->total_blocks * 128 + 256));
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
-    if (!(b->flags & HJD_FLAG_FUSED)) CU(b->d_planes.ensure(b->plane_bytes + 256));
+    if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
     if (!b->ss.empty()) {
         uint32_t scan_n = b->ss_chunks + 1;
         if (b->ss_subs + 1 > scan_n) scan_n = b->ss_subs + 1;
@@ -629,7 +630,15 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
         b->launches += 1;
     }
     if (ev) CU(cudaEventRecord(ev[2], st));
-    if (b->flags & HJD_FLAG_FUSED) {
+    if (!(b->flags & (HJD_FLAG_KEEP_PLANES | HJD_FLAG_FUSED))) {
+        // default: kernels 2+3 fused per MCU, planes never reach HBM
+        if (c.blocks) {
+            CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
+                                  (uint8_t*)b->d_rgb.p, n, c.max_mcus, st));
+            b->launches += (n + 65534) / 65535;
+        }
+        if (ev) CU(cudaEventRecord(ev[3], st));
+    } else if ((b->flags & HJD_FLAG_FUSED) && !(b->flags & HJD_FLAG_KEEP_PLANES)) {
         if (c.blocks) {
             CU(hjd_launch_idct_color((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                      (uint8_t*)b->d_rgb.p, n, c.max_strips, b->fused_smem, st));
@@ -823,7 +832,7 @@ extern "C" int hjd_batch_download_coef(hjd_batch* b, int16_t* dst)
 
 extern "C" int hjd_batch_download_planes(hjd_batch* b, uint8_t* dst)
 {
-    if (b && (b->flags & HJD_FLAG_FUSED)) return fail(HJD_ERR_STATE, "hjd_batch_download_planes", "HJD_FLAG_FUSED keeps the planes in shared memory only");
+    if (b && !(b->flags & HJD_FLAG_KEEP_PLANES)) return fail(HJD_ERR_STATE, "hjd_batch_download_planes", "planes exist in HBM only with HJD_FLAG_KEEP_PLANES (the default kernels keep them in shared memory)");
     return download(b, dst, b ? b->d_planes.p : nullptr, b ? b->plane_bytes : 0, "hjd_batch_download_planes");
 }
 

@@ -618,31 +618,35 @@ __device__ __forceinline__ float hjd_byte_to_float(uint32_t word)
     return (float)((word >> (8 * SEL)) & 255u);
 }
 
-// 16 pixels -> 48 packed bytes.  HS = log2(horizontal luma factor): chroma sample i >> HS.
-template <int HS>
-__device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_t cbw[4], const uint32_t crw[4],
-                                             uint32_t out[12])
+// Chroma terms of NC chroma samples: (1.402*(Cr-128), 0.34414*(Cb-128), 0.71414*(Cr-128), 1.772*(Cb-128)),
+// each product rounded once as in loadjpg.cpp:873-879.  Shared by every luma sample that maps to the
+// chroma sample (2x1, 1x2 or 2x2 of them): nearest-neighbour upsampling, loadjpg.cpp:911-912.
+template <int NC>
+__device__ __forceinline__ void hjd_chroma_terms(const uint32_t* cbw, const uint32_t* crw, float4* terms)
 {
-    int ch[48];                           // R, G, B of the 16 pixels before clamping
-    float rr = 0.f, g1 = 0.f, g2 = 0.f, bb = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (HS == 0 || (i & 1) == 0) {
-            const int ci = i >> HS;
-            float cb, cr;
-            switch (ci & 3) {
-                case 0: cb = hjd_byte_to_float<0>(cbw[ci >> 2]); cr = hjd_byte_to_float<0>(crw[ci >> 2]); break;
-                case 1: cb = hjd_byte_to_float<1>(cbw[ci >> 2]); cr = hjd_byte_to_float<1>(crw[ci >> 2]); break;
-                case 2: cb = hjd_byte_to_float<2>(cbw[ci >> 2]); cr = hjd_byte_to_float<2>(crw[ci >> 2]); break;
-                default: cb = hjd_byte_to_float<3>(cbw[ci >> 2]); cr = hjd_byte_to_float<3>(crw[ci >> 2]); break;
-            }
-            cb = __fadd_rn(cb, -128.0f);  // (float)(Cb - 128), exact
-            cr = __fadd_rn(cr, -128.0f);
-            rr = __fmul_rn(1.402f, cr);
-            g1 = __fmul_rn(0.34414f, cb);
-            g2 = __fmul_rn(0.71414f, cr);
-            bb = __fmul_rn(1.772f, cb);
+    for (int ci = 0; ci < NC; ci++) {
+        float cb, cr;
+        switch (ci & 3) {
+            case 0: cb = hjd_byte_to_float<0>(cbw[ci >> 2]); cr = hjd_byte_to_float<0>(crw[ci >> 2]); break;
+            case 1: cb = hjd_byte_to_float<1>(cbw[ci >> 2]); cr = hjd_byte_to_float<1>(crw[ci >> 2]); break;
+            case 2: cb = hjd_byte_to_float<2>(cbw[ci >> 2]); cr = hjd_byte_to_float<2>(crw[ci >> 2]); break;
+            default: cb = hjd_byte_to_float<3>(cbw[ci >> 2]); cr = hjd_byte_to_float<3>(crw[ci >> 2]); break;
         }
+        cb = __fadd_rn(cb, -128.0f);      // (float)(Cb - 128), exact
+        cr = __fadd_rn(cr, -128.0f);
+        terms[ci] = make_float4(__fmul_rn(1.402f, cr), __fmul_rn(0.34414f, cb), __fmul_rn(0.71414f, cr), __fmul_rn(1.772f, cb));
+    }
+}
+
+// NP luma samples (8 or 16) + their chroma terms -> 3*NP packed bytes.  HS = log2(horizontal luma factor).
+template <int HS, int NP>
+__device__ __forceinline__ void hjd_color_apply(const uint32_t* yw, const float4* terms, uint32_t* out)
+{
+    int ch[3 * NP];                       // R, G, B before clamping
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const float4 t = terms[i >> HS];
         float fy;
         switch (i & 3) {
             case 0: fy = hjd_byte_to_float<0>(yw[i >> 2]); break;
@@ -651,13 +655,28 @@ __device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_
             default: fy = hjd_byte_to_float<3>(yw[i >> 2]); break;
         }
         // loadjpg.cpp:873-879 with the argument swap of the call at 918 resolved; (int) truncates
-        ch[3 * i]     = __float2int_rz(__fadd_rn(fy, rr));
-        ch[3 * i + 1] = __float2int_rz(__fsub_rn(__fsub_rn(fy, g1), g2));
-        ch[3 * i + 2] = __float2int_rz(__fadd_rn(fy, bb));
+        ch[3 * i]     = __float2int_rz(__fadd_rn(fy, t.x));
+        ch[3 * i + 1] = __float2int_rz(__fsub_rn(__fsub_rn(fy, t.y), t.z));
+        ch[3 * i + 2] = __float2int_rz(__fadd_rn(fy, t.w));
     }
 #pragma unroll
-    for (int w = 0; w < 12; w++)          // Clamp (loadjpg.cpp:83-91) + pack, two values per instruction
+    for (int w = 0; w < 3 * NP / 4; w++)  // Clamp (loadjpg.cpp:83-91) + pack, two values per instruction
         out[w] = hjd_pack_sat_u8(ch[4 * w + 1], ch[4 * w], hjd_pack_sat_u8(ch[4 * w + 3], ch[4 * w + 2], 0u));
+}
+
+template <int HS, int NP>
+__device__ __forceinline__ void hjd_color_n(const uint32_t* yw, const uint32_t* cbw, const uint32_t* crw, uint32_t* out)
+{
+    float4 terms[NP >> HS];
+    hjd_chroma_terms<(NP >> HS)>(cbw, crw, terms);
+    hjd_color_apply<HS, NP>(yw, terms, out);
+}
+
+template <int HS>
+__device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_t cbw[4], const uint32_t crw[4],
+                                             uint32_t out[12])
+{
+    hjd_color_n<HS, 16>(yw, cbw, crw, out);
 }
 
 __global__ void __launch_bounds__(HJD_COLOR_THREADS)
@@ -843,6 +862,100 @@ cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs,
     for (int base = 0; base < n_images; base += 65535) {
         const int n = min(65535, n_images - base);
         hjd_k_idct_color<<<dim3(max_strips, n), HJD_FUSED_THREADS, smem, st>>>(coef, imgs, qsets, rgb, base);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels 2+3 fused per MCU (HJD_FLAG_FUSED_MCU): one thread decodes a whole MCU to RGB
+// ------------------------------------------------------------------------------------------
+// The reference couples DecodeMCU and YCrCB_to_RGB24_Block8x8 per MCU (loadjpg.cpp:1179-1180); so
+// does this kernel, with no barrier at all: a thread runs the IDCT of its MCU's Cb and Cr blocks into
+// thread-private shared-memory tiles, then, Y block by Y block, the IDCT into a third private tile
+// followed at once by upsampling + colour conversion of those 8x8 pixels and 24-byte row stores.
+// Planes never reach HBM.  Tiles are interleaved by thread (row r of thread t at [(r*T + t) * 8 B])
+// so row stores and loads are bank-conflict free; the exact re-evaluation patches bytes in the tile
+// before the colour step reads them.
+__global__ void __launch_bounds__(HJD_MCU_THREADS, 4)
+hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
+              const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb, int img_base)
+{
+    __shared__ float s_cos[64];
+    __shared__ uint2 s_tile[3][8 * HJD_MCU_THREADS];             // Y, Cb, Cr: 8 rows x T threads x 8 bytes
+    const uint32_t t = threadIdx.x;
+    if (t < 64) s_cos[t] = c_cos[t];
+    __syncthreads();
+
+    const HjdImageDesc* d = imgs + (blockIdx.y + img_base);
+    const uint32_t m = blockIdx.x * HJD_MCU_THREADS + t;
+    if (m >= d->n_mcus || d->blocks_per_mcu == 0) return;
+    const uint32_t hf = d->hf, vf = d->vf, bpm = d->blocks_per_mcu;
+    const bool gray = d->ncomp == 1;
+    const uint32_t ny = gray ? 1u : hf * vf;
+    const uint32_t my = m / d->mcus_x, mx = m - my * d->mcus_x;
+    const int hs = (int)hf - 1, vs = (int)vf - 1;
+    const HjdQuantSet* qs = qsets + d->quant_set;
+    const uint4* cp = (const uint4*)(coef + (d->block_base + (uint64_t)m * bpm) * 64);
+    constexpr uint32_t kPitch = HJD_MCU_THREADS * 8;
+    uint8_t* tY = (uint8_t*)&s_tile[0][t];
+    uint8_t* tCb = (uint8_t*)&s_tile[1][t];
+    uint8_t* tCr = (uint8_t*)&s_tile[2][t];
+
+    const uint32_t W = d->width, H = d->height;
+    const uint64_t img_pitch = (uint64_t)W * 3;
+    uint8_t* img_rgb = rgb + d->rgb_off;
+    // one loop, one inlined IDCT: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order
+    const uint32_t n_pre = gray ? 0u : 2u;
+#pragma unroll 1
+    for (uint32_t it = 0; it < n_pre + ny; it++) {
+        const bool chroma = it < n_pre;
+        const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
+        hjd_idct_block(cp + bi * 8, (const uint4*)qs->qp[chroma ? 1 + it : 0], s_cos, chroma ? (it ? tCr : tCb) : tY, kPitch);
+        if (chroma) continue;
+        const uint32_t bx = bi % hf, by = bi / hf;
+        const uint32_t px = (mx * hf + bx) * 8, py0 = (my * vf + by) * 8;
+        if (px >= W) continue;                                    // loadjpg.cpp:907
+        const uint32_t npix = min(8u, W - px);
+#pragma unroll 1
+        for (uint32_t r = 0; r < 8; r++) {
+            const uint32_t py = py0 + r;
+            if (py >= H) break;                                   // loadjpg.cpp:908
+            const uint2 yv = *(const uint2*)(tY + r * kPitch);
+            const uint32_t yw[2] = {yv.x, yv.y};
+            uint32_t cbw[2] = {0x80808080u, 0x80808080u}, crw[2] = {0x80808080u, 0x80808080u};
+            if (!gray) {
+                const uint32_t crow = (by * 8 + r) >> vs;         // nearest neighbour, loadjpg.cpp:911-912
+                const uint2 b8 = *(const uint2*)(tCb + crow * kPitch), r8 = *(const uint2*)(tCr + crow * kPitch);
+                if (hs) { cbw[0] = bx ? b8.y : b8.x; crw[0] = bx ? r8.y : r8.x; }
+                else { cbw[0] = b8.x; cbw[1] = b8.y; crw[0] = r8.x; crw[1] = r8.y; }
+            }
+            // (sharing the chroma products between the two luma rows of a chroma row was measured slower:
+            //  the extra live registers spill)
+            uint32_t out[6];
+            if (hs) hjd_color_n<1, 8>(yw, cbw, crw, out); else hjd_color_n<0, 8>(yw, cbw, crw, out);
+            uint8_t* dst = img_rgb + (uint64_t)py * img_pitch + (uint64_t)px * 3;      // loadjpg.cpp:921-925
+            if (npix == 8 && (((uintptr_t)dst) & 7) == 0) {
+                uint2* o = (uint2*)dst;
+                o[0] = make_uint2(out[0], out[1]);
+                o[1] = make_uint2(out[2], out[3]);
+                o[2] = make_uint2(out[4], out[5]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 24; i++)
+                    if ((uint32_t)i < npix * 3) dst[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+            }
+        }
+    }
+}
+
+cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
+                               uint8_t* rgb, int n_images, uint32_t max_mcus, cudaStream_t st)
+{
+    if (n_images <= 0 || max_mcus == 0) return cudaSuccess;
+    const unsigned gx = (max_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS;
+    for (int base = 0; base < n_images; base += 65535) {
+        const int n = min(65535, n_images - base);
+        hjd_k_mcu_rgb<<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, base);
     }
     return cudaGetLastError();
 }

@@ -12,6 +12,7 @@
 #endif
 #define HJD_IDCT_THREADS  128   // unfused IDCT kernel: one 8x8 block per thread
 #define HJD_COLOR_THREADS 128   // unfused colour kernel: 16 pixels of one row per thread
+#define HJD_MCU_THREADS   128   // per-MCU fused kernel: one MCU (all its blocks -> RGB) per thread
 #define HJD_FUSED_THREADS 128   // fused IDCT+colour kernel: one strip of floor(128 / blocks_per_mcu) MCUs per CTA
 
 // Upload the IDCT constants (host libm values, loadjpg.cpp:96-102,120).
@@ -40,3 +41,7 @@ cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, ui
 size_t hjd_fused_smem_bytes(int ncomp, int hf, int vf);
 cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                   uint8_t* rgb, int n_images, uint32_t max_strips, size_t smem, cudaStream_t st);
+
+// Kernels 2+3 fused per MCU: one thread = one MCU, coefficients -> RGB, no plane traffic, no barriers.
+cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
+                               uint8_t* rgb, int n_images, uint32_t max_mcus, cudaStream_t st);

@@ -59,9 +59,10 @@ extern "C" {
 #define HJD_IMG_WARN_RESTART       8   /* RSTn count differs from ceil(MCUs/Ri)-1 */
 
 /* hjd_batch_create flags */
-#define HJD_FLAG_KEEP_PLANES   1u   /* (default behaviour; kept for compatibility) Y/Cb/Cr planes stay in HBM */
+#define HJD_FLAG_KEEP_PLANES   1u   /* unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap, hjd_batch_download_planes) */
 #define HJD_FLAG_HOST_SCAN     2u   /* find RSTn markers on the host instead of the GPU pre-pass */
-#define HJD_FLAG_FUSED         4u   /* kernels 2+3 fused: planes live in shared memory only (no plane tap) */
+#define HJD_FLAG_FUSED         4u   /* kernels 2+3 fused per MCU strip with CTA-wide phases (slower than the default; kept for comparison) */
+#define HJD_FLAG_FUSED_MCU    16u   /* (default behaviour) kernels 2+3 fused per MCU: one thread decodes a whole MCU to RGB */
 #define HJD_FLAG_NO_SELFSYNC   8u   /* restart-free scans: one thread per scan (kernel 1a) instead of kernel 1b */
 
 typedef struct hjd_batch hjd_batch;
