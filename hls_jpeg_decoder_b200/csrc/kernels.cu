@@ -910,6 +910,10 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
     for (uint32_t it = 0; it < n_pre + ny; it++) {
         const bool chroma = it < n_pre;
         const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
+        if (it + 1 < n_pre + ny) {                                // next block's 128-byte line -> L1 while this one computes
+            const uint32_t nbi = (it + 1 < n_pre) ? ny + it + 1 : it + 1 - n_pre;
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(cp + nbi * 8));
+        }
         hjd_idct_block(cp + bi * 8, (const uint4*)qs->qp[chroma ? 1 + it : 0], s_cos, chroma ? (it ? tCr : tCb) : tY, kPitch);
         if (chroma) continue;
         const uint32_t bx = bi % hf, by = bi / hf;
