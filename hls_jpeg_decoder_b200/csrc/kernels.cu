@@ -881,7 +881,7 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
               const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb, int img_base)
 {
     __shared__ float s_cos[64];
-    __shared__ uint2 s_tile[3][8 * HJD_MCU_THREADS];             // Y, Cb, Cr: 8 rows x T threads x 8 bytes
+    __shared__ uint2 s_tile[4][8 * HJD_MCU_THREADS];             // Y (left), Y (right), Cb, Cr: 8 rows x T threads x 8 bytes
     const uint32_t t = threadIdx.x;
     if (t < 64) s_cos[t] = c_cos[t];
     __syncthreads();
@@ -897,14 +897,18 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
     const HjdQuantSet* qs = qsets + d->quant_set;
     const uint4* cp = (const uint4*)(coef + (d->block_base + (uint64_t)m * bpm) * 64);
     constexpr uint32_t kPitch = HJD_MCU_THREADS * 8;
-    uint8_t* tY = (uint8_t*)&s_tile[0][t];
-    uint8_t* tCb = (uint8_t*)&s_tile[1][t];
-    uint8_t* tCr = (uint8_t*)&s_tile[2][t];
+    uint8_t* tY0 = (uint8_t*)&s_tile[0][t];
+    uint8_t* tY1 = (uint8_t*)&s_tile[1][t];
+    uint8_t* tCb = (uint8_t*)&s_tile[2][t];
+    uint8_t* tCr = (uint8_t*)&s_tile[3][t];
 
     const uint32_t W = d->width, H = d->height;
     const uint64_t img_pitch = (uint64_t)W * 3;
     uint8_t* img_rgb = rgb + d->rgb_off;
-    // one loop, one inlined IDCT: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order
+    const uint32_t px = mx * hf * 8;                              // left edge of the MCU
+    const uint32_t npix = px < W ? min(8u * hf, W - px) : 0u;     // loadjpg.cpp:907
+    // one loop, one inlined IDCT: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order;
+    // after the last Y block of a block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB
     const uint32_t n_pre = gray ? 0u : 2u;
 #pragma unroll 1
     for (uint32_t it = 0; it < n_pre + ny; it++) {
@@ -914,39 +918,52 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
             const uint32_t nbi = (it + 1 < n_pre) ? ny + it + 1 : it + 1 - n_pre;
             asm volatile("prefetch.global.L1 [%0];" :: "l"(cp + nbi * 8));
         }
-        hjd_idct_block(cp + bi * 8, (const uint4*)qs->qp[chroma ? 1 + it : 0], s_cos, chroma ? (it ? tCr : tCb) : tY, kPitch);
-        if (chroma) continue;
-        const uint32_t bx = bi % hf, by = bi / hf;
-        const uint32_t px = (mx * hf + bx) * 8, py0 = (my * vf + by) * 8;
-        if (px >= W) continue;                                    // loadjpg.cpp:907
-        const uint32_t npix = min(8u, W - px);
+        const uint32_t bx = chroma ? 0u : bi % hf, by = chroma ? 0u : bi / hf;
+        hjd_idct_block(cp + bi * 8, (const uint4*)qs->qp[chroma ? 1 + it : 0], s_cos,
+                       chroma ? (it ? tCr : tCb) : (bx ? tY1 : tY0), kPitch);
+        if (chroma || bx + 1 < hf || npix == 0) continue;
+        const uint32_t py0 = (my * vf + by) * 8;
 #pragma unroll 1
         for (uint32_t r = 0; r < 8; r++) {
             const uint32_t py = py0 + r;
             if (py >= H) break;                                   // loadjpg.cpp:908
-            const uint2 yv = *(const uint2*)(tY + r * kPitch);
-            const uint32_t yw[2] = {yv.x, yv.y};
             uint32_t cbw[2] = {0x80808080u, 0x80808080u}, crw[2] = {0x80808080u, 0x80808080u};
             if (!gray) {
                 const uint32_t crow = (by * 8 + r) >> vs;         // nearest neighbour, loadjpg.cpp:911-912
                 const uint2 b8 = *(const uint2*)(tCb + crow * kPitch), r8 = *(const uint2*)(tCr + crow * kPitch);
-                if (hs) { cbw[0] = bx ? b8.y : b8.x; crw[0] = bx ? r8.y : r8.x; }
-                else { cbw[0] = b8.x; cbw[1] = b8.y; crw[0] = r8.x; crw[1] = r8.y; }
+                cbw[0] = b8.x; cbw[1] = b8.y; crw[0] = r8.x; crw[1] = r8.y;
             }
-            // (sharing the chroma products between the two luma rows of a chroma row was measured slower:
-            //  the extra live registers spill)
-            uint32_t out[6];
-            if (hs) hjd_color_n<1, 8>(yw, cbw, crw, out); else hjd_color_n<0, 8>(yw, cbw, crw, out);
             uint8_t* dst = img_rgb + (uint64_t)py * img_pitch + (uint64_t)px * 3;      // loadjpg.cpp:921-925
-            if (npix == 8 && (((uintptr_t)dst) & 7) == 0) {
-                uint2* o = (uint2*)dst;
-                o[0] = make_uint2(out[0], out[1]);
-                o[1] = make_uint2(out[2], out[3]);
-                o[2] = make_uint2(out[4], out[5]);
-            } else {
+            const uint2 ya = *(const uint2*)(tY0 + r * kPitch);
+            if (hs) {                                             // 16 pixels: 48 bytes, three 128-bit stores
+                const uint2 yb = *(const uint2*)(tY1 + r * kPitch);
+                const uint32_t yw[4] = {ya.x, ya.y, yb.x, yb.y};
+                uint32_t out[12];
+                hjd_color_n<1, 16>(yw, cbw, crw, out);
+                if (npix == 16 && (((uintptr_t)dst) & 15) == 0) {
+                    uint4* o = (uint4*)dst;
+                    o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                    o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+                    o[2] = make_uint4(out[8], out[9], out[10], out[11]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 24; i++)
-                    if ((uint32_t)i < npix * 3) dst[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                    for (int i = 0; i < 48; i++)
+                        if ((uint32_t)i < npix * 3) dst[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                }
+            } else {                                              // 8 pixels: 24 bytes
+                const uint32_t yw[2] = {ya.x, ya.y};
+                uint32_t out[6];
+                hjd_color_n<0, 8>(yw, cbw, crw, out);
+                if (npix == 8 && (((uintptr_t)dst) & 7) == 0) {
+                    uint2* o = (uint2*)dst;
+                    o[0] = make_uint2(out[0], out[1]);
+                    o[1] = make_uint2(out[2], out[3]);
+                    o[2] = make_uint2(out[4], out[5]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; i++)
+                        if ((uint32_t)i < npix * 3) dst[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                }
             }
         }
     }
