@@ -41,7 +41,7 @@ def parse_args():
                          "restart-free image, c5 = 256x256 gray/4:2:0 thumbnails")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank decodes its own batch; strong: one batch sharded over the ranks (config 3)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -352,7 +352,7 @@ def run_ours(args, rank, local_rank, world):
                 "data": "synthetic",
                 "config": {"workload": f"{int(job_images)} x {wl['desc']}; inputs resident in HBM",
                            "images_per_gpu": n, "scan_bytes_per_image": scan_bytes // max(n, 1),
-                           "l2_policy": f"per-step working set (coefficient + plane + RGB slabs, {(dec.coef_bytes + 2 * dec.rgb_bytes) / 1e9:.2f} GB on rank 0) "
+                           "l2_policy": f"per-step working set (coefficient + RGB slabs, {(dec.coef_bytes + dec.rgb_bytes) / 1e9:.2f} GB on rank 0) "
                                         "against a 126 MB L2; every step rewrites all of it",
                            "parallelism": f"{world} independent shards ({args.scaling} scaling), no collective"},
                 "compressed_GB_per_s": round(job_scan * args.steps / (ms_max / 1e3) / 1e9, 2),
