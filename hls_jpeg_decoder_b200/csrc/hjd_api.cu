@@ -431,7 +431,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (!b->ss.empty()) {
         uint32_t scan_n = b->ss_chunks + 1;
         if (b->ss_subs + 1 > scan_n) scan_n = b->ss_subs + 1;
-        if (3 * b->ss_mcus + 1 > scan_n) scan_n = 3 * b->ss_mcus + 1;
+        if (4 * b->ss_subs + 2 > scan_n) scan_n = 4 * b->ss_subs + 2;
         CU(b->d_ss.ensure(sizeof(HjdSsImage) * b->ss.size()));
         CU(b->d_sswork.ensure(sizeof(HjdSsWork) * b->sswork.size()));
         CU(b->d_destuff.ensure(b->ss_dst_bytes + 256));
@@ -441,8 +441,7 @@ static int upload_common(hjd_batch* b, bool chunked)
         CU(b->d_ssE0.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssE1.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssX.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
-        CU(b->d_ssnb.ensure(sizeof(uint32_t) * ((size_t)b->ss_subs + 2)));
-        CU(b->d_dcsums.ensure(sizeof(uint32_t) * (3 * (size_t)b->ss_mcus + 2)));
+        CU(b->d_ssnb.ensure(sizeof(uint32_t) * (4 * (size_t)b->ss_subs + 4)));
         CU(b->d_flag.ensure(sizeof(int) * 4));
         CU(b->h_flag.ensure(sizeof(int) * 4));
     }
@@ -569,41 +568,34 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     uint32_t* dlen = (uint32_t*)b->d_dlen.p;
     uint64_t* E[2] = {(uint64_t*)b->d_ssE0.p, (uint64_t*)b->d_ssE1.p};
     uint64_t* X = (uint64_t*)b->d_ssX.p;
-    uint32_t* nb = (uint32_t*)b->d_ssnb.p;
+    uint32_t* cnt = (uint32_t*)b->d_ssnb.p;                       // [4][ss_subs] (+1): starts, DC sums Y/Cb/Cr
     int* flag = (int*)b->d_flag.p;
     int* hflag = (int*)b->h_flag.p;
+    const uint32_t N = b->ss_subs;
 
     CU(hjd_launch_destuff(arena, imgs, ss, n_ss, b->ss_chunks, (uint32_t*)b->d_counts.p, (uint32_t*)b->d_scantmp.p,
                           dst, dlen, st));
     b->launches += 2 + (b->ss_chunks + 1 > 2048 ? 3 : 1);
-    // the coefficient regions are written sparsely: zero them first
-    for (const HjdSsImage& si : b->ss) {
-        const HjdImageDesc& d = b->imgs[si.img];
-        CU(cudaMemsetAsync((uint8_t*)b->d_coef.p + d.block_base * 128, 0, d.n_blocks * 128, st));
-    }
     CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
-    CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 1, E[1], E[0], X, nb, flag, st));
+    CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 1, N, E[1], E[0], X, cnt, flag, st));
     b->launches += 1;
-    const int max_rounds = (int)(b->ss_subs / 32) + 8;
+    const int max_rounds = (int)(N / 32) + 8;
     int r = 1;
     for (;; r++) {
         if (r > max_rounds) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
         CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
-        CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 0, E[(r - 1) & 1], E[r & 1], X, nb, flag, st));
+        CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 0, N, E[(r - 1) & 1], E[r & 1], X, cnt, flag, st));
         b->launches += 1;
         CU(cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (*hflag == 0) break;
     }
     b->ss_rounds = r + 1;
-    CU(hjd_scan_u32(nb, b->ss_subs + 1, (uint32_t*)b->d_scantmp.p, st));          // nb[] becomes first_block[]
-    CU(hjd_launch_ss_write(imgs, tsets, ss, work, n_work, dst, dlen, X, nb, (int16_t*)b->d_coef.p,
+    CU(cudaMemsetAsync(cnt + 4 * (size_t)N, 0, sizeof(uint32_t), st));
+    CU(hjd_scan_u32(cnt, 4 * N + 1, (uint32_t*)b->d_scantmp.p, st));              // cnt[] becomes its exclusive prefix
+    CU(hjd_launch_ss_write(imgs, tsets, ss, work, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
                            (int32_t*)b->d_status.p, st));
-    uint32_t* sums = (uint32_t*)b->d_dcsums.p;
-    CU(hjd_launch_dc_sums(imgs, ss, n_ss, b->ss_mcus, (const int16_t*)b->d_coef.p, sums, st));
-    CU(hjd_scan_u32(sums, 3 * b->ss_mcus + 1, (uint32_t*)b->d_scantmp.p, st));
-    CU(hjd_launch_dc_apply(imgs, ss, n_ss, b->ss_mcus, sums, (int16_t*)b->d_coef.p, st));
-    b->launches += 3 + 2 * 3;
+    b->launches += 1 + (4 * N + 1 > 2048 ? 3 : 1);
     return HJD_OK;
 }
 

@@ -7,19 +7,19 @@
 //
 //   0. de-stuff: FF00 -> FF once, in parallel (count / prefix-sum / scatter), so that bit positions
 //      are plain offsets and the decoders carry no marker logic;
-//   1. every thread decodes one 128-byte sub-sequence starting at its fixed bit offset, assuming a
-//      block starts there, and records its exit state (bit position, zig-zag index, block-in-MCU);
+//   1. every thread decodes from a fixed bit offset one sub-sequence ahead of its own 128-byte
+//      sub-sequence (assuming a block starts there), then its own, and records its exit state
+//      (bit position, zig-zag index, block-in-MCU);
 //   2. sync rounds: a thread re-decodes its sub-sequence from its left neighbour's exit state whenever
 //      that state differs from the one it last used.  Inside a warp the neighbour state travels by
 //      warp shuffle and the round iterates until the warp is stable; across warps it travels through
 //      HBM and the host repeats the round until no exit state moves.  Sub-sequence 0 starts from the
 //      true state, so by induction the fixed point is exactly the sequential decode;
-//   3. an exclusive prefix sum of the per-sub-sequence block counts gives every thread its first
-//      output block;
-//   4. the final pass decodes from the correct entry states and writes int16 coefficients (DC still
-//      as differences) into the zero-filled slab;
-//   5. a per-component prefix sum over MCUs turns DC differences into DC values
-//      (DCT[0] = data + prevDC in int16, loadjpg.cpp:664-665).
+//   3. an exclusive prefix sum of, per sub-sequence, the number of blocks that start in it and the sums
+//      of their DC differences gives every thread its first output block and its DC predictors
+//      (DCT[0] = data + prevDC in int16, loadjpg.cpp:664-665);
+//   4. the final pass decodes, from the correct entry states, the blocks that start in each
+//      sub-sequence and writes every block once, in full, as one 128-byte line.
 // Output: the same dense [block][64] zig-zag int16 layout kernel 1a produces.
 #include "selfsync.cuh"
 #include "device_common.cuh"
@@ -207,7 +207,7 @@ cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, c
 }
 
 // ------------------------------------------------------------------------------------------
-// the sub-sequence decoder shared by the sync rounds and the final pass
+// the sub-sequence decoder of the synchronisation rounds
 // ------------------------------------------------------------------------------------------
 // state = bit position (40 bits) | zig-zag index (7 bits) << 40 | block-in-MCU index (4 bits) << 47
 #define SS_INVALID 0xFFFFFFFFFFFFFFFFull
@@ -219,6 +219,10 @@ struct SsCtx {
     uint32_t bpm, ny;
 };
 
+// What a sub-sequence contributes to the output layout: blocks that START inside it (a block belongs
+// to the sub-sequence in which its DC symbol begins) and the sums of their DC differences per component.
+struct SsCount { uint32_t ns, dc0, dc1, dc2; };
+
 __device__ __forceinline__ uint32_t ss_load_be32(const uint8_t* D, uint32_t bpos)
 {
     const uintptr_t a = (uintptr_t)(D + bpos);
@@ -227,12 +231,35 @@ __device__ __forceinline__ uint32_t ss_load_be32(const uint8_t* D, uint32_t bpos
     return __byte_perm(x, 0, 0x0123);
 }
 
-// Decode symbols from `state` until the bit position reaches end_bit (sync rounds) or, when WRITE,
-// until the image's last block is complete.  Same symbol semantics as kernel 1a / the reference
-// (loadjpg.cpp:559-829); an undecodable code consumes one bit so that every path makes progress.
-template <bool WRITE>
-__device__ __forceinline__ uint64_t ss_decode(const SsCtx& cx, uint64_t state, uint64_t end_bit, uint32_t* nb_out,
-                                              int16_t* coef_img, uint32_t blk0, uint32_t n_blocks, int* flags)
+// One Huffman symbol from the window (hi:lo): the fields of hjd_sym_fields plus the extended value.
+// An undecodable code consumes one bit (as a size-0 symbol) so that every path makes progress; the
+// synchronisation rounds and the write pass must agree on this rule, which is why they share this code.
+struct SsSym { uint32_t used, size, kadv; int val; bool bad; };
+
+__device__ __forceinline__ SsSym ss_symbol(uint32_t t, uint32_t hi, uint32_t lo, bool is_ac)
+{
+    SsSym s;
+    uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
+    s.bad = false;
+    if ((e & 31u) == 0) {
+        e = hjd_long_code(t, hi >> 16, is_ac);
+        if (e == 0) { e = hjd_sym_fields(1, 0, is_ac); s.bad = true; }
+    }
+    const uint32_t len = e & 31u;
+    s.size = (e >> 5) & 15u;
+    s.kadv = (e >> 9) & 127u;
+    const uint32_t after = __funnelshift_l(lo, hi, len);
+    const uint32_t v = hjd_shr(after, 32u - s.size);
+    const int neg = ~((int)after >> 31);
+    s.val = (int)v + (neg & (int)(hjd_shl(0xFFFFFFFFu, s.size) + 1u));       // DetermineSign, loadjpg.cpp:396-409
+    s.used = len + s.size;
+    return s;
+}
+
+// Decode symbols from `state` until the bit position reaches end_bit; returns the exit state.
+// COUNT: also count the blocks that start in [entry, end_bit) and sum their DC differences.
+template <bool COUNT>
+__device__ __forceinline__ uint64_t ss_scan_decode(const SsCtx& cx, uint64_t state, uint64_t end_bit, SsCount* cnt)
 {
     constexpr uint32_t kTabBytes = (uint32_t)sizeof(HjdHuffTable);
     uint64_t p = state & 0xFFFFFFFFFFull;
@@ -244,49 +271,39 @@ __device__ __forceinline__ uint64_t ss_decode(const SsCtx& cx, uint64_t state, u
     hi = __funnelshift_l(lo, hi, sh0);
     lo <<= sh0;
     int nbits = 64 - (int)sh0;
-    uint32_t nb = 0;
-    uint32_t tbase = cx.sh_tab + ((uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 2u : 4u)) * kTabBytes;
+    uint32_t comp = (uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 1u : 2u);
+    uint32_t tbase = cx.sh_tab + comp * 2u * kTabBytes;
+    uint32_t ns = 0, d0 = 0, d1 = 0, d2 = 0;
 
-    while (p < end_bit && (!WRITE || blk0 + nb < n_blocks)) {
+    while (p < end_bit) {
         if (nbits < 32) {
             const uint32_t w = ss_load_be32(cx.D, bpos);
             bpos += 4;
-            hi |= hjd_shr(w, (uint32_t)nbits);                 // nbits in [1, 31]
+            hi |= hjd_shr(w, (uint32_t)nbits);
             lo |= hjd_shl(w, 32u - (uint32_t)nbits);
             nbits += 32;
         }
-        const uint32_t is_ac = (uint32_t)min(k, 1);
-        const uint32_t t = tbase + is_ac * kTabBytes;
-        uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
-        if ((e & 31u) == 0) {
-            e = hjd_long_code(t, hi >> 16, is_ac != 0);
-            if (e == 0) { e = hjd_sym_fields(1, 0, is_ac != 0); *flags |= HJD_ST_BAD_CODE; }   // consume one bit
+        const bool is_ac = k != 0;
+        const SsSym s = ss_symbol(tbase + (is_ac ? kTabBytes : 0u), hi, lo, is_ac);
+        hi = __funnelshift_l(lo, hi, s.used);
+        lo <<= s.used;
+        nbits -= (int)s.used;
+        p += s.used;
+        if (COUNT && !is_ac) {
+            ns++;
+            d0 += comp == 0u ? (uint32_t)s.val : 0u;
+            d1 += comp == 1u ? (uint32_t)s.val : 0u;
+            d2 += comp == 2u ? (uint32_t)s.val : 0u;
         }
-        const uint32_t len = e & 31u, size = (e >> 5) & 15u, kadv = (e >> 9) & 127u;
-        const bool store = size != 0u;              // a size-0 DC difference adds nothing; the slab is pre-zeroed
-        const uint32_t after = __funnelshift_l(lo, hi, len);
-        const uint32_t v = hjd_shr(after, 32u - size);
-        const int neg = ~((int)after >> 31);
-        const int val = (int)v + (neg & (int)(hjd_shl(0xFFFFFFFFu, size) + 1u));     // DetermineSign, loadjpg.cpp:396-409
-        const uint32_t used = len + size;
-        hi = __funnelshift_l(lo, hi, used);
-        lo <<= used;
-        nbits -= (int)used;
-        p += used;
-        const uint32_t kpos = (uint32_t)k + kadv - 1u;
-        if (WRITE && store) {
-            if (kpos <= 63u) coef_img[(size_t)(blk0 + nb) * 64 + kpos] = (int16_t)val;   // DC: the difference
-            else *flags |= HJD_ST_COEF_RANGE;
-        }
-        k += (int)kadv;
+        k += (int)s.kadv;
         if (k >= 64) {
-            nb++;
             k = 0;
             c = (c + 1 == (int)cx.bpm) ? 0 : c + 1;
-            tbase = cx.sh_tab + ((uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 2u : 4u)) * kTabBytes;
+            comp = (uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 1u : 2u);
+            tbase = cx.sh_tab + comp * 2u * kTabBytes;
         }
     }
-    *nb_out = nb;
+    if (COUNT) { cnt->ns = ns; cnt->dc0 = d0; cnt->dc1 = d1; cnt->dc2 = d2; }
     return ss_pack(p, k, c);
 }
 
@@ -306,12 +323,20 @@ __device__ __forceinline__ void ss_load_tables(const HjdTableSet* ts, uint8_t* s
 // ------------------------------------------------------------------------------------------
 // steps 1-2: speculative decode + synchronisation rounds
 // ------------------------------------------------------------------------------------------
+// Round 0 (first = 1): every thread decodes the sub-sequence BEFORE its own from the fixed bit offset
+// (assuming a block starts there) and takes the state it arrives in as the entry state of its own
+// sub-sequence: after 1024 bits of Huffman data the decoder has almost surely synchronised, so most
+// entry states are already correct and independent of the neighbours.
+// Later rounds: a thread whose left neighbour's exit state differs from the entry state it used
+// re-decodes; inside a warp the neighbour state travels by warp shuffle and the round iterates until
+// the warp is stable, across warps it travels through HBM and the host repeats the round until no exit
+// state moves.  Sub-sequence 0 starts from the true state, so the fixed point is the sequential decode.
 __global__ void __launch_bounds__(HJD_SS_THREADS)
 hjd_k_ss_round(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
                const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
-               const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, int first,
+               const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, int first, uint32_t n_subs_total,
                const uint64_t* __restrict__ e_in, uint64_t* __restrict__ e_out, uint64_t* __restrict__ x_arr,
-               uint32_t* __restrict__ nb_arr, int* __restrict__ changed)
+               uint32_t* __restrict__ cnt_arr, int* __restrict__ changed)
 {
     extern __shared__ __align__(16) uint8_t s_tab[];
     const HjdSsWork wk = work[blockIdx.x];
@@ -330,157 +355,248 @@ hjd_k_ss_round(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     cx.sh_tab = (uint32_t)__cvta_generic_to_shared(s_tab);
     cx.bpm = d->blocks_per_mcu;
     cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
-    const uint64_t end_bit = (uint64_t)(li + 1) * HJD_SS_SUB_BYTES * 8;
+    const uint64_t sub_bits = (uint64_t)HJD_SS_SUB_BYTES * 8;
+    const uint64_t end_bit = (uint64_t)(li + 1) * sub_bits;
 
     uint64_t e = 0, x_used = SS_INVALID;
-    uint32_t nb = 0;
-    if (active && !first) { e = e_in[gi]; x_used = x_arr[gi]; nb = nb_arr[gi]; }
-    const uint64_t e_start = e;
-    // entry state that does not change during this launch: the true start, or (lane 0) the previous
-    // warp's exit state of the previous round, or the speculative guess of the very first pass
-    uint64_t x_fixed = ss_pack((uint64_t)li * HJD_SS_SUB_BYTES * 8, 0, 0);     // guess: a block starts here
-    if (li == 0) x_fixed = ss_pack(0, 0, 0);
-    else if (!first && active && lane == 0) x_fixed = e_in[gi - 1];
-    int flags = 0;
-
-    for (int iter = 0; iter < 33; iter++) {
-        const uint64_t from_left = __shfl_up_sync(0xffffffffu, e, 1);
-        uint64_t xin = x_fixed;
-        if (li != 0 && lane != 0 && !(first && iter == 0)) xin = from_left;
-        const bool need = active && xin != x_used;
-        if (need) {
-            e = ss_decode<false>(cx, xin, end_bit, &nb, nullptr, 0, 0, &flags);
-            x_used = xin;
+    SsCount cnt = {0, 0, 0, 0};
+    bool moved = false;
+    if (first) {
+        if (active) {
+            x_used = ss_pack(0, 0, 0);
+            if (li != 0) x_used = ss_scan_decode<false>(cx, ss_pack((uint64_t)(li - 1) * sub_bits, 0, 0), (uint64_t)li * sub_bits, nullptr);
+            e = ss_scan_decode<true>(cx, x_used, end_bit, &cnt);
+            moved = true;
         }
-        if (!__any_sync(0xffffffffu, need)) break;
+    } else {
+        if (active) {
+            e = e_in[gi]; x_used = x_arr[gi];
+            cnt.ns = cnt_arr[gi]; cnt.dc0 = cnt_arr[n_subs_total + gi];
+            cnt.dc1 = cnt_arr[2 * n_subs_total + gi]; cnt.dc2 = cnt_arr[3 * n_subs_total + gi];
+        }
+        const uint64_t e_start = e;
+        uint64_t x_fixed = ss_pack(0, 0, 0);                         // li == 0: the true start
+        if (li != 0 && active && lane == 0) x_fixed = e_in[gi - 1];  // previous warp: last round's exit state
+        for (int iter = 0; iter < 33; iter++) {
+            const uint64_t from_left = __shfl_up_sync(0xffffffffu, e, 1);
+            const uint64_t xin = (li != 0 && lane != 0) ? from_left : x_fixed;
+            const bool need = active && xin != x_used;
+            if (need) {
+                e = ss_scan_decode<true>(cx, xin, end_bit, &cnt);
+                x_used = xin;
+            }
+            if (!__any_sync(0xffffffffu, need)) break;
+        }
+        moved = active && e != e_start;
     }
     if (active) {
         e_out[gi] = e;
         x_arr[gi] = x_used;
-        nb_arr[gi] = nb;
-        if (first || e != e_start) *changed = 1;
+        cnt_arr[gi] = cnt.ns;
+        cnt_arr[n_subs_total + gi] = cnt.dc0;
+        cnt_arr[2 * n_subs_total + gi] = cnt.dc1;
+        cnt_arr[3 * n_subs_total + gi] = cnt.dc2;
+        if (moved) *changed = 1;
     } else if (li < s.n_subs) {
-        e_out[gi] = 0; x_arr[gi] = SS_INVALID; nb_arr[gi] = 0;
+        e_out[gi] = 0; x_arr[gi] = SS_INVALID;
+        cnt_arr[gi] = 0; cnt_arr[n_subs_total + gi] = 0; cnt_arr[2 * n_subs_total + gi] = 0; cnt_arr[3 * n_subs_total + gi] = 0;
     }
 }
 
 cudaError_t hjd_launch_ss_round(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
                                 const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                                int first, const uint64_t* e_in, uint64_t* e_out, uint64_t* x, uint32_t* nb,
-                                int* changed, cudaStream_t st)
+                                int first, uint32_t n_subs_total, const uint64_t* e_in, uint64_t* e_out, uint64_t* x,
+                                uint32_t* cnt, int* changed, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
     const size_t smem = 6 * sizeof(HjdHuffTable);
-    hjd_k_ss_round<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, first, e_in, e_out, x, nb, changed);
+    hjd_k_ss_round<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, first, n_subs_total,
+                                                        e_in, e_out, x, cnt, changed);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
 // step 4: final pass with output
 // ------------------------------------------------------------------------------------------
+// Every thread decodes the blocks that START in its sub-sequence, each to its end (running into the
+// next sub-sequence if need be), after skipping the tail of the block it was entered in the middle of
+// (that block belongs to an earlier thread).  So every 8x8 block is produced by exactly one thread, in
+// full, and leaves the SM as one 128-byte line through the same slot / list / four-at-a-time flush as
+// kernel 1a; the coefficient slab needs no zero-fill.  prefix[] = exclusive scan of the counts of the
+// last round: first owned block and, per component, the DC predictor at it
+// (DCT[0] = data + prevDC in int16, loadjpg.cpp:664-665).
+#define SS_WRITE_SYMS 4
+
 __global__ void __launch_bounds__(HJD_SS_THREADS)
 hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
                const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
-               const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen,
-               const uint64_t* __restrict__ x_arr, const uint32_t* __restrict__ first_block,
+               const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
+               const uint64_t* __restrict__ x_arr, const uint32_t* __restrict__ prefix,
                int16_t* __restrict__ coef, int32_t* __restrict__ status)
 {
-    extern __shared__ __align__(16) uint8_t s_tab[];
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    constexpr uint32_t kTabBytes = (uint32_t)sizeof(HjdHuffTable);
+    constexpr uint32_t kSlotBytes = HJD_SS_THREADS * 128, kListBytes = HJD_SS_THREADS * 8;
+    uint8_t* s_tab = s_raw + kSlotBytes + kListBytes;
     const HjdSsWork wk = work[blockIdx.x];
     const HjdSsImage s = ss[wk.ss];
     const HjdImageDesc* d = imgs + s.img;
     ss_load_tables(tsets + d->table_set, s_tab);
+    {
+        uint4* z = (uint4*)s_raw;
+        for (int i = threadIdx.x; i < HJD_SS_THREADS * 8; i += HJD_SS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
 
-    const uint32_t li = wk.first_sub + threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t sh_list = sh_base + kSlotBytes;
+    const uint32_t sh_tab = sh_list + kListBytes;
+    const uint32_t my_slot = sh_base + (uint32_t)tid * 128u;
+    const uint32_t swz = (uint32_t)(lane & 7) << 4;
+    const uint32_t warp_slots = sh_base + (uint32_t)(tid & ~31) * 128u;
+    const uint32_t warp_list = sh_list + (uint32_t)(tid & ~31) * 8u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    const uint32_t li = wk.first_sub + tid;
     const uint32_t L = dlen[wk.ss];
-    if (li >= s.n_subs || (uint64_t)li * HJD_SS_SUB_BYTES >= L) return;
-    const uint32_t gi = s.sub_base + li;
-    SsCtx cx;
-    cx.D = dst + s.dst_off;
-    cx.sh_tab = (uint32_t)__cvta_generic_to_shared(s_tab);
-    cx.bpm = d->blocks_per_mcu;
-    cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
-    const uint64_t end_bit = (uint64_t)(li + 1) * HJD_SS_SUB_BYTES * 8;
-    const uint32_t blk0 = first_block[gi] - first_block[s.sub_base];
+    const uint32_t bpm = d->blocks_per_mcu, ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
     const uint32_t n_blocks = (uint32_t)d->n_blocks;
-    int flags = 0;
-    uint32_t nb = 0;
-    const uint64_t xs = x_arr[gi];
-    if (xs == SS_INVALID) flags |= HJD_ST_BAD_CODE;                 // the rounds did not reach this sub-sequence
-    else ss_decode<true>(cx, xs, end_bit, &nb, coef + d->block_base * 64, blk0, n_blocks, &flags);
-    // the last sub-sequence that holds data must complete the image
-    const bool last = (li + 1 == s.n_subs) || ((uint64_t)(li + 1) * HJD_SS_SUB_BYTES >= L);
-    if (last && blk0 + nb < n_blocks) flags |= HJD_ST_OVERRUN;
+    const uint32_t blk_base = (uint32_t)d->block_base;
+    const uint8_t* D = dst + s.dst_off;
+    const uint64_t end_bit = (uint64_t)(li + 1) * HJD_SS_SUB_BYTES * 8;
+
+    bool finished = true;
+    bool owned = false;               // false while skipping the tail of a block entered in the middle
+    uint64_t p = 0;
+    int k = 0, c = 0;
+    uint32_t blk = 0;                 // image-local index of the block being decoded (when owned)
+    int p0 = 0, p1 = 0, p2 = 0;       // DC predictors, p0 = current component
+    uint32_t t0 = sh_tab, t1 = sh_tab + 2 * kTabBytes, t2 = sh_tab + 4 * kTabBytes;
+    uint32_t hi = 0, lo = 0, bpos = 0;
+    int nbits = 0, flags = 0;
+    if (li < s.n_subs && (uint64_t)li * HJD_SS_SUB_BYTES < L) {
+        const uint32_t gi = s.sub_base + li;
+        const uint64_t xs = x_arr[gi];
+        if (xs == SS_INVALID) flags |= HJD_ST_BAD_CODE;
+        else {
+            p = xs & 0xFFFFFFFFFFull;
+            k = (int)((xs >> 40) & 127u);
+            c = (int)((xs >> 47) & 15u);
+            blk = prefix[gi] - prefix[s.sub_base];
+            const int dY = (int)(short)(prefix[n_subs_total + gi] - prefix[n_subs_total + s.sub_base]);
+            const int dB = (int)(short)(prefix[2 * n_subs_total + gi] - prefix[2 * n_subs_total + s.sub_base]);
+            const int dR = (int)(short)(prefix[3 * n_subs_total + gi] - prefix[3 * n_subs_total + s.sub_base]);
+            const uint32_t comp = (uint32_t)c < ny ? 0u : ((uint32_t)c == ny ? 1u : 2u);
+            // rotate so that (p0, t0) belong to the component of block c
+            if (comp == 0) { p0 = dY; p1 = dB; p2 = dR; }
+            else if (comp == 1) { p0 = dB; p1 = dR; p2 = dY; t0 = sh_tab + 2 * kTabBytes; t1 = sh_tab + 4 * kTabBytes; t2 = sh_tab; }
+            else { p0 = dR; p1 = dY; p2 = dB; t0 = sh_tab + 4 * kTabBytes; t1 = sh_tab; t2 = sh_tab + 2 * kTabBytes; }
+            owned = (k == 0);
+            finished = (p >= end_bit) || (owned && blk >= n_blocks);
+            bpos = (uint32_t)(p >> 3);
+            hi = ss_load_be32(D, bpos); lo = ss_load_be32(D, bpos + 4);
+            bpos += 8;
+            const uint32_t sh0 = (uint32_t)p & 7u;
+            hi = __funnelshift_l(lo, hi, sh0);
+            lo <<= sh0;
+            nbits = 64 - (int)sh0;
+        }
+    }
+    const bool last_sub = (li + 1 == s.n_subs) || ((uint64_t)(li + 1) * HJD_SS_SUB_BYTES >= L);
+
+    while (__any_sync(0xffffffffu, !finished)) {
+        bool done_block = false;
+        if (!finished) {
+#pragma unroll
+            for (int rep = 0; rep < SS_WRITE_SYMS; rep++) {
+                if (!done_block && !finished) {
+                    if (nbits < 32) {
+                        const uint32_t w = ss_load_be32(D, bpos);
+                        bpos += 4;
+                        hi |= hjd_shr(w, (uint32_t)nbits);
+                        lo |= hjd_shl(w, 32u - (uint32_t)nbits);
+                        nbits += 32;
+                    }
+                    const bool is_ac = k != 0;
+                    const SsSym sy = ss_symbol(t0 + (is_ac ? kTabBytes : 0u), hi, lo, is_ac);
+                    if (sy.bad) flags |= HJD_ST_BAD_CODE;
+                    hi = __funnelshift_l(lo, hi, sy.used);
+                    lo <<= sy.used;
+                    nbits -= (int)sy.used;
+                    p += sy.used;
+                    const uint32_t kpos = (uint32_t)k + sy.kadv - 1u;
+                    if (owned && sy.size) {
+                        if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)sy.val);
+                        else flags |= HJD_ST_COEF_RANGE;
+                    }
+                    k += (int)sy.kadv;
+                    if (k >= 64) {
+                        if (owned) done_block = true;             // hand-over below
+                        else {                                    // the foreign block is over: the next one is mine
+                            owned = true;
+                            k = 0;
+                            if ((uint32_t)++c == bpm) c = 0;
+                            if (bpm > 1 && (c == 0 || (uint32_t)c >= ny)) {
+                                const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
+                                const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
+                            }
+                            if (p >= end_bit || blk >= n_blocks) finished = true;
+                        }
+                    } else if (!owned && p >= end_bit) {
+                        finished = true;                          // one block covers this whole sub-sequence
+                    }
+                }
+            }
+        }
+        // ---- block hand-over ---------------------------------------------------------------
+        uint32_t flush_blk = 0;
+        if (done_block) {
+            p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
+            hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
+            flush_blk = blk_base + blk;
+            blk++;
+            k = 0;
+            if ((uint32_t)++c == bpm) c = 0;
+            if (bpm > 1 && (c == 0 || (uint32_t)c >= ny)) {
+                const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
+                const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
+            }
+            if (p >= end_bit || blk >= n_blocks) finished = true;
+        }
+        // ---- cooperative flush, four blocks per step (as in kernel 1a) ----------------------
+        const uint32_t m = __ballot_sync(0xffffffffu, done_block);
+        if (m) {
+            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane);
+            __syncwarp();
+            const int n_done = __popc(m);
+            const uint32_t chunk = (uint32_t)lane & 7u;
+            for (int base = 0; base < n_done; base += 4) {
+                const int idx = base + (lane >> 3);
+                if (idx < n_done) {
+                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);
+                    const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
+                    const uint4 w = hjd_lds_v4_sync(src);
+                    hjd_sts_zero16_sync(src);
+                    ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // the last sub-sequence that holds data must have completed the image
+    if (last_sub && li < s.n_subs && (uint64_t)li * HJD_SS_SUB_BYTES < L && blk < n_blocks) flags |= HJD_ST_OVERRUN;
     if (flags) atomicOr(&status[s.img], flags);
 }
 
 cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
                                 const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                                const uint64_t* x, const uint32_t* first_block, int16_t* coef, int32_t* status,
-                                cudaStream_t st)
+                                uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
+                                int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    const size_t smem = 6 * sizeof(HjdHuffTable);
-    hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, x, first_block, coef, status);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
-// step 5: DC differences -> DC values
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-hjd_k_dc_sums(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __restrict__ ss, int n_ss,
-              uint32_t n_mcus_total, const int16_t* __restrict__ coef, uint32_t* __restrict__ sums)
-{
-    const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-    if (m >= n_mcus_total) return;
-    const HjdSsImage s = ss[ss_find<2>(ss, n_ss, m)];
-    const HjdImageDesc* d = imgs + s.img;
-    const uint32_t bpm = d->blocks_per_mcu, ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
-    const int16_t* c0 = coef + (d->block_base + (uint64_t)(m - s.mcu_base) * bpm) * 64;
-    uint32_t sy = 0;
-    for (uint32_t j = 0; j < ny; j++) sy += (uint32_t)(int)c0[(size_t)j * 64];
-    sums[m] = sy;
-    sums[n_mcus_total + m] = bpm > 1 ? (uint32_t)(int)c0[(size_t)ny * 64] : 0u;
-    sums[2 * n_mcus_total + m] = bpm > 1 ? (uint32_t)(int)c0[(size_t)(ny + 1) * 64] : 0u;
-}
-
-__global__ void __launch_bounds__(256)
-hjd_k_dc_apply(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __restrict__ ss, int n_ss,
-               uint32_t n_mcus_total, const uint32_t* __restrict__ prefix, int16_t* __restrict__ coef)
-{
-    const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-    if (m >= n_mcus_total) return;
-    const HjdSsImage s = ss[ss_find<2>(ss, n_ss, m)];
-    const HjdImageDesc* d = imgs + s.img;
-    const uint32_t bpm = d->blocks_per_mcu, ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
-    int16_t* c0 = coef + (d->block_base + (uint64_t)(m - s.mcu_base) * bpm) * 64;
-    uint32_t run = prefix[m] - prefix[s.mcu_base];                        // predictor before this MCU (mod 2^16 matters)
-    for (uint32_t j = 0; j < ny; j++) {
-        run += (uint32_t)(int)c0[(size_t)j * 64];
-        c0[(size_t)j * 64] = (int16_t)run;                                // DCT[0] = data + prevDC, loadjpg.cpp:664
-    }
-    if (bpm > 1) {
-        const uint32_t pb = prefix[n_mcus_total + m] - prefix[n_mcus_total + s.mcu_base];
-        const uint32_t pr = prefix[2 * n_mcus_total + m] - prefix[2 * n_mcus_total + s.mcu_base];
-        c0[(size_t)ny * 64] = (int16_t)(pb + (uint32_t)(int)c0[(size_t)ny * 64]);
-        c0[(size_t)(ny + 1) * 64] = (int16_t)(pr + (uint32_t)(int)c0[(size_t)(ny + 1) * 64]);
-    }
-}
-
-cudaError_t hjd_launch_dc_sums(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, uint32_t n_mcus_total,
-                               const int16_t* coef, uint32_t* sums, cudaStream_t st)
-{
-    if (n_ss <= 0 || n_mcus_total == 0) return cudaSuccess;
-    hjd_k_dc_sums<<<(n_mcus_total + 255) / 256, 256, 0, st>>>(imgs, ss, n_ss, n_mcus_total, coef, sums);
-    return cudaGetLastError();
-}
-
-cudaError_t hjd_launch_dc_apply(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, uint32_t n_mcus_total,
-                                const uint32_t* prefix, int16_t* coef, cudaStream_t st)
-{
-    if (n_ss <= 0 || n_mcus_total == 0) return cudaSuccess;
-    hjd_k_dc_apply<<<(n_mcus_total + 255) / 256, 256, 0, st>>>(imgs, ss, n_ss, n_mcus_total, prefix, coef);
+    const size_t smem = HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
+    hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, n_subs_total, x, prefix,
+                                                        coef, status);
     return cudaGetLastError();
 }

@@ -15,22 +15,16 @@ cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, c
 
 // One synchronisation round over all sub-sequences (first = 1: speculative decode from the fixed
 // bit offsets).  e_in/e_out: exit states (double buffered), x: entry state each exit was computed
-// from, nb: blocks completed inside each sub-sequence, changed: set to 1 when any exit state moved.
+// from, cnt: [4][n_subs_total] blocks started / DC-difference sums per component of each sub-sequence,
+// changed: set to 1 when any exit state moved.
 cudaError_t hjd_launch_ss_round(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
                                 const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                                int first, const uint64_t* e_in, uint64_t* e_out, uint64_t* x, uint32_t* nb,
-                                int* changed, cudaStream_t st);
+                                int first, uint32_t n_subs_total, const uint64_t* e_in, uint64_t* e_out, uint64_t* x,
+                                uint32_t* cnt, int* changed, cudaStream_t st);
 
-// Final pass: decode every sub-sequence from its (now correct) entry state and write the
-// coefficients (DC as differences) at block offsets first_block[] (exclusive scan of nb[]).
+// Final pass: every thread decodes, from its (now correct) entry state, the blocks that start in its
+// sub-sequence and writes them as whole 128-byte lines, DC un-differenced.  prefix = exclusive scan of cnt.
 cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
                                 const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                                const uint64_t* x, const uint32_t* first_block, int16_t* coef, int32_t* status,
-                                cudaStream_t st);
-
-// DC pass: per-MCU, per-component sums of the DC differences -> sums[3][n_mcus_total].
-cudaError_t hjd_launch_dc_sums(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, uint32_t n_mcus_total,
-                               const int16_t* coef, uint32_t* sums, cudaStream_t st);
-// ... and, after an exclusive scan of sums[], the un-differenced DC values written back.
-cudaError_t hjd_launch_dc_apply(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, uint32_t n_mcus_total,
-                                const uint32_t* prefix, int16_t* coef, cudaStream_t st);
+                                uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
+                                int32_t* status, cudaStream_t st);

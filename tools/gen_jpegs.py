@@ -101,9 +101,14 @@ def make_c5(i: int, restart: bool = True) -> bytes:
     return encode_jpeg(rgb, 75, "4:2:0", 8 if restart else 0, gray=(i % 2 == 0))
 
 
+def make_c2_restart_free(i: int) -> bytes:
+    """The restart-free twin of config-2 image i (same pixels, no DRI): what most real-world files look like."""
+    return make_c2(i, restart=False)
+
+
 def _job(args):
     kind, i = args
-    return {"c2": make_c2, "c5": make_c5}[kind](i)
+    return {"c2": make_c2, "c2nr": make_c2_restart_free, "c5": make_c5}[kind](i)
 
 
 def make_batch(kind: str, count: int, workers: int | None = None) -> list[bytes]:
