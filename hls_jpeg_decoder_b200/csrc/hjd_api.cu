@@ -116,7 +116,9 @@ struct hjd_batch {
     std::vector<HjdEntropyWork> work;
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
-    std::vector<HjdSsWork> sswork;
+    std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
+    size_t n_sswork_main = 0;            // entries of the first list
+    uint32_t ss_range = 0;               // sub-sequences per warp in the synchronisation rounds
     uint32_t ss_subs = 0, ss_chunks = 0, ss_mcus = 0;
     uint64_t ss_dst_bytes = 0;
     int ss_rounds = 0;                          // sync rounds of the last decode
@@ -131,7 +133,7 @@ struct hjd_batch {
     int launches = 0;
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_istart, d_coef, d_planes, d_rgb, d_status;
-    DevBuf d_ss, d_sswork, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssE1, d_ssX, d_ssnb, d_dcsums, d_flag;
+    DevBuf d_ss, d_sswork, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
     PinBuf h_meta, h_flag;
 };
 
@@ -201,8 +203,8 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release();
     b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
     b->d_ss.release(); b->d_sswork.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
-    b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssE1.release(); b->d_ssX.release(); b->d_ssnb.release();
-    b->d_dcsums.release(); b->d_flag.release();
+    b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
+    b->d_flag.release();
     b->h_meta.release(); b->h_flag.release();
     for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     for (int i = 0; i < 4; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
@@ -428,6 +430,14 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
     if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
+    // synchronisation rounds: longer ranges make the re-decode lists denser, shorter ones give more
+    // independent warps; pick by the amount of work.  Their work list is staged behind the first one.
+    b->n_sswork_main = b->sswork.size();
+    b->ss_range = b->ss_subs >= 400000 ? 256 : b->ss_subs >= 150000 ? 128 : 64;
+    for (size_t k = 0; k < b->ss.size(); k++)
+        for (uint32_t f = 0; f < b->ss[k].n_subs; f += HJD_SS_FIX_WARPS * b->ss_range)
+            b->sswork.push_back(HjdSsWork{(uint32_t)k, f});
+
     if (!b->ss.empty()) {
         uint32_t scan_n = b->ss_chunks + 1;
         if (b->ss_subs + 1 > scan_n) scan_n = b->ss_subs + 1;
@@ -439,7 +449,6 @@ static int upload_common(hjd_batch* b, bool chunked)
         CU(b->d_counts.ensure(sizeof(uint32_t) * ((size_t)b->ss_chunks + 2)));
         CU(b->d_scantmp.ensure(sizeof(uint32_t) * ((size_t)scan_n / 2048 + 4)));
         CU(b->d_ssE0.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
-        CU(b->d_ssE1.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssX.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssnb.ensure(sizeof(uint32_t) * (4 * (size_t)b->ss_subs + 4)));
         CU(b->d_flag.ensure(sizeof(int) * 4));
@@ -563,10 +572,12 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     const HjdTableSet* tsets = (const HjdTableSet*)b->d_tsets.p;
     const HjdSsImage* ss = (const HjdSsImage*)b->d_ss.p;
     const HjdSsWork* work = (const HjdSsWork*)b->d_sswork.p;
-    const int n_ss = (int)b->ss.size(), n_work = (int)b->sswork.size();
+    const int n_ss = (int)b->ss.size(), n_work = (int)b->n_sswork_main;
+    const HjdSsWork* work_fix = work + b->n_sswork_main;
+    const int n_work_fix = (int)(b->sswork.size() - b->n_sswork_main);
     uint8_t* dst = (uint8_t*)b->d_destuff.p;
     uint32_t* dlen = (uint32_t*)b->d_dlen.p;
-    uint64_t* E[2] = {(uint64_t*)b->d_ssE0.p, (uint64_t*)b->d_ssE1.p};
+    uint64_t* E = (uint64_t*)b->d_ssE0.p;
     uint64_t* X = (uint64_t*)b->d_ssX.p;
     uint32_t* cnt = (uint32_t*)b->d_ssnb.p;                       // [4][ss_subs] (+1): starts, DC sums Y/Cb/Cr
     int* flag = (int*)b->d_flag.p;
@@ -576,15 +587,14 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     CU(hjd_launch_destuff(arena, imgs, ss, n_ss, b->ss_chunks, (uint32_t*)b->d_counts.p, (uint32_t*)b->d_scantmp.p,
                           dst, dlen, st));
     b->launches += 2 + (b->ss_chunks + 1 > 2048 ? 3 : 1);
-    CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
-    CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 1, N, E[1], E[0], X, cnt, flag, st));
+    CU(hjd_launch_ss_spec(imgs, tsets, ss, work, n_work, dst, dlen, N, E, X, cnt, st));
     b->launches += 1;
     const int max_rounds = (int)(N / 32) + 8;
     int r = 1;
     for (;; r++) {
         if (r > max_rounds) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
         CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
-        CU(hjd_launch_ss_round(imgs, tsets, ss, work, n_work, dst, dlen, 0, N, E[(r - 1) & 1], E[r & 1], X, cnt, flag, st));
+        CU(hjd_launch_ss_fix(imgs, tsets, ss, work_fix, n_work_fix, dst, dlen, b->ss_range, N, E, X, cnt, flag, st));
         b->launches += 1;
         CU(cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -81,7 +81,9 @@ struct HjdEntropyWork {
 #define HJD_SS_SUB_BYTES   128          // sub-sequence length in (de-stuffed) bytes = 1024 bits
 #define HJD_SS_MIN_BYTES   1024         // restart-free scans shorter than this stay on the 1-thread path
 #define HJD_SS_SLACK       256          // zeroed bytes after every de-stuffed stream
-#define HJD_SS_THREADS     128
+#define HJD_SS_THREADS     256
+#define HJD_SS_FIX_WARPS   4     // warps per CTA of the synchronisation rounds, one range of sub-sequences each
+#define HJD_SS_FIX_MAXR    256   // largest range
 
 // One per image decoded by the self-synchronising kernels; all index spaces below are global
 // over the batch (sub-sequences, 16-byte de-stuffing chunks, MCUs).

@@ -223,13 +223,45 @@ struct SsCtx {
 // to the sub-sequence in which its DC symbol begins) and the sums of their DC differences per component.
 struct SsCount { uint32_t ns, dc0, dc1, dc2; };
 
-__device__ __forceinline__ uint32_t ss_load_be32(const uint8_t* D, uint32_t bpos)
-{
-    const uintptr_t a = (uintptr_t)(D + bpos);
-    const uint32_t* ap = (const uint32_t*)(a & ~(uintptr_t)3);
-    const uint32_t x = __funnelshift_r(__ldg(ap), __ldg(ap + 1), (uint32_t)(a & 3) * 8);
-    return __byte_perm(x, 0, 0x0123);
-}
+// Bit reader over the de-stuffed stream: a 64-bit window (hi:lo, MSB first, zero beyond nbits) fed by
+// aligned big-endian words that are loaded two refills ahead, so that the load latency stays off the
+// serial symbol-to-symbol dependence (what the synchronisation rounds, with few warps, are bound by).
+struct SsBits {
+    uint32_t hi, lo;
+    int nbits;
+    uint32_t wa, wb;            // the next two words
+    const uint32_t* wp;         // the word after them
+    __device__ __forceinline__ void init(const uint8_t* D, uint64_t p)
+    {
+        const uint32_t* w = (const uint32_t*)D + (p >> 5);           // D is 256-byte aligned
+        hi = __byte_perm(__ldg(w), 0, 0x0123);
+        lo = __byte_perm(__ldg(w + 1), 0, 0x0123);
+        wa = __byte_perm(__ldg(w + 2), 0, 0x0123);
+        wb = __byte_perm(__ldg(w + 3), 0, 0x0123);
+        wp = w + 4;
+        const uint32_t sh = (uint32_t)p & 31u;
+        hi = __funnelshift_l(lo, hi, sh);
+        lo <<= sh;
+        nbits = 64 - (int)sh;
+    }
+    // at least 32 valid bits afterwards (a symbol takes at most 16 + 15)
+    __device__ __forceinline__ void ensure()
+    {
+        if (nbits < 32) {                                            // lo holds no valid bit here
+            hi |= wa >> nbits;
+            lo = hjd_shl(wa, 32u - (uint32_t)nbits);
+            nbits += 32;
+            wa = wb;
+            wb = __byte_perm(__ldg(wp++), 0, 0x0123);
+        }
+    }
+    __device__ __forceinline__ void skip(uint32_t n)                 // n <= 31
+    {
+        hi = __funnelshift_l(lo, hi, n);
+        lo <<= n;
+        nbits -= (int)n;
+    }
+};
 
 // One Huffman symbol from the window (hi:lo): the fields of hjd_sym_fields plus the extended value.
 // An undecodable code consumes one bit (as a size-0 symbol) so that every path makes progress; the
@@ -262,33 +294,21 @@ template <bool COUNT>
 __device__ __forceinline__ uint64_t ss_scan_decode(const SsCtx& cx, uint64_t state, uint64_t end_bit, SsCount* cnt)
 {
     constexpr uint32_t kTabBytes = (uint32_t)sizeof(HjdHuffTable);
-    uint64_t p = state & 0xFFFFFFFFFFull;
+    const uint64_t p0 = state & 0xFFFFFFFFFFull;
     int k = (int)((state >> 40) & 127u), c = (int)((state >> 47) & 15u);
-    uint32_t bpos = (uint32_t)(p >> 3);
-    uint32_t hi = ss_load_be32(cx.D, bpos), lo = ss_load_be32(cx.D, bpos + 4);
-    bpos += 8;
-    const uint32_t sh0 = (uint32_t)p & 7u;
-    hi = __funnelshift_l(lo, hi, sh0);
-    lo <<= sh0;
-    int nbits = 64 - (int)sh0;
+    SsBits br;
+    br.init(cx.D, p0);
+    int rem = (int)(end_bit - p0);                       // bits left in the sub-sequence (entry is at most one behind)
     uint32_t comp = (uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 1u : 2u);
     uint32_t tbase = cx.sh_tab + comp * 2u * kTabBytes;
     uint32_t ns = 0, d0 = 0, d1 = 0, d2 = 0;
 
-    while (p < end_bit) {
-        if (nbits < 32) {
-            const uint32_t w = ss_load_be32(cx.D, bpos);
-            bpos += 4;
-            hi |= hjd_shr(w, (uint32_t)nbits);
-            lo |= hjd_shl(w, 32u - (uint32_t)nbits);
-            nbits += 32;
-        }
+    while (rem > 0) {
+        br.ensure();
         const bool is_ac = k != 0;
-        const SsSym s = ss_symbol(tbase + (is_ac ? kTabBytes : 0u), hi, lo, is_ac);
-        hi = __funnelshift_l(lo, hi, s.used);
-        lo <<= s.used;
-        nbits -= (int)s.used;
-        p += s.used;
+        const SsSym s = ss_symbol(tbase + (is_ac ? kTabBytes : 0u), br.hi, br.lo, is_ac);
+        br.skip(s.used);
+        rem -= (int)s.used;
         if (COUNT && !is_ac) {
             ns++;
             d0 += comp == 0u ? (uint32_t)s.val : 0u;
@@ -304,7 +324,7 @@ __device__ __forceinline__ uint64_t ss_scan_decode(const SsCtx& cx, uint64_t sta
         }
     }
     if (COUNT) { cnt->ns = ns; cnt->dc0 = d0; cnt->dc1 = d1; cnt->dc2 = d2; }
-    return ss_pack(p, k, c);
+    return ss_pack(end_bit - (uint64_t)(int64_t)rem, k, c);
 }
 
 // Loads the three per-component (DC, AC) table pairs of a table set into shared memory.
@@ -321,22 +341,19 @@ __device__ __forceinline__ void ss_load_tables(const HjdTableSet* ts, uint8_t* s
 }
 
 // ------------------------------------------------------------------------------------------
-// steps 1-2: speculative decode + synchronisation rounds
+// step 1: speculative decode
 // ------------------------------------------------------------------------------------------
-// Round 0 (first = 1): every thread decodes the sub-sequence BEFORE its own from the fixed bit offset
-// (assuming a block starts there) and takes the state it arrives in as the entry state of its own
-// sub-sequence: after 1024 bits of Huffman data the decoder has almost surely synchronised, so most
-// entry states are already correct and independent of the neighbours.
-// Later rounds: a thread whose left neighbour's exit state differs from the entry state it used
-// re-decodes; inside a warp the neighbour state travels by warp shuffle and the round iterates until
-// the warp is stable, across warps it travels through HBM and the host repeats the round until no exit
-// state moves.  Sub-sequence 0 starts from the true state, so the fixed point is the sequential decode.
+// Every thread decodes the sub-sequence BEFORE its own from the fixed bit offset (assuming a block
+// starts there) and takes the state it arrives in as the entry state of its own sub-sequence, which
+// it then decodes and counts.  About three quarters of the entry states are already right after
+// 1024 bits of lead-in (measured on 1080p 4:2:0: 23 % wrong, then 6 %, 1.5 %, ... per further
+// sub-sequence; the block-in-MCU index is what takes long to lock).  Sub-sequence 0 starts from the
+// true state.
 __global__ void __launch_bounds__(HJD_SS_THREADS)
-hjd_k_ss_round(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
-               const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
-               const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, int first, uint32_t n_subs_total,
-               const uint64_t* __restrict__ e_in, uint64_t* __restrict__ e_out, uint64_t* __restrict__ x_arr,
-               uint32_t* __restrict__ cnt_arr, int* __restrict__ changed)
+hjd_k_ss_spec(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
+              const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
+              const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
+              uint64_t* __restrict__ e_arr, uint64_t* __restrict__ x_arr, uint32_t* __restrict__ cnt_arr)
 {
     extern __shared__ __align__(16) uint8_t s_tab[];
     const HjdSsWork wk = work[blockIdx.x];
@@ -345,73 +362,145 @@ hjd_k_ss_round(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     ss_load_tables(tsets + d->table_set, s_tab);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
     const uint32_t li = wk.first_sub + threadIdx.x;                  // local sub-sequence index
+    if (li >= s.n_subs) return;
     const uint32_t L = dlen[wk.ss];
-    const bool active = li < s.n_subs && (uint64_t)li * HJD_SS_SUB_BYTES < L;
     const uint32_t gi = s.sub_base + li;
+    SsCount cnt = {0, 0, 0, 0};
+    uint64_t e = 0, x = SS_INVALID;
+    if ((uint64_t)li * HJD_SS_SUB_BYTES < L) {
+        SsCtx cx;
+        cx.D = dst + s.dst_off;
+        cx.sh_tab = (uint32_t)__cvta_generic_to_shared(s_tab);
+        cx.bpm = d->blocks_per_mcu;
+        cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
+        const uint64_t sub_bits = (uint64_t)HJD_SS_SUB_BYTES * 8;
+        x = ss_pack(0, 0, 0);
+        if (li != 0) x = ss_scan_decode<false>(cx, ss_pack((uint64_t)(li - 1) * sub_bits, 0, 0), (uint64_t)li * sub_bits, nullptr);
+        e = ss_scan_decode<true>(cx, x, (uint64_t)(li + 1) * sub_bits, &cnt);
+    }
+    e_arr[gi] = e;
+    x_arr[gi] = x;
+    cnt_arr[gi] = cnt.ns;
+    cnt_arr[n_subs_total + gi] = cnt.dc0;
+    cnt_arr[2 * n_subs_total + gi] = cnt.dc1;
+    cnt_arr[3 * n_subs_total + gi] = cnt.dc2;
+}
+
+cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                               const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                               uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt, cudaStream_t st)
+{
+    if (n_work <= 0) return cudaSuccess;
+    hjd_k_ss_spec<<<n_work, HJD_SS_THREADS, 6 * sizeof(HjdHuffTable), st>>>(imgs, tsets, ss, work, dst, dlen,
+                                                                           n_subs_total, e, x, cnt);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// step 2: synchronisation rounds
+// ------------------------------------------------------------------------------------------
+// One WARP owns `range` consecutive sub-sequences of one image (a CTA = HJD_SS_FIX_WARPS such warps
+// sharing the image's tables).  A sub-sequence whose left neighbour's exit state differs from the
+// entry state it was decoded from goes on the warp's list in shared memory; the list is decoded 32
+// entries at a time, so the few sub-sequences still wrong cost a few dense warp passes instead of one
+// mostly idle pass per 32 sub-sequences; repeat until the range is consistent.  The entry state of
+// the range's first sub-sequence is the previous range's last exit state, read from HBM: whichever
+// value the read returns (the previous round's or this round's), a range whose last exit state moved
+// raises `changed`, and the host repeats the round until nothing moves.  Sub-sequence 0 starts from
+// the true state, so the fixed point is the sequential decode.
+__global__ void __launch_bounds__(HJD_SS_FIX_WARPS * 32)
+hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
+             const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
+             const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t range, uint32_t n_subs_total,
+             uint64_t* __restrict__ e_arr, uint64_t* __restrict__ x_arr, uint32_t* __restrict__ cnt_arr,
+             int* __restrict__ changed)
+{
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    constexpr uint32_t kWarpBytes = HJD_SS_FIX_MAXR * 18;
+    uint8_t* s_tab = s_raw + HJD_SS_FIX_WARPS * kWarpBytes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* sE = (uint64_t*)(s_raw + warp * kWarpBytes);           // exit state per sub-sequence of the range
+    uint64_t* sX = sE + HJD_SS_FIX_MAXR;                             // entry state it was computed from
+    uint16_t* sL = (uint16_t*)(sX + HJD_SS_FIX_MAXR);                // sub-sequences to decode again
+    const HjdSsWork wk = work[blockIdx.x];
+    const HjdSsImage s = ss[wk.ss];
+    const HjdImageDesc* d = imgs + s.img;
+
+    const uint32_t L = dlen[wk.ss];
+    const uint32_t first = wk.first_sub + (uint32_t)warp * range;    // local index of the range's first sub-sequence
+    uint32_t n_have = (L + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES; // sub-sequences that hold data
+    if (n_have > s.n_subs) n_have = s.n_subs;
+    const int n_act = first < n_have ? (int)min(range, n_have - first) : 0;
+    const uint32_t g0 = s.sub_base + first;
+    for (int j = lane; j < n_act; j += 32) { sE[j] = e_arr[g0 + j]; sX[j] = x_arr[g0 + j]; }
+    uint64_t boundary = ss_pack(0, 0, 0), e_last_start = 0;
+    if (n_act) {
+        if (first != 0) boundary = e_arr[g0 - 1];
+        e_last_start = e_arr[g0 + n_act - 1];
+    }
+    __syncwarp();
+    bool any = false;
+    for (int j = lane; j < n_act; j += 32) any |= (j == 0 ? boundary : sE[j - 1]) != sX[j];
+    if (!__syncthreads_or(any)) return;                              // the usual case in the later rounds
+    ss_load_tables(tsets + d->table_set, s_tab);
+    __syncthreads();
+
     SsCtx cx;
     cx.D = dst + s.dst_off;
     cx.sh_tab = (uint32_t)__cvta_generic_to_shared(s_tab);
     cx.bpm = d->blocks_per_mcu;
     cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
     const uint64_t sub_bits = (uint64_t)HJD_SS_SUB_BYTES * 8;
-    const uint64_t end_bit = (uint64_t)(li + 1) * sub_bits;
-
-    uint64_t e = 0, x_used = SS_INVALID;
-    SsCount cnt = {0, 0, 0, 0};
-    bool moved = false;
-    if (first) {
-        if (active) {
-            x_used = ss_pack(0, 0, 0);
-            if (li != 0) x_used = ss_scan_decode<false>(cx, ss_pack((uint64_t)(li - 1) * sub_bits, 0, 0), (uint64_t)li * sub_bits, nullptr);
-            e = ss_scan_decode<true>(cx, x_used, end_bit, &cnt);
-            moved = true;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    bool stable = false;
+    for (int iter = 0; iter < n_act + 2; iter++) {
+        int n = 0;
+        for (int j0 = 0; j0 < n_act; j0 += 32) {
+            const int j = j0 + lane;
+            const bool need = j < n_act && (j == 0 ? boundary : sE[j - 1]) != sX[j];
+            const uint32_t bal = __ballot_sync(0xffffffffu, need);
+            if (need) sL[n + __popc(bal & lt_mask)] = (uint16_t)j;
+            n += __popc(bal);
         }
-    } else {
-        if (active) {
-            e = e_in[gi]; x_used = x_arr[gi];
-            cnt.ns = cnt_arr[gi]; cnt.dc0 = cnt_arr[n_subs_total + gi];
-            cnt.dc1 = cnt_arr[2 * n_subs_total + gi]; cnt.dc2 = cnt_arr[3 * n_subs_total + gi];
-        }
-        const uint64_t e_start = e;
-        uint64_t x_fixed = ss_pack(0, 0, 0);                         // li == 0: the true start
-        if (li != 0 && active && lane == 0) x_fixed = e_in[gi - 1];  // previous warp: last round's exit state
-        for (int iter = 0; iter < 33; iter++) {
-            const uint64_t from_left = __shfl_up_sync(0xffffffffu, e, 1);
-            const uint64_t xin = (li != 0 && lane != 0) ? from_left : x_fixed;
-            const bool need = active && xin != x_used;
-            if (need) {
-                e = ss_scan_decode<true>(cx, xin, end_bit, &cnt);
-                x_used = xin;
+        __syncwarp();
+        if (n == 0) { stable = true; break; }
+        for (int q0 = 0; q0 < n; q0 += 32) {
+            int t = -1;
+            uint64_t txin = 0;
+            if (q0 + lane < n) {
+                t = sL[q0 + lane];
+                txin = t == 0 ? boundary : sE[t - 1];
             }
-            if (!__any_sync(0xffffffffu, need)) break;
+            __syncwarp();                                            // entry states read before any is rewritten
+            if (t >= 0) {
+                SsCount cnt;
+                const uint64_t te = ss_scan_decode<true>(cx, txin, (uint64_t)(first + t + 1) * sub_bits, &cnt);
+                const uint32_t g = g0 + (uint32_t)t;
+                cnt_arr[g] = cnt.ns;
+                cnt_arr[n_subs_total + g] = cnt.dc0;
+                cnt_arr[2 * n_subs_total + g] = cnt.dc1;
+                cnt_arr[3 * n_subs_total + g] = cnt.dc2;
+                sE[t] = te;
+                sX[t] = txin;
+            }
+            __syncwarp();
         }
-        moved = active && e != e_start;
     }
-    if (active) {
-        e_out[gi] = e;
-        x_arr[gi] = x_used;
-        cnt_arr[gi] = cnt.ns;
-        cnt_arr[n_subs_total + gi] = cnt.dc0;
-        cnt_arr[2 * n_subs_total + gi] = cnt.dc1;
-        cnt_arr[3 * n_subs_total + gi] = cnt.dc2;
-        if (moved) *changed = 1;
-    } else if (li < s.n_subs) {
-        e_out[gi] = 0; x_arr[gi] = SS_INVALID;
-        cnt_arr[gi] = 0; cnt_arr[n_subs_total + gi] = 0; cnt_arr[2 * n_subs_total + gi] = 0; cnt_arr[3 * n_subs_total + gi] = 0;
-    }
+    for (int j = lane; j < n_act; j += 32) { e_arr[g0 + j] = sE[j]; x_arr[g0 + j] = sX[j]; }
+    if (lane == 0 && n_act && (!stable || sE[n_act - 1] != e_last_start)) *changed = 1;
 }
 
-cudaError_t hjd_launch_ss_round(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                                const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                                int first, uint32_t n_subs_total, const uint64_t* e_in, uint64_t* e_out, uint64_t* x,
-                                uint32_t* cnt, int* changed, cudaStream_t st)
+cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                              const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                              uint32_t range, uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
+                              int* changed, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    const size_t smem = 6 * sizeof(HjdHuffTable);
-    hjd_k_ss_round<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, first, n_subs_total,
-                                                        e_in, e_out, x, cnt, changed);
+    if (range == 0 || range > HJD_SS_FIX_MAXR || (range & 31u)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)HJD_SS_FIX_WARPS * HJD_SS_FIX_MAXR * 18 + 6 * sizeof(HjdHuffTable);
+    hjd_k_ss_fix<<<n_work, HJD_SS_FIX_WARPS * 32, smem, st>>>(imgs, tsets, ss, work, dst, dlen, range, n_subs_total,
+                                                             e, x, cnt, changed);
     return cudaGetLastError();
 }
 
@@ -468,19 +557,21 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
 
     bool finished = true;
     bool owned = false;               // false while skipping the tail of a block entered in the middle
-    uint64_t p = 0;
+    int rem = 0;                      // bits left in the sub-sequence (<= 0: past its end)
     int k = 0, c = 0;
     uint32_t blk = 0;                 // image-local index of the block being decoded (when owned)
     int p0 = 0, p1 = 0, p2 = 0;       // DC predictors, p0 = current component
     uint32_t t0 = sh_tab, t1 = sh_tab + 2 * kTabBytes, t2 = sh_tab + 4 * kTabBytes;
-    uint32_t hi = 0, lo = 0, bpos = 0;
-    int nbits = 0, flags = 0;
+    SsBits br;
+    br.hi = br.lo = br.wa = br.wb = 0; br.nbits = 64; br.wp = (const uint32_t*)D;
+    int flags = 0;
     if (li < s.n_subs && (uint64_t)li * HJD_SS_SUB_BYTES < L) {
         const uint32_t gi = s.sub_base + li;
         const uint64_t xs = x_arr[gi];
         if (xs == SS_INVALID) flags |= HJD_ST_BAD_CODE;
         else {
-            p = xs & 0xFFFFFFFFFFull;
+            const uint64_t p = xs & 0xFFFFFFFFFFull;
+            rem = (int)(end_bit - p);
             k = (int)((xs >> 40) & 127u);
             c = (int)((xs >> 47) & 15u);
             blk = prefix[gi] - prefix[s.sub_base];
@@ -493,14 +584,8 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
             else if (comp == 1) { p0 = dB; p1 = dR; p2 = dY; t0 = sh_tab + 2 * kTabBytes; t1 = sh_tab + 4 * kTabBytes; t2 = sh_tab; }
             else { p0 = dR; p1 = dY; p2 = dB; t0 = sh_tab + 4 * kTabBytes; t1 = sh_tab; t2 = sh_tab + 2 * kTabBytes; }
             owned = (k == 0);
-            finished = (p >= end_bit) || (owned && blk >= n_blocks);
-            bpos = (uint32_t)(p >> 3);
-            hi = ss_load_be32(D, bpos); lo = ss_load_be32(D, bpos + 4);
-            bpos += 8;
-            const uint32_t sh0 = (uint32_t)p & 7u;
-            hi = __funnelshift_l(lo, hi, sh0);
-            lo <<= sh0;
-            nbits = 64 - (int)sh0;
+            finished = (rem <= 0) || (owned && blk >= n_blocks);
+            br.init(D, p);
         }
     }
     const bool last_sub = (li + 1 == s.n_subs) || ((uint64_t)(li + 1) * HJD_SS_SUB_BYTES >= L);
@@ -511,20 +596,12 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
 #pragma unroll
             for (int rep = 0; rep < SS_WRITE_SYMS; rep++) {
                 if (!done_block && !finished) {
-                    if (nbits < 32) {
-                        const uint32_t w = ss_load_be32(D, bpos);
-                        bpos += 4;
-                        hi |= hjd_shr(w, (uint32_t)nbits);
-                        lo |= hjd_shl(w, 32u - (uint32_t)nbits);
-                        nbits += 32;
-                    }
+                    br.ensure();
                     const bool is_ac = k != 0;
-                    const SsSym sy = ss_symbol(t0 + (is_ac ? kTabBytes : 0u), hi, lo, is_ac);
+                    const SsSym sy = ss_symbol(t0 + (is_ac ? kTabBytes : 0u), br.hi, br.lo, is_ac);
                     if (sy.bad) flags |= HJD_ST_BAD_CODE;
-                    hi = __funnelshift_l(lo, hi, sy.used);
-                    lo <<= sy.used;
-                    nbits -= (int)sy.used;
-                    p += sy.used;
+                    br.skip(sy.used);
+                    rem -= (int)sy.used;
                     const uint32_t kpos = (uint32_t)k + sy.kadv - 1u;
                     if (owned && sy.size) {
                         if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)sy.val);
@@ -541,9 +618,9 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                                 const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
                                 const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
                             }
-                            if (p >= end_bit || blk >= n_blocks) finished = true;
+                            if (rem <= 0 || blk >= n_blocks) finished = true;
                         }
-                    } else if (!owned && p >= end_bit) {
+                    } else if (!owned && rem <= 0) {
                         finished = true;                          // one block covers this whole sub-sequence
                     }
                 }
@@ -562,7 +639,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                 const int tp = p0; p0 = p1; p1 = p2; p2 = tp;
                 const uint32_t tt = t0; t0 = t1; t1 = t2; t2 = tt;
             }
-            if (p >= end_bit || blk >= n_blocks) finished = true;
+            if (rem <= 0 || blk >= n_blocks) finished = true;
         }
         // ---- cooperative flush, four blocks per step (as in kernel 1a) ----------------------
         const uint32_t m = __ballot_sync(0xffffffffu, done_block);
@@ -596,6 +673,12 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
 {
     if (n_work <= 0) return cudaSuccess;
     const size_t smem = HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(hjd_k_ss_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, n_subs_total, x, prefix,
                                                         coef, status);
     return cudaGetLastError();

@@ -13,14 +13,20 @@ cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, c
                                uint32_t n_chunks_total, uint32_t* counts, uint32_t* scan_tmp,
                                uint8_t* dst, uint32_t* dlen, cudaStream_t st);
 
-// One synchronisation round over all sub-sequences (first = 1: speculative decode from the fixed
-// bit offsets).  e_in/e_out: exit states (double buffered), x: entry state each exit was computed
-// from, cnt: [4][n_subs_total] blocks started / DC-difference sums per component of each sub-sequence,
-// changed: set to 1 when any exit state moved.
-cudaError_t hjd_launch_ss_round(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                                const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                                int first, uint32_t n_subs_total, const uint64_t* e_in, uint64_t* e_out, uint64_t* x,
-                                uint32_t* cnt, int* changed, cudaStream_t st);
+// Speculative decode of every sub-sequence (one CTA per `work` entry, HJD_SS_THREADS sub-sequences).
+// e: exit states, x: the entry state each exit was computed from, cnt: [4][n_subs_total] blocks
+// started / DC-difference sums per component of each sub-sequence.
+cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                               const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                               uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt, cudaStream_t st);
+
+// One synchronisation round, in place.  `work` here has one entry per HJD_SS_FIX_WARPS * range
+// sub-sequences (range: multiple of 32, <= HJD_SS_FIX_MAXR).  changed is set to 1 when the last exit
+// state of any range moved.
+cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                              const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                              uint32_t range, uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
+                              int* changed, cudaStream_t st);
 
 // Final pass: every thread decodes, from its (now correct) entry state, the blocks that start in its
 // sub-sequence and writes them as whole 128-byte lines, DC un-differenced.  prefix = exclusive scan of cnt.
