@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=0, help="images per GPU (default: 1024 for c2, 1 for c4, 8192 for c5)")
-    ap.add_argument("--config", default="c2", choices=["c2", "c2nr", "c4", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c2nr", "c2q50", "c2q95", "c4", "c5"],
                     help="BASELINE.json workload: c2 = 1080p 4:2:0 Ri=8 batch (headline), c4 = one 8192x8192 4:4:4 "
                          "restart-free image, c5 = 256x256 gray/4:2:0 thumbnails")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -65,6 +65,8 @@ def measured_peak():
 WORKLOADS = {
     "c2": dict(n=1024, w=1920, h=1080, desc="synthetic 1920x1080 4:2:0 baseline JPEGs, q85, restart interval 8 MCUs (BASELINE.json configs[1])"),
     "c2nr": dict(n=1024, w=1920, h=1080, desc="synthetic 1920x1080 4:2:0 baseline JPEGs, q85, NO restart markers (restart-free twins of configs[1]): self-synchronising path"),
+    "c2q50": dict(n=1024, w=1920, h=1080, desc="synthetic 1920x1080 4:2:0 baseline JPEGs, q50, restart interval 8 MCUs (quality sensitivity of configs[1])"),
+    "c2q95": dict(n=1024, w=1920, h=1080, desc="synthetic 1920x1080 4:2:0 baseline JPEGs, q95, restart interval 8 MCUs (quality sensitivity of configs[1])"),
     "c4": dict(n=1, w=8192, h=8192, desc="one synthetic 8192x8192 4:4:4 baseline JPEG, q85, no restart markers: self-synchronising path (BASELINE.json configs[3])"),
     "c5": dict(n=8192, w=256, h=256, desc="synthetic 256x256 thumbnails, even = grayscale, odd = 4:2:0, q75, restart interval 8 MCUs (BASELINE.json configs[4], per-GPU share)"),
 }

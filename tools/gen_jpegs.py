@@ -87,9 +87,9 @@ def synth_rgb_fast(width: int, height: int, i: int, noise_sigma: float = 6.0) ->
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def make_c2(i: int, restart: bool = True, width: int = 1920, height: int = 1080) -> bytes:
+def make_c2(i: int, restart: bool = True, width: int = 1920, height: int = 1080, quality: int = 85) -> bytes:
     """Config 2/3 image i (and, with restart=False, its restart-free twin: same pixels)."""
-    return encode_jpeg(synth_rgb_fast(width, height, i), 85, "4:2:0", 8 if restart else 0)
+    return encode_jpeg(synth_rgb_fast(width, height, i), quality, "4:2:0", 8 if restart else 0)
 
 
 def make_c4(size: int = 8192, seed: int = 4) -> bytes:
@@ -106,9 +106,20 @@ def make_c2_restart_free(i: int) -> bytes:
     return make_c2(i, restart=False)
 
 
+def make_c2_q50(i: int) -> bytes:
+    """Quality sensitivity of config 2: same pixels at q50 (about 0.4x the scan bytes)."""
+    return make_c2(i, quality=50)
+
+
+def make_c2_q95(i: int) -> bytes:
+    """Quality sensitivity of config 2: same pixels at q95 (about 2.4x the scan bytes)."""
+    return make_c2(i, quality=95)
+
+
 def _job(args):
     kind, i = args
-    return {"c2": make_c2, "c2nr": make_c2_restart_free, "c5": make_c5}[kind](i)
+    return {"c2": make_c2, "c2nr": make_c2_restart_free, "c2q50": make_c2_q50, "c2q95": make_c2_q95,
+            "c5": make_c5}[kind](i)
 
 
 def make_batch(kind: str, count: int, workers: int | None = None) -> list[bytes]:
