@@ -86,6 +86,7 @@ _SIGS = {
     "hjd_batch_decode": (c_int, [c_void_p]),
     "hjd_batch_sync": (c_int, [c_void_p]),
     "hjd_batch_set_overlap": (c_int, [c_void_p, c_int]),
+    "hjd_batch_set_selfsync_range": (c_int, [c_void_p, c_int]),
     "hjd_batch_num_images": (c_int, [c_void_p]),
     "hjd_batch_selfsync_rounds": (c_int, [c_void_p]),
     "hjd_batch_get_info": (c_int, [c_void_p, c_int, POINTER(ImageInfo)]),
@@ -293,6 +294,11 @@ class BatchDecoder:
         """Chunked multi-stream execution: 0/False = one stream (per-stage timings valid), 1/True =
         default chunking, n > 1 = target blocks per chunk.  Takes effect at the next upload."""
         _check(lib().hjd_batch_set_overlap(self._h, int(on)), "hjd_batch_set_overlap")
+
+    def set_selfsync_range(self, rng: int) -> None:
+        """Sub-sequences per warp in the synchronisation rounds of the restart-free path (0 = automatic).
+        Results do not depend on it; takes effect at the next upload."""
+        _check(lib().hjd_batch_set_selfsync_range(self._h, int(rng)), "hjd_batch_set_selfsync_range")
 
     def mark(self, slot: int) -> None:
         _check(lib().hjd_batch_mark(self._h, slot), "hjd_batch_mark")

@@ -119,6 +119,7 @@ struct hjd_batch {
     std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
     size_t n_sswork_main = 0;            // entries of the first list
     uint32_t ss_range = 0;               // sub-sequences per warp in the synchronisation rounds
+    uint32_t ss_range_req = 0;           // 0 = automatic
     uint32_t ss_subs = 0, ss_chunks = 0, ss_mcus = 0;
     uint64_t ss_dst_bytes = 0;
     int ss_rounds = 0;                          // sync rounds of the last decode
@@ -433,7 +434,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     // synchronisation rounds: longer ranges make the re-decode lists denser, shorter ones give more
     // independent warps; pick by the amount of work.  Their work list is staged behind the first one.
     b->n_sswork_main = b->sswork.size();
-    b->ss_range = b->ss_subs >= 400000 ? 256 : b->ss_subs >= 150000 ? 128 : 64;
+    b->ss_range = b->ss_range_req ? b->ss_range_req : b->ss_subs >= 400000 ? 256 : b->ss_subs >= 150000 ? 128 : 64;
     for (size_t k = 0; k < b->ss.size(); k++)
         for (uint32_t f = 0; f < b->ss[k].n_subs; f += HJD_SS_FIX_WARPS * b->ss_range)
             b->sswork.push_back(HjdSsWork{(uint32_t)k, f});
@@ -559,6 +560,15 @@ extern "C" int hjd_batch_set_overlap(hjd_batch* b, int on)
 {
     if (!b) return fail(HJD_ERR_ARG, "hjd_batch_set_overlap", "null batch");
     b->overlap = on < 0 ? 0 : on;     // 0 serial, 1 default chunking, > 1: target blocks per chunk; next upload
+    return HJD_OK;
+}
+
+extern "C" int hjd_batch_set_selfsync_range(hjd_batch* b, int range)
+{
+    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_set_selfsync_range", "null batch");
+    if (range < 0 || range > HJD_SS_FIX_MAXR || (range & 31))
+        return fail(HJD_ERR_ARG, "hjd_batch_set_selfsync_range", "range must be 0 or a multiple of 32 up to 256");
+    b->ss_range_req = (uint32_t)range;
     return HJD_OK;
 }
 

@@ -145,6 +145,9 @@ int  hjd_batch_set_overlap(hjd_batch* b, int on);
 
 /* Synchronisation rounds the self-synchronising kernel (restart-free scans) needed in the last decode. */
 int  hjd_batch_selfsync_rounds(const hjd_batch* b);
+/* Sub-sequences per warp in those rounds: 0 = pick by batch size (default), else a multiple of 32 up
+ * to 256 (testing / tuning; results do not depend on it).  Takes effect at the next upload. */
+int  hjd_batch_set_selfsync_range(hjd_batch* b, int range);
 int  hjd_batch_num_images(const hjd_batch* b);
 int  hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* out);
 int  hjd_batch_get_status(hjd_batch* b, int32_t* status /* n */);   /* syncs */

@@ -295,6 +295,34 @@ def test_selfsync_large_scan(hjd, port):
         assert d.selfsync_rounds <= 6, d.selfsync_rounds
 
 
+def test_selfsync_ranges_and_twins(hjd, port):
+    """Restart-free 1080p twins of config 2 (the stream shape the fix-up rounds were tuned on): every
+    range length of the synchronisation rounds gives the coefficients of the restart twins (decoded by
+    kernel 1a), and image 0 matches the oracle."""
+    from tools.gen_jpegs import make_c2
+    n = 6
+    twins = [make_c2(i, restart=False) for i in range(n)]
+    with hjd.BatchDecoder(0) as d:
+        d.upload([make_c2(i, restart=True) for i in range(n)])
+        d.decode()
+        assert (d.status() == 0).all()
+        want = d.coefficients().copy()
+        want_rgb = d.rgb_slab().copy()
+        for rng in (0, 32, 64, 128, 256):
+            d.set_selfsync_range(rng)
+            d.upload(twins)
+            d.decode()
+            assert (d.status() == 0).all(), (rng, d.status())
+            assert d.selfsync_rounds >= 2
+            assert np.array_equal(d.coefficients(), want), rng
+            assert np.array_equal(d.rgb_slab(), want_rgb), rng
+        o = port.decode(twins[0])
+        assert np.array_equal(d.image_coefficients(0), o["coef"])
+        assert np.array_equal(d.rgb(0), o["rgb"])
+        with pytest.raises(Exception):
+            d.set_selfsync_range(48)
+
+
 def _patch_component_ids(jpg: bytes, ids):
     """Rewrite the component identifiers in SOF0 and SOS (the reference indexes arrays with them,
     openjpg.cpp:212-213,343-345, so it only works for 1,2,3)."""
