@@ -615,7 +615,8 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     CU(hjd_scan_u32(cnt, 4 * N + 1, (uint32_t*)b->d_scantmp.p, st));              // cnt[] becomes its exclusive prefix
     CU(hjd_launch_ss_write(imgs, tsets, ss, work, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
                            (int32_t*)b->d_status.p, st));
-    b->launches += 1 + (4 * N + 1 > 2048 ? 3 : 1);
+    CU(hjd_launch_ss_fill_tail(imgs, ss, n_ss, cnt, (int16_t*)b->d_coef.p, st));
+    b->launches += 2 + (4 * N + 1 > 2048 ? 3 : 1);
     return HJD_OK;
 }
 

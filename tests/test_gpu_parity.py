@@ -323,6 +323,53 @@ def test_selfsync_ranges_and_twins(hjd, port):
             d.set_selfsync_range(48)
 
 
+@pytest.mark.timeout(600)
+def test_selfsync_damaged_scans_are_deterministic(hjd):
+    """Truncated and corrupted restart-free scans through kernel 1b: the call returns with a per-image
+    warning, good neighbours are untouched, and the output depends on the input alone (blocks the
+    scan never reached are zero, whatever the slab held before)."""
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    rng = np.random.default_rng(7)
+    good = encode_jpeg(synth_rgb(640, 480, 51), 85, "4:2:0")
+    other = encode_jpeg(cases.noise_rgb(640, 480, 52), 95, "4:4:4")
+    eoi = good[-2:]
+    bad = [good[:len(good) * 2 // 5] + eoi,                    # truncated at 40 %
+           good[:len(good) - 700] + eoi]                       # truncated inside the last sub-sequences
+    for k in range(6):                                         # random damage inside the scan
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(len(b) // 3, len(b) - 2))
+            mode = int(rng.integers(0, 3))
+            if mode == 0:
+                b[pos] = int(rng.integers(0, 256))
+            elif mode == 1:
+                b[pos:pos + 2] = b"\xff\x00"
+            else:
+                del b[pos:pos + int(rng.integers(1, 300))]
+        bad.append(bytes(b))
+    with hjd.BatchDecoder(0) as d:
+        d.upload([good])
+        d.decode()
+        want = d.rgb(0).copy()
+        outs = []
+        for rep in range(2):
+            d.upload([other, other, other])                    # different content in the slabs in between
+            d.decode()
+            files = [good] + bad + [good]
+            d.upload(files)
+            d.decode()
+            st = d.status()
+            assert st[0] == 0 and st[-1] == 0, st
+            assert st[1] > 0 and (st[1] & 4), st                # HJD_IMG_WARN_OVERRUN on the truncated one
+            assert np.array_equal(d.rgb(0), want) and np.array_equal(d.rgb(len(files) - 1), want)
+            outs.append((st.copy(), d.coefficients().copy()))
+        assert np.array_equal(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1], outs[1][1])
+        inf = d.info(1)
+        tail = d.image_coefficients(1, outs[1][1])[inf.n_blocks * 3 // 5:]
+        assert not tail.any()
+
+
 def _patch_component_ids(jpg: bytes, ids):
     """Rewrite the component identifiers in SOF0 and SOS (the reference indexes arrays with them,
     openjpg.cpp:212-213,343-345, so it only works for 1,2,3)."""
