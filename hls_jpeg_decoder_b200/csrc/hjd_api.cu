@@ -120,7 +120,7 @@ struct hjd_batch {
     size_t n_sswork_main = 0;            // entries of the first list
     uint32_t ss_range = 0;               // sub-sequences per warp in the synchronisation rounds
     uint32_t ss_range_req = 0;           // 0 = automatic
-    uint32_t ss_subs = 0, ss_chunks = 0, ss_mcus = 0;
+    uint32_t ss_subs = 0, ss_chunks = 0;
     uint64_t ss_dst_bytes = 0;
     int ss_rounds = 0;                          // sync rounds of the last decode
     std::vector<uint8_t> host_restart_warn;     // HJD_FLAG_HOST_SCAN only
@@ -241,7 +241,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
     b->ss.clear(); b->sswork.clear();
-    b->ss_subs = b->ss_chunks = b->ss_mcus = 0;
+    b->ss_subs = b->ss_chunks = 0;
     b->ss_dst_bytes = 0;
     b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
     b->total_intervals = b->max_blocks = b->max_w = b->max_h = b->max_strips = 0;
@@ -308,7 +308,6 @@ static int upload_common(hjd_batch* b, bool chunked)
             si.lead = (uint32_t)(d.scan_off & 15);
             si.chunk_base = b->ss_chunks;
             si.n_chunks = (uint32_t)((ps.scan_len + si.lead + 15) / 16);
-            si.mcu_base = b->ss_mcus;
             si.dst_off = b->ss_dst_bytes;
             d.n_intervals = 0;
             d.sub_base = si.sub_base;
@@ -317,7 +316,6 @@ static int upload_common(hjd_batch* b, bool chunked)
             b->ss.push_back(si);
             b->ss_subs += si.n_subs;
             b->ss_chunks += si.n_chunks;
-            b->ss_mcus += d.n_mcus;
             b->ss_dst_bytes += align_up(ps.scan_len + HJD_SS_SLACK, 256);
         }
         d.table_set = tset; d.quant_set = qset;

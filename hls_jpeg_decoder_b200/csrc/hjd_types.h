@@ -86,20 +86,19 @@ struct HjdEntropyWork {
 #define HJD_SS_FIX_MAXR    256   // largest range
 
 // One per image decoded by the self-synchronising kernels; all index spaces below are global
-// over the batch (sub-sequences, 16-byte de-stuffing chunks, MCUs).
+// over the batch (sub-sequences, 16-byte de-stuffing chunks).
 struct HjdSsImage {
     uint32_t img;          // image index in the batch
     uint32_t sub_base;     // first sub-sequence
     uint32_t n_subs;
     uint32_t chunk_base;   // first 16-byte chunk of the (16-byte aligned) stuffed scan
     uint32_t n_chunks;
-    uint32_t mcu_base;     // first MCU (DC prefix pass)
     uint32_t lead;         // bytes between the aligned chunk origin and the first scan byte
-    uint32_t pad;
     uint64_t dst_off;      // offset of the de-stuffed stream in the de-stuff buffer
 };
 
-// One CTA of the sync / write kernels: HJD_SS_THREADS consecutive sub-sequences of one image.
+// One CTA of the speculative / write kernels (HJD_SS_THREADS consecutive sub-sequences of one image)
+// or of the synchronisation rounds (HJD_SS_FIX_WARPS ranges of sub-sequences).
 struct HjdSsWork {
     uint32_t ss;           // index into the HjdSsImage array
     uint32_t first_sub;    // local index of the CTA's first sub-sequence

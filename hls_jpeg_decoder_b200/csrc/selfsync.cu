@@ -114,15 +114,13 @@ cudaError_t hjd_scan_u32(uint32_t* data, uint32_t n, uint32_t* tmp, cudaStream_t
 // ------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------
-// Index of the HjdSsImage whose [base, base + count) range (selected by FIELD) contains key.
-template <int FIELD>   // 0: sub-sequences, 1: chunks, 2: MCUs
-__device__ __forceinline__ int ss_find(const HjdSsImage* __restrict__ ss, int n_ss, uint32_t key)
+// Index of the HjdSsImage whose [chunk_base, chunk_base + n_chunks) range contains the chunk `key`.
+__device__ __forceinline__ int ss_find_chunk(const HjdSsImage* __restrict__ ss, int n_ss, uint32_t key)
 {
     int lo = 0, hi = n_ss - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        const uint32_t b = FIELD == 0 ? ss[mid].sub_base : (FIELD == 1 ? ss[mid].chunk_base : ss[mid].mcu_base);
-        if (b <= key) lo = mid; else hi = mid - 1;
+        if (ss[mid].chunk_base <= key) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -160,7 +158,7 @@ hjd_k_destuff_count(const uint8_t* __restrict__ arena, const HjdImageDesc* __res
 {
     const uint32_t t = blockIdx.x * 256 + threadIdx.x;
     if (t >= n_chunks_total) { if (t == n_chunks_total) counts[t] = 0; return; }
-    const HjdSsImage s = ss[ss_find<1>(ss, n_ss, t)];
+    const HjdSsImage s = ss[ss_find_chunk(ss, n_ss, t)];
     const HjdImageDesc* d = imgs + s.img;
     const uint8_t* a0 = arena + d->scan_off - s.lead;
     uint4 bytes;
@@ -174,7 +172,7 @@ hjd_k_destuff_scatter(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
 {
     const uint32_t t = blockIdx.x * 256 + threadIdx.x;
     if (t >= n_chunks_total) return;
-    const int si = ss_find<1>(ss, n_ss, t);
+    const int si = ss_find_chunk(ss, n_ss, t);
     const HjdSsImage s = ss[si];
     const HjdImageDesc* d = imgs + s.img;
     const uint8_t* a0 = arena + d->scan_off - s.lead;
