@@ -20,6 +20,7 @@
 // ------------------------------------------------------------------------------------------
 __constant__ float c_cos[64];     // c_cos[p*8+k] = cosf(((2p+1)*k*3.14f)/16)  (host libm, loadjpg.cpp:120)
 __constant__ float2 c_cos2[64];  // c_cos2[p*8+k] = (c_cos[p*8+k], c_cos[p*8+k]): FFMA2 operand for two rows at once
+__constant__ float c_cosq[64];    // 0.25f * c_cos: the final scaling folded into pass 2 (exact, a power of two)
 __constant__ float c_cc0;         // C(0)*C(k>0) = 1/sqrtf(2)                    (loadjpg.cpp:96-102)
 __constant__ float c_cc00;        // C(0)*C(0) = fl(0.70710677^2) = 0.49999997
 
@@ -30,6 +31,10 @@ cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc0
     float2 dup[64];
     for (int i = 0; i < 64; i++) dup[i] = make_float2(cos_tab[i], cos_tab[i]);
     e = cudaMemcpyToSymbol(c_cos2, dup, sizeof dup);
+    if (e != cudaSuccess) return e;
+    float quarter[64];
+    for (int i = 0; i < 64; i++) quarter[i] = 0.25f * cos_tab[i];
+    e = cudaMemcpyToSymbol(c_cosq, quarter, sizeof quarter);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_cc0, &cc0, sizeof(float));
     if (e != cudaSuccess) return e;
@@ -446,6 +451,16 @@ __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4
     return a_ac;
 }
 
+// d = {sat_s8(a), sat_s8(b)} in the low half-word, c's low half-word in the high one.  Flipping the top
+// bit of each byte afterwards adds 128: sat_u8(v + 128) == sat_s8(v) ^ 0x80, once per word instead of
+// once per sample.
+__device__ __forceinline__ uint32_t hjd_pack_sat_s8(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // d = {sat_u8(a), sat_u8(b)} in the low half-word, c's low half-word in the high one: clamp + pack.
 __device__ __forceinline__ uint32_t hjd_pack_sat_u8(int a, int b, uint32_t c)
 {
@@ -510,7 +525,7 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
             for (int u = 1; u < 8; u++) acc = __ffma2_rn(bp2[vp * 8 + u], c_cos2[x * 8 + u], acc);
             r2[vp * 8 + x] = acc;
         }
-    const float2* cosp = (const float2*)c_cos;     // cosp[y*4+vp] = (cos[y][2vp], cos[y][2vp+1])
+    const float2* cosp = (const float2*)c_cosq;    // cosp[y*4+vp] = 0.25 * (cos[y][2vp], cos[y][2vp+1])
     // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples:
     // |h - rint(h)| <= win  <=  an integer (truncation boundary) lies within the error window of h;
     // everywhere else trunc(h) is provably the reference's value.
@@ -530,24 +545,26 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int x = 2 * xp + e;
-                // pass 2: even and odd vertical frequencies accumulate in the two halves
-                float2 a2 = __fmul2_rn(r2[x], cosp[y * 4]);          // (r[0][x] * 1, r[1][x] * cos[y][1])
+                // pass 2: even and odd vertical frequencies accumulate in the two halves; the table
+                // carries the 0.25 (0.25 * fl(s) == fl(0.25 * s): scaling by a power of two commutes with rounding)
+                float2 a2 = __fmul2_rn(r2[x], cosp[y * 4]);          // 0.25 * (r[0][x] * 1, r[1][x] * cos[y][1])
 #pragma unroll
                 for (int vp = 1; vp < 4; vp++) a2 = __ffma2_rn(r2[vp * 8 + x], cosp[y * 4 + vp], a2);
-                const float h = 0.25f * (a2.x + a2.y);
+                const float h = a2.x + a2.y;
                 const bool nearint = fabsf(h - rintf(h)) <= win;
-                iv[e] = __float2int_rz(h) + 128;   // (int)(0.25*sum) + 128, loadjpg.cpp:123,137
+                iv[e] = __float2int_rz(h);         // (int)(0.25*sum), loadjpg.cpp:123; the + 128 of :137 follows the packing
                 if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
                 else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + x); }
             }
-            if (xp < 2) row_lo[y] = hjd_pack_sat_u8(iv[1], iv[0], row_lo[y]);
-            else        row_hi[y] = hjd_pack_sat_u8(iv[1], iv[0], row_hi[y]);
+            if (xp < 2) row_lo[y] = hjd_pack_sat_s8(iv[1], iv[0], row_lo[y]);
+            else        row_hi[y] = hjd_pack_sat_s8(iv[1], iv[0], row_hi[y]);
         }
     }
     if (a_ac + a_dc >= 1.0e5f) { near_lo = 0xFFFFFFFFu; near_hi = 0xFFFFFFFFu; }
 
 #pragma unroll
-    for (int y = 0; y < 8; y++) *(uint2*)(dst + (size_t)y * pitch) = make_uint2(row_lo[y], row_hi[y]);
+    for (int y = 0; y < 8; y++)
+        *(uint2*)(dst + (size_t)y * pitch) = make_uint2(row_lo[y] ^ 0x80808080u, row_hi[y] ^ 0x80808080u);
 
     // exact re-evaluation of the flagged samples (same thread, later store wins)
     while (near_lo | near_hi) {
