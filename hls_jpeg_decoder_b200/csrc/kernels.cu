@@ -72,72 +72,75 @@ hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restr
     if (tid == 0) out[0] = 0;
     if (d.restart_interval == 0 || d.n_intervals <= 1) return;
 
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_running;
-    if (tid == 0) s_running = 0;
-    __syncthreads();
+    // 64 contiguous bytes per thread and step (four 16-byte loads), one barrier per step: the per-warp
+    // counts are double buffered and every thread keeps the running total itself
+    __shared__ uint32_t s_warp[2][8];
+    uint32_t running = 0;
 
     const uint8_t* s = arena + d.scan_off;
     const uint32_t lead = (uint32_t)((uintptr_t)s & 15);
     const uint8_t* a0 = s - lead;
     const uint32_t total = d.scan_len + lead;
 
-    for (uint32_t chunk = 0; chunk < total; chunk += 256 * 16) {
-        const uint32_t off = chunk + tid * 16;
-        uint32_t mask = 0;
-        if (off < total) {
-            const uint4 v = __ldg((const uint4*)(a0 + off));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int buf = 0;
+    for (uint32_t chunk = 0; chunk < total; chunk += 256 * 64, buf ^= 1) {
+        const uint32_t off0 = chunk + tid * 64;
+        uint64_t mask = 0;                       // bit p: an RSTn marker starts at byte off0 + p
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            v[q] = (off0 + 16u * q < total) ? __ldg((const uint4*)(a0 + off0 + 16u * q)) : make_uint4(0, 0, 0, 0);
+        if (off0 < total) {
+            const uint32_t nb = (off0 + 64 < total) ? a0[off0 + 64] : 0u;
             // SIMD-within-a-register byte tests (exact per byte, no carries between bytes):
             //   ff: bytes equal to FF;  dn: bytes whose SUCCESSOR is D0..D7 (RSTn)
-            const uint32_t nb = (off + 16 < total) ? a0[off + 16] : 0u;
-            uint32_t dd[5];
+            uint32_t dd[17];
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const uint32_t x = ((k < 4 ? w[k] : nb) ^ 0xD0D0D0D0u) & 0xF8F8F8F8u;      // zero byte <=> D0..D7
+            for (int k = 0; k < 17; k++) {
+                const uint32_t wk = k < 16 ? ((const uint32_t*)v)[k] : nb;
+                const uint32_t x = (wk ^ 0xD0D0D0D0u) & 0xF8F8F8F8u;                      // zero byte <=> D0..D7
                 dd[k] = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);           // 0x80 in those bytes
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t ff = ((w[k] & 0x7F7F7F7Fu) + 0x01010101u) & w[k] & 0x80808080u;
+            for (int k = 0; k < 16; k++) {
+                const uint32_t wk = ((const uint32_t*)v)[k];
+                const uint32_t ff = ((wk & 0x7F7F7F7Fu) + 0x01010101u) & wk & 0x80808080u;
                 uint32_t hit = ff & __funnelshift_r(dd[k], dd[k + 1], 8);                 // FF followed by RSTn
                 while (hit) {                                                             // rare: ~1 marker per 365 bytes
                     const int bit = __ffs((int)hit) - 1;
                     hit &= hit - 1;
                     const uint32_t p = 4u * k + ((uint32_t)bit >> 3);
-                    if (off + p >= lead && off + p + 1 < total) mask |= 1u << p;
+                    if (off0 + p >= lead && off0 + p + 1 < total) mask |= 1ull << p;
                 }
             }
         }
-        const uint32_t cnt = __popc(mask);
+        const uint32_t cnt = __popcll(mask);
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 31) s_warp[buf][warp] = incl;
         __syncthreads();
-        uint32_t before = s_running;
+        uint32_t before = running;
         uint32_t block_total = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const uint32_t c = s_warp[k];
+            const uint32_t c = s_warp[buf][k];
             if (k < warp) before += c;
             block_total += c;
         }
         uint32_t ord = before + incl - cnt;
         while (mask) {
-            const int p = __ffs(mask) - 1;
+            const int p = __ffsll((long long)mask) - 1;
             mask &= mask - 1;
-            if (ord + 1 < d.n_intervals) out[ord + 1] = off + p + 2 - lead;
+            if (ord + 1 < d.n_intervals) out[ord + 1] = off0 + p + 2 - lead;
             ord++;
         }
-        __syncthreads();
-        if (tid == 0) s_running += block_total;
-        __syncthreads();
+        running += block_total;
     }
-    const uint32_t found = s_running;
+    const uint32_t found = running;
     if (found != d.n_intervals - 1) {
         if (tid == 0) atomicOr(&status[img], HJD_ST_RESTART);
         // intervals with no marker become empty: the entropy kernel zero-fills them and flags overrun
