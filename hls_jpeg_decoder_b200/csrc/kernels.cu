@@ -554,7 +554,11 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
 #pragma unroll
                 for (int vp = 1; vp < 4; vp++) a2 = __ffma2_rn(r2[vp * 8 + x], cosp[y * 4 + vp], a2);
                 const float h = a2.x + a2.y;
-                const bool nearint = fabsf(h - rintf(h)) <= win;
+                // rint(h) as (h + 1.5*2^23) - 1.5*2^23 (|h| < 2^22 whenever the window is in use): two FADDs
+                // instead of an FRND, which runs on the conversion unit that this kernel loads as much as
+                // the FMA pipe (ncu: pipe_xu 56 %); 4.23 -> 4.08 ms
+                const float hr = __fadd_rn(__fadd_rn(h, 12582912.0f), -12582912.0f);
+                const bool nearint = fabsf(__fadd_rn(h, -hr)) <= win;
                 iv[e] = __float2int_rz(h);         // (int)(0.25*sum), loadjpg.cpp:123; the + 128 of :137 follows the packing
                 if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
                 else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + x); }

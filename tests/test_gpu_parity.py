@@ -370,6 +370,49 @@ def test_selfsync_damaged_scans_are_deterministic(hjd):
         assert not tail.any()
 
 
+def _patch_dqt(jpg: bytes, value: int) -> bytes:
+    """Overwrite every 8-bit quantisation table entry with `value`."""
+    b = bytearray(jpg)
+    i = 2
+    while i + 4 < len(b):
+        assert b[i] == 0xFF
+        m = b[i + 1]
+        ln = (b[i + 2] << 8) | b[i + 3]
+        if m == 0xDB:
+            p = i + 4
+            while p < i + 2 + ln:
+                assert b[p] >> 4 == 0
+                b[p + 1:p + 65] = bytes([value]) * 64
+                p += 65
+        if m == 0xDA:
+            break
+        i += 2 + ln
+    return bytes(b)
+
+
+def test_absurd_dequantisation_wraps_like_the_reference(hjd, port):
+    """Large coefficients (a q100 noise image) against quantisation tables patched to 255 and to 64:
+    coef*q overflows the reference's short (loadjpg.cpp:150), the IDCT sums reach 1e6 and wrap again
+    (loadjpg.cpp:136-137).  Every sample then goes through the exact path; the result must still be
+    the reference's, bit for bit."""
+    from tools.gen_jpegs import encode_jpeg
+    base = [encode_jpeg(cases.noise_rgb(96, 80, 71), 100, "4:4:4"),
+            encode_jpeg(cases.noise_rgb(112, 64, 72), 100, "4:2:0", restart_blocks=4)]
+    files = [_patch_dqt(f, v) for f in base for v in (255, 64, 17)]
+    with hjd.BatchDecoder(0, hjd.FLAG_KEEP_PLANES) as d1, hjd.BatchDecoder(0) as d2:
+        for d in (d1, d2):
+            d.upload(files)
+            d.decode()
+            assert (d.status() == 0).all(), d.status()
+        for i, f in enumerate(files):
+            o = port.decode(f)
+            assert np.array_equal(d1.image_coefficients(i), o["coef"]), i
+            for a, b in zip(d1.planes(i), o["planes"]):
+                assert np.array_equal(a, b), i
+            assert np.array_equal(d1.rgb(i), o["rgb"]), i
+            assert np.array_equal(d2.rgb(i), o["rgb"]), i
+
+
 def _patch_component_ids(jpg: bytes, ids):
     """Rewrite the component identifiers in SOF0 and SOS (the reference indexes arrays with them,
     openjpg.cpp:212-213,343-345, so it only works for 1,2,3)."""
