@@ -176,7 +176,13 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
 // Shared memory: [threads x 128 B] coefficient slots, 16-byte chunks XOR-swizzled by (lane & 7)
 // (conflict-free 128-bit flush, spread 2-byte scatter stores); [warps x 32 x 8 B] flush lists;
 // the table set of this CTA's images (per component: DC table then AC table, contiguous).
-#define HJD_ENT_SYMS 4       // measured on B200 (ms per 1024 x 1080p): 2: 5.2, 3: 4.2, 4: 3.9, 5: 4.0 at 192 threads
+#ifndef HJD_ENT_SYMS
+#define HJD_ENT_SYMS 4
+#endif
+#ifndef HJD_ENT_TOPUP
+#define HJD_ENT_TOPUP 32   // second top-up of a round when fewer bits than this are left (B200, config 2: 40: 3.19, 32: 3.12, 16: 3.14 ms)
+#endif
+// HJD_ENT_SYMS measured on B200 (ms per 1024 x 1080p): 2: 5.2, 3: 4.2, 4: 3.9, 5: 4.0 at 192 threads
 
 struct BitReader {
     const uint8_t* base;   // entropy-coded segment of the image
@@ -300,7 +306,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     while (__any_sync(0xffffffffu, blocks_left > 0)) {
         // scheduled top-up, all lanes together, from the words prefetched during the previous round
         br_refill<true>(br);
-        if (br.nbits <= 40) br_refill<false>(br);        // busy stretch: keep the reserve up
+        if (br.nbits <= HJD_ENT_TOPUP) br_refill<false>(br);        // busy stretch: keep the reserve up
         br_prefetch(br);                                 // in flight while this round's symbols decode
         if (br.padbits > 512) dead = true;
         const bool live = blocks_left > 0;
@@ -900,7 +906,10 @@ cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs,
 // Planes never reach HBM.  Tiles are interleaved by thread (row r of thread t at [(r*T + t) * 8 B])
 // so row stores and loads are bank-conflict free; the exact re-evaluation patches bytes in the tile
 // before the colour step reads them.
-__global__ void __launch_bounds__(HJD_MCU_THREADS, 4)
+#ifndef HJD_MCU_MINBLOCKS
+#define HJD_MCU_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(HJD_MCU_THREADS, HJD_MCU_MINBLOCKS)
 hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
               const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb, int img_base)
 {
