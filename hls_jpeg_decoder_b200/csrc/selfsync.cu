@@ -297,31 +297,45 @@ __device__ __forceinline__ uint64_t ss_scan_decode(const SsCtx& cx, uint64_t sta
     SsBits br;
     br.init(cx.D, p0);
     int rem = (int)(end_bit - p0);                       // bits left in the sub-sequence (entry is at most one behind)
-    uint32_t comp = (uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 1u : 2u);
-    uint32_t tbase = cx.sh_tab + comp * 2u * kTabBytes;
+    // The block-end bookkeeping is straight-line code: nearly every iteration of a warp has some lane
+    // at a block end, so a branch here costs more than always executing the selects (it was a quarter
+    // of the kernel's instructions).  DC sums rotate with the component, slot 0 = current component.
+    uint32_t comp = (uint32_t)c < cx.ny ? 0u : (uint32_t)c - cx.ny + 1u;
+    uint32_t t0 = cx.sh_tab + comp * 2u * kTabBytes;
     uint32_t ns = 0, d0 = 0, d1 = 0, d2 = 0;
 
     while (rem > 0) {
         br.ensure();
         const bool is_ac = k != 0;
-        const SsSym s = ss_symbol(tbase + (is_ac ? kTabBytes : 0u), br.hi, br.lo, is_ac);
+        const SsSym s = ss_symbol(t0 + (is_ac ? kTabBytes : 0u), br.hi, br.lo, is_ac);
         br.skip(s.used);
         rem -= (int)s.used;
-        if (COUNT && !is_ac) {
-            ns++;
-            d0 += comp == 0u ? (uint32_t)s.val : 0u;
-            d1 += comp == 1u ? (uint32_t)s.val : 0u;
-            d2 += comp == 2u ? (uint32_t)s.val : 0u;
+        if (COUNT) {
+            ns += is_ac ? 0u : 1u;
+            d0 += is_ac ? 0u : (uint32_t)s.val;
         }
         k += (int)s.kadv;
-        if (k >= 64) {
-            k = 0;
-            c = (c + 1 == (int)cx.bpm) ? 0 : c + 1;
-            comp = (uint32_t)c < cx.ny ? 0u : ((uint32_t)c == cx.ny ? 1u : 2u);
-            tbase = cx.sh_tab + comp * 2u * kTabBytes;
+        const bool blk_end = k >= 64;
+        k = blk_end ? 0 : k;
+        int c1 = c + 1;
+        c1 = (uint32_t)c1 == cx.bpm ? 0 : c1;
+        c = blk_end ? c1 : c;
+        const uint32_t comp_new = (uint32_t)c < cx.ny ? 0u : (uint32_t)c - cx.ny + 1u;
+        if (COUNT) {
+            const bool chg = comp_new != comp;           // Y -> Cb -> Cr -> Y: always to the next slot
+            const uint32_t r0 = chg ? d1 : d0, r1 = chg ? d2 : d1, r2 = chg ? d0 : d2;
+            d0 = r0; d1 = r1; d2 = r2;
         }
+        comp = comp_new;
+        t0 = cx.sh_tab + comp * 2u * kTabBytes;
     }
-    if (COUNT) { cnt->ns = ns; cnt->dc0 = d0; cnt->dc1 = d1; cnt->dc2 = d2; }
+    if (COUNT) {
+        // back to (Y, Cb, Cr): slot 0 holds the component of block c
+        cnt->ns = ns;
+        cnt->dc0 = comp == 0u ? d0 : (comp == 1u ? d2 : d1);
+        cnt->dc1 = comp == 0u ? d1 : (comp == 1u ? d0 : d2);
+        cnt->dc2 = comp == 0u ? d2 : (comp == 1u ? d1 : d0);
+    }
     return ss_pack(end_bit - (uint64_t)(int64_t)rem, k, c);
 }
 
