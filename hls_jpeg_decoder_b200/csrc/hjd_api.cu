@@ -316,7 +316,7 @@ static int upload_common(hjd_batch* b, bool chunked)
             b->ss.push_back(si);
             b->ss_subs += si.n_subs;
             b->ss_chunks += si.n_chunks;
-            b->ss_dst_bytes += align_up(ps.scan_len + HJD_SS_SLACK, 256);
+            b->ss_dst_bytes += align_up(ps.scan_len + HJD_SS_SLACK + 16, 256);   // + 16: the slack is zeroed from the next 16-byte boundary
         }
         d.table_set = tset; d.quant_set = qset;
         d.n_blocks = (uint64_t)d.n_mcus * d.blocks_per_mcu;

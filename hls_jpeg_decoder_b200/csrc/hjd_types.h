@@ -80,7 +80,8 @@ struct HjdEntropyWork {
 // ---- self-synchronising path (restart-free scans) -------------------------------------------
 #define HJD_SS_SUB_BYTES   128          // sub-sequence length in (de-stuffed) bytes = 1024 bits
 #define HJD_SS_MIN_BYTES   1024         // restart-free scans shorter than this stay on the 1-thread path
-#define HJD_SS_SLACK       256          // zeroed bytes after every de-stuffed stream
+#define HJD_SS_SLACK       512          // zeroed bytes after every de-stuffed stream: a block that starts in the last
+                                        // sub-sequence may run 63 x 26 bits past it, plus the words in flight
 #define HJD_SS_THREADS     256
 #define HJD_SS_FIX_WARPS   4     // warps per CTA of the synchronisation rounds, one range of sub-sequences each
 #define HJD_SS_FIX_MAXR    256   // largest range
