@@ -85,6 +85,7 @@ struct HjdEntropyWork {
 #define HJD_SS_THREADS     256
 #define HJD_SS_FIX_WARPS   4     // warps per CTA of the synchronisation rounds, one range of sub-sequences each
 #define HJD_SS_FIX_MAXR    256   // largest range
+#define HJD_SS_FIX_OVERLAP 4     // sub-sequences before a range that its warp re-checks privately
 
 // One per image decoded by the self-synchronising kernels; all index spaces below are global
 // over the batch (sub-sequences, 16-byte de-stuffing chunks).

@@ -192,27 +192,65 @@ hjd_k_destuff_count(const uint8_t* __restrict__ arena, const HjdImageDesc* __res
     counts[t] = __popc(destuff_mask(a0, t - s.chunk_base, s.lead, d->scan_len, &bytes));
 }
 
+// The kept bytes of a warp's 32 chunks form one contiguous output range of at most 512 bytes.  They are
+// compacted in shared memory (at the same alignment modulo 4 as their destination) and leave as
+// aligned 32-bit words, adjacent lanes adjacent: sixteen one-byte global stores per thread kept this
+// kernel at 260 us per 91 MB.  A warp that straddles two images falls back to byte stores.
 __global__ void __launch_bounds__(256)
 hjd_k_destuff_scatter(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
                       const HjdSsImage* __restrict__ ss, int n_ss, uint32_t n_chunks_total,
                       const uint32_t* __restrict__ prefix, uint8_t* __restrict__ dst, uint32_t* __restrict__ dlen)
 {
     __shared__ int s_first;
+    __shared__ __align__(16) uint8_t s_stage[8][544];
     const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int si = destuff_image_of(ss, n_ss, t < n_chunks_total ? t : n_chunks_total - 1, &s_first);
-    if (t >= n_chunks_total) return;
-    const HjdSsImage s = ss[si];
-    const HjdImageDesc* d = imgs + s.img;
-    const uint8_t* a0 = arena + d->scan_off - s.lead;
-    uint4 bytes;
-    uint32_t keep = destuff_mask(a0, t - s.chunk_base, s.lead, d->scan_len, &bytes);
-    const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
-    uint8_t* out = dst + s.dst_off + (prefix[t] - prefix[s.chunk_base]);
+    const bool in = t < n_chunks_total;
+    uint32_t keep = 0, cnt = 0;
+    uint32_t w[4] = {0, 0, 0, 0};
+    uint64_t my_out = 0;                                // byte offset of this chunk's output in dst
+    HjdSsImage s = ss[si];
+    if (in) {
+        const HjdImageDesc* d = imgs + s.img;
+        const uint8_t* a0 = arena + d->scan_off - s.lead;
+        uint4 bytes;
+        keep = destuff_mask(a0, t - s.chunk_base, s.lead, d->scan_len, &bytes);
+        w[0] = bytes.x; w[1] = bytes.y; w[2] = bytes.z; w[3] = bytes.w;
+        cnt = __popc(keep);
+        my_out = s.dst_off + (prefix[t] - prefix[s.chunk_base]);
+    }
+    const uint64_t next_out = __shfl_down_sync(0xffffffffu, my_out, 1);
+    const bool chained = in && (lane == 31 || next_out == my_out + cnt);
+    if (__all_sync(0xffffffffu, chained)) {
+        const uint64_t base = __shfl_sync(0xffffffffu, my_out, 0);
+        const uint32_t total = (uint32_t)(__shfl_sync(0xffffffffu, my_out + cnt, 31) - base);
+        const uint32_t al = (uint32_t)base & 3u;          // dst is 256-byte aligned: offset alignment == address alignment
+        uint8_t* st = s_stage[warp];
+        uint32_t o = (uint32_t)(my_out - base) + al;
 #pragma unroll
-    for (int j = 0; j < 16; j++)
-        if (keep & (1u << j)) *out++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
-    if (t == s.chunk_base + s.n_chunks - 1) {          // last chunk of the image: length + zero slack
-        const uint32_t len = prefix[t] - prefix[s.chunk_base] + __popc(keep);
+        for (int j = 0; j < 16; j++)
+            if (keep & (1u << j)) st[o++] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        __syncwarp();
+        const uint32_t end = al + total;                 // staged bytes are [al, end)
+        const uint32_t first_full = al ? 4u : 0u;
+        uint8_t* g = dst + (base - al);                   // 4-byte aligned
+        if (end <= first_full) {
+            if ((uint32_t)lane >= al && (uint32_t)lane < end) g[lane] = st[lane];
+        } else {
+            const uint32_t end_full = end & ~3u;
+            for (uint32_t i = first_full / 4 + lane; i < end_full / 4; i += 32) ((uint32_t*)g)[i] = ((const uint32_t*)st)[i];
+            if ((uint32_t)lane >= al && (uint32_t)lane < first_full) g[lane] = st[lane];                 // head bytes
+            if (end_full + lane < end) g[end_full + lane] = st[end_full + lane];                         // tail bytes
+        }
+    } else if (in) {
+        uint8_t* out = dst + my_out;
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (keep & (1u << j)) *out++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+    }
+    if (in && t == s.chunk_base + s.n_chunks - 1) {    // last chunk of the image: length + zero slack
+        const uint32_t len = prefix[t] - prefix[s.chunk_base] + cnt;
         dlen[si] = len;
         uint4* z = (uint4*)(dst + s.dst_off + ((len + 15u) & ~15u));
         for (uint32_t j = len; j < ((len + 15u) & ~15u); j++) dst[s.dst_off + j] = 0;
@@ -459,11 +497,10 @@ cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tset
 // sharing the image's tables).  A sub-sequence whose left neighbour's exit state differs from the
 // entry state it was decoded from goes on the warp's list in shared memory; the list is decoded 32
 // entries at a time, so the few sub-sequences still wrong cost a few dense warp passes instead of one
-// mostly idle pass per 32 sub-sequences; repeat until the range is consistent.  The entry state of
-// the range's first sub-sequence is the previous range's last exit state, read from HBM: whichever
-// value the read returns (the previous round's or this round's), a range whose last exit state moved
-// raises `changed`, and the host repeats the round until nothing moves.  Sub-sequence 0 starts from
-// the true state, so the fixed point is the sequential decode.
+// mostly idle pass per 32 sub-sequences; repeat until the range is consistent.  The states before the
+// range come from HBM, where the previous warp may still be correcting them: whichever values the
+// reads return, the host repeats the round until one passes in which no warp had anything to decode.
+// Sub-sequence 0 starts from the true state, so the fixed point is the sequential decode.
 __global__ void __launch_bounds__(HJD_SS_FIX_WARPS * 32)
 hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
              const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
@@ -472,12 +509,13 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
              int* __restrict__ changed)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    constexpr uint32_t kWarpBytes = HJD_SS_FIX_MAXR * 18;
+    constexpr uint32_t kEntries = HJD_SS_FIX_MAXR + HJD_SS_FIX_OVERLAP;
+    constexpr uint32_t kWarpBytes = (kEntries * 18 + 15) & ~15u;
     uint8_t* s_tab = s_raw + HJD_SS_FIX_WARPS * kWarpBytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t* sE = (uint64_t*)(s_raw + warp * kWarpBytes);           // exit state per sub-sequence of the range
-    uint64_t* sX = sE + HJD_SS_FIX_MAXR;                             // entry state it was computed from
-    uint16_t* sL = (uint16_t*)(sX + HJD_SS_FIX_MAXR);                // sub-sequences to decode again
+    uint64_t* sE = (uint64_t*)(s_raw + warp * kWarpBytes);           // exit state per sub-sequence of the window
+    uint64_t* sX = sE + kEntries;                                    // entry state it was computed from
+    uint16_t* sL = (uint16_t*)(sX + kEntries);                       // sub-sequences to decode again
     const HjdSsWork wk = work[blockIdx.x];
     const HjdSsImage s = ss[wk.ss];
     const HjdImageDesc* d = imgs + s.img;
@@ -486,17 +524,25 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
     const uint32_t first = wk.first_sub + (uint32_t)warp * range;    // local index of the range's first sub-sequence
     uint32_t n_have = (L + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES; // sub-sequences that hold data
     if (n_have > s.n_subs) n_have = s.n_subs;
-    const int n_act = first < n_have ? (int)min(range, n_have - first) : 0;
-    const uint32_t g0 = s.sub_base + first;
+    const int n_own = first < n_have ? (int)min(range, n_have - first) : 0;
+    // The window starts HJD_SS_FIX_OVERLAP sub-sequences before the range: they are re-checked (and, if
+    // need be, re-decoded) privately, never written back -- they belong to the previous warp, which
+    // may be correcting them at this very moment.  So the entry state of the range no longer hinges on
+    // one exit state of the speculative pass, and the round after this one is normally a pure check.
+    const uint32_t lo = first >= HJD_SS_FIX_OVERLAP ? first - HJD_SS_FIX_OVERLAP : 0u;
+    const int kov = n_own ? (int)(first - lo) : 0;
+    const int n_act = n_own ? kov + n_own : 0;
+    const uint32_t g0 = s.sub_base + lo;
     for (int j = lane; j < n_act; j += 32) { sE[j] = e_arr[g0 + j]; sX[j] = x_arr[g0 + j]; }
-    uint64_t boundary = ss_pack(0, 0, 0), e_last_start = 0;
-    if (n_act) {
-        if (first != 0) boundary = e_arr[g0 - 1];
-        e_last_start = e_arr[g0 + n_act - 1];
-    }
+    uint64_t boundary = ss_pack(0, 0, 0);
+    if (n_act && lo != 0) boundary = e_arr[g0 - 1];
     __syncwarp();
     bool any = false;
     for (int j = lane; j < n_act; j += 32) any |= (j == 0 ? boundary : sE[j - 1]) != sX[j];
+    // A warp that has anything to decode again raises `changed`.  The host stops after a round in which
+    // no warp did: every warp then found its window -- read from HBM while nobody was writing --
+    // consistent, including the entry of its range against the previous range's last exit state.
+    if (__any_sync(0xffffffffu, any) && lane == 0) *changed = 1;
     if (!__syncthreads_or(any)) return;                              // the usual case in the later rounds
     ss_load_tables(tsets + d->table_set, s_tab);
     __syncthreads();
@@ -508,7 +554,6 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
     cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
     const uint64_t sub_bits = (uint64_t)HJD_SS_SUB_BYTES * 8;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    bool stable = false;
     for (int iter = 0; iter < n_act + 2; iter++) {
         int n = 0;
         for (int j0 = 0; j0 < n_act; j0 += 32) {
@@ -519,7 +564,7 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
             n += __popc(bal);
         }
         __syncwarp();
-        if (n == 0) { stable = true; break; }
+        if (n == 0) break;
         for (int q0 = 0; q0 < n; q0 += 32) {
             int t = -1;
             uint64_t txin = 0;
@@ -530,20 +575,21 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
             __syncwarp();                                            // entry states read before any is rewritten
             if (t >= 0) {
                 SsCount cnt;
-                const uint64_t te = ss_scan_decode<true>(cx, txin, (uint64_t)(first + t + 1) * sub_bits, &cnt);
-                const uint32_t g = g0 + (uint32_t)t;
-                cnt_arr[g] = cnt.ns;
-                cnt_arr[n_subs_total + g] = cnt.dc0;
-                cnt_arr[2 * n_subs_total + g] = cnt.dc1;
-                cnt_arr[3 * n_subs_total + g] = cnt.dc2;
+                const uint64_t te = ss_scan_decode<true>(cx, txin, (uint64_t)(lo + t + 1) * sub_bits, &cnt);
+                if (t >= kov) {
+                    const uint32_t g = g0 + (uint32_t)t;
+                    cnt_arr[g] = cnt.ns;
+                    cnt_arr[n_subs_total + g] = cnt.dc0;
+                    cnt_arr[2 * n_subs_total + g] = cnt.dc1;
+                    cnt_arr[3 * n_subs_total + g] = cnt.dc2;
+                }
                 sE[t] = te;
                 sX[t] = txin;
             }
             __syncwarp();
         }
     }
-    for (int j = lane; j < n_act; j += 32) { e_arr[g0 + j] = sE[j]; x_arr[g0 + j] = sX[j]; }
-    if (lane == 0 && n_act && (!stable || sE[n_act - 1] != e_last_start)) *changed = 1;
+    for (int j = kov + lane; j < n_act; j += 32) { e_arr[g0 + j] = sE[j]; x_arr[g0 + j] = sX[j]; }
 }
 
 cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
@@ -553,7 +599,7 @@ cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets
 {
     if (n_work <= 0) return cudaSuccess;
     if (range == 0 || range > HJD_SS_FIX_MAXR || (range & 31u)) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)HJD_SS_FIX_WARPS * HJD_SS_FIX_MAXR * 18 + 6 * sizeof(HjdHuffTable);
+    const size_t smem = (size_t)HJD_SS_FIX_WARPS * (((HJD_SS_FIX_MAXR + HJD_SS_FIX_OVERLAP) * 18 + 15) & ~15u) + 6 * sizeof(HjdHuffTable);
     hjd_k_ss_fix<<<n_work, HJD_SS_FIX_WARPS * 32, smem, st>>>(imgs, tsets, ss, work, dst, dlen, range, n_subs_total,
                                                              e, x, cnt, changed);
     return cudaGetLastError();

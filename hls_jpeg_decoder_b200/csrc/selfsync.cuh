@@ -21,8 +21,8 @@ cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tset
                                uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt, cudaStream_t st);
 
 // One synchronisation round, in place.  `work` here has one entry per HJD_SS_FIX_WARPS * range
-// sub-sequences (range: multiple of 32, <= HJD_SS_FIX_MAXR).  changed is set to 1 when the last exit
-// state of any range moved.
+// sub-sequences (range: multiple of 32, <= HJD_SS_FIX_MAXR).  changed is set to 1 when any warp had a
+// sub-sequence to decode again; the states are final after a round that leaves it 0.
 cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
                               const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
                               uint32_t range, uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
