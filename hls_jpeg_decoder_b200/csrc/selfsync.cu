@@ -10,11 +10,12 @@
 //   1. every thread decodes from a fixed bit offset one sub-sequence ahead of its own 128-byte
 //      sub-sequence (assuming a block starts there), then its own, and records its exit state
 //      (bit position, zig-zag index, block-in-MCU);
-//   2. sync rounds: a thread re-decodes its sub-sequence from its left neighbour's exit state whenever
-//      that state differs from the one it last used.  Inside a warp the neighbour state travels by
-//      warp shuffle and the round iterates until the warp is stable; across warps it travels through
-//      HBM and the host repeats the round until no exit state moves.  Sub-sequence 0 starts from the
-//      true state, so by induction the fixed point is exactly the sequential decode;
+//   2. sync rounds: a sub-sequence is decoded again from its left neighbour's exit state whenever that
+//      state differs from the one it was last decoded from.  A warp owns a range of sub-sequences,
+//      collects the ones to redo in shared memory and decodes them 32 at a time until the range is
+//      stable; between ranges the states travel through HBM and the host repeats the round until one
+//      passes with nothing to redo.  Sub-sequence 0 starts from the true state, so by induction the
+//      fixed point is exactly the sequential decode;
 //   3. an exclusive prefix sum of, per sub-sequence, the number of blocks that start in it and the sums
 //      of their DC differences gives every thread its first output block and its DC predictors
 //      (DCT[0] = data + prevDC in int16, loadjpg.cpp:664-665);
