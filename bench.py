@@ -301,12 +301,13 @@ def run_ours(args, rank, local_rank, world):
     launches = t["launches"]
 
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(pixels), float(scan_bytes), float(alg_bytes), float(n)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(pixels), float(scan_bytes), float(alg_bytes), float(n), float(launches * args.steps)],
+                       dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_max = float(t_ms.item())
-    job_pixels, job_scan, job_alg, job_images = (float(v) for v in tot.tolist())
+    job_pixels, job_scan, job_alg, job_images, job_launches = (float(v) for v in tot.tolist())
     value = job_pixels / 1e6 * args.steps / (ms_max / 1e3)
 
     # end to end through the C ABI with host buffers (pinned in, pinned out), copies inside the timed region
@@ -326,10 +327,12 @@ def run_ours(args, rank, local_rank, world):
         te = time.perf_counter() - te
         assert (st2 == 0).all()
         t_e = torch.tensor([te], dtype=torch.float64, device="cuda")
+        io = torch.tensor([float(arena.bytes), float(need)], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(io, op=dist.ReduceOp.SUM)          # whole job, like the value
         e2e = {"value": round(job_pixels / 1e6 * args.e2e_steps / float(t_e.item()), 1), "unit": "MP/s",
-               "h2d_bytes_per_step": int(arena.bytes), "d2h_bytes_per_step": int(need), "steps": args.e2e_steps}
+               "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()), "steps": args.e2e_steps}
         hjd.lib().hjd_host_free(out_ptr)
 
     if rank == 0:
@@ -361,7 +364,7 @@ def run_ours(args, rank, local_rank, world):
                              "traffic_source": "profiles/r1_final_traffic.json (ncu --set full, per launch)" if traffic else None,
                              "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
                              "whole_step_frac": round(whole / peak, 4)},
-                "clocks": clocks, "gpu_launches": launches * args.steps}
+                "clocks": clocks, "gpu_launches": int(job_launches)}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
