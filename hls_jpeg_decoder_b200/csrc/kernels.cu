@@ -182,7 +182,7 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
 #ifndef HJD_ENT_TOPUP
 #define HJD_ENT_TOPUP 32   // second top-up of a round when fewer bits than this are left (B200, config 2: 40: 3.19, 32: 3.12, 16: 3.14 ms)
 #endif
-// HJD_ENT_SYMS measured on B200 (ms per 1024 x 1080p): 2: 5.2, 3: 4.2, 4: 3.9, 5: 4.0 at 192 threads
+// HJD_ENT_SYMS measured on B200 (ms per 1024 x 1080p, 256 threads): 3: 3.25, 4: 3.19, 5: 3.61, 6: 4.19
 
 struct BitReader {
     const uint8_t* base;   // entropy-coded segment of the image
