@@ -701,7 +701,9 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                     br.ensure();
                     const bool is_ac = k != 0;
                     const SsSym sy = ss_symbol(t0 + (is_ac ? kTabBytes : 0u), br.hi, br.lo, is_ac);
-                    if (sy.bad) flags |= HJD_ST_BAD_CODE;
+                    // only inside an owned (real) block: what a thread skips may be the padding after the
+                    // last block, decoded as if a block followed, and every real block has an owner who sees all of it
+                    if (sy.bad && owned) flags |= HJD_ST_BAD_CODE;
                     br.skip(sy.used);
                     rem -= (int)sy.used;
                     const uint32_t kpos = (uint32_t)k + sy.kadv - 1u;

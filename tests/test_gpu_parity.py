@@ -370,6 +370,22 @@ def test_selfsync_damaged_scans_are_deterministic(hjd):
         assert not tail.any()
 
 
+def test_selfsync_padding_after_the_last_block_is_not_an_error(hjd, port):
+    """Found by tools/soak_parity.py (2 of 40,000 images): when the last block ends a few bytes before
+    the end of the last sub-sequence, the thread of that sub-sequence is entered in the padding after
+    the image; skipping it must not raise HJD_IMG_WARN_BAD_CODE."""
+    from tools.soak_parity import make
+    files = [make(10674, 3), make(25358, 3)]
+    with hjd.BatchDecoder(0) as d:
+        d.upload(files)
+        d.decode()
+        assert (d.status() == 0).all(), d.status()
+        for i, f in enumerate(files):
+            o = port.decode(f)
+            assert np.array_equal(d.image_coefficients(i), o["coef"]), i
+            assert np.array_equal(d.rgb(i), o["rgb"]), i
+
+
 def _patch_dqt(jpg: bytes, value: int) -> bytes:
     """Overwrite every 8-bit quantisation table entry with `value`."""
     b = bytearray(jpg)

@@ -2,7 +2,7 @@
 quality, content, Huffman optimisation and restart interval, decoded through the C ABI and compared
 bit for bit (coefficients and RGB) with the oracle port.
 
-    python tools/soak_parity.py [N] [seed]
+    python tools/soak_parity.py [N] [seed] [max_width max_height]     (default sizes: up to 200 x 160)
 """
 import os
 import sys
@@ -13,10 +13,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def make(i, seed):
+def make(i, seed, max_w=200, max_h=160):
     from tools.gen_jpegs import encode_jpeg, synth_rgb
     rng = np.random.default_rng(seed * 100003 + i)
-    w, h = int(rng.integers(8, 200)), int(rng.integers(8, 160))
+    w, h = int(rng.integers(8, max_w)), int(rng.integers(8, max_h))
     kind = int(rng.integers(0, 5))
     if kind == 0:
         rgb = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
@@ -36,7 +36,15 @@ def make(i, seed):
     gray = bool(rng.integers(0, 6) == 0)
     q = int(rng.choice([1, 5, 10, 25, 50, 75, 85, 90, 95, 98, 100]))
     ri = int(rng.choice([0, 0, 1, 2, 3, 8, 17]))
-    return encode_jpeg(rgb, q, sub, ri, gray=gray, optimize=bool(rng.integers(0, 2)))
+    opt = bool(rng.integers(0, 2))
+    try:
+        return encode_jpeg(rgb, q, sub, ri, gray=gray, optimize=opt)
+    except OSError:                                                     # PIL refuses a few corner combinations
+        return encode_jpeg(rgb, q, sub, 0, gray=gray, optimize=False)
+
+
+def make_job(args):
+    return make(*args)
 
 
 def oracle(jpg):
@@ -48,9 +56,11 @@ def oracle(jpg):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    max_w = int(sys.argv[3]) if len(sys.argv) > 4 else 200
+    max_h = int(sys.argv[4]) if len(sys.argv) > 4 else 160
     import hls_jpeg_decoder_b200 as hjd
-    files = [make(i, seed) for i in range(n)]
     with ProcessPoolExecutor(max_workers=os.cpu_count()) as ex:
+        files = list(ex.map(make_job, [(i, seed, max_w, max_h) for i in range(n)], chunksize=4 if max_w > 400 else 32))
         want = list(ex.map(oracle, files, chunksize=8))
     bad = 0
     with hjd.BatchDecoder(0) as d:
