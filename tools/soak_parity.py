@@ -63,20 +63,23 @@ def main():
         files = list(ex.map(make_job, [(i, seed, max_w, max_h) for i in range(n)], chunksize=4 if max_w > 400 else 32))
         want = list(ex.map(oracle, files, chunksize=8))
     bad = 0
-    with hjd.BatchDecoder(0) as d:
-        d.upload(files)
-        d.decode()
-        st = d.status()
-        coef = d.coefficients()
-        for i in range(n):
-            wc, wr = want[i]
-            ok = st[i] == 0 and np.array_equal(d.image_coefficients(i, coef), wc) and np.array_equal(d.rgb(i), wr)
-            if not ok:
-                bad += 1
-                diff = int(np.abs(d.rgb(i).astype(int) - wr.astype(int)).max()) if d.rgb(i).shape == wr.shape else -1
-                print(f"MISMATCH image {i}: status {st[i]}, max |rgb diff| {diff}, {len(files[i])} bytes")
+    variants = (("default", 0), ("planes", hjd.FLAG_KEEP_PLANES), ("strip-fused", hjd.FLAG_FUSED),
+                ("no-selfsync", hjd.FLAG_NO_SELFSYNC))
+    for name, flags in variants:
+        with hjd.BatchDecoder(0, flags) as d:
+            d.upload(files)
+            d.decode()
+            st = d.status()
+            coef = d.coefficients()
+            for i in range(n):
+                wc, wr = want[i]
+                ok = st[i] == 0 and np.array_equal(d.image_coefficients(i, coef), wc) and np.array_equal(d.rgb(i), wr)
+                if not ok:
+                    bad += 1
+                    diff = int(np.abs(d.rgb(i).astype(int) - wr.astype(int)).max()) if d.rgb(i).shape == wr.shape else -1
+                    print(f"MISMATCH [{name}] image {i}: status {st[i]}, max |rgb diff| {diff}, {len(files[i])} bytes")
     pixels = sum(int(w[1].shape[0]) * int(w[1].shape[1]) for w in want)
-    print(f"soak: {n} images, {pixels / 1e6:.1f} MP, seed {seed}: {bad} mismatches")
+    print(f"soak: {n} images, {pixels / 1e6:.1f} MP, seed {seed}, {len(variants)} decoder variants: {bad} mismatches")
     sys.exit(1 if bad else 0)
 
 
