@@ -283,14 +283,21 @@ def run_ours(args, rank, local_rank, world):
     launches = 0
     barrier()
     t0 = time.time()
+    per_step = args.steps <= 128             # one event per step boundary as long as the slots last
     dec.mark(0)
-    for _ in range(args.steps):
+    for i in range(args.steps):
         dec.decode()
+        if per_step and i + 1 < args.steps:
+            dec.mark(2 + i)
     dec.mark(1)
     dec.sync()
     barrier()
     t1 = time.time()
     ms_total = dec.elapsed_ms(0, 1)
+    step_ms = []
+    if per_step:
+        marks = [0] + [2 + i for i in range(args.steps - 1)] + [1]
+        step_ms = sorted(dec.elapsed_ms(marks[i], marks[i + 1]) for i in range(args.steps))
     clocks = sampler.stop(t0, t1)
     # per-stage CUDA-event times of the LAST TIMED step (the HBM-resident decode runs on one stream, in
     # order, and records its stage boundaries on that stream at every step): the roofline's kernel
@@ -365,6 +372,9 @@ def run_ours(args, rank, local_rank, world):
                              "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
                              "whole_step_frac": round(whole / peak, 4)},
                 "clocks": clocks, "gpu_launches": int(job_launches)}
+        if step_ms:     # rank 0's own steps, CUDA events between consecutive steps (best and median)
+            line["ms_per_step_best"] = round(step_ms[0], 4)
+            line["ms_per_step_median"] = round(step_ms[len(step_ms) // 2], 4)
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -100,7 +100,7 @@ struct hjd_batch {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t mark[4] = {nullptr, nullptr, nullptr, nullptr};   // hjd_batch_mark
+    cudaEvent_t mark[HJD_MARK_SLOTS] = {};                          // hjd_batch_mark
     cudaStream_t aux[HJD_NSTREAMS] = {nullptr, nullptr, nullptr}; // chunk streams
     cudaEvent_t ev_fork = nullptr, ev_join[HJD_NSTREAMS] = {nullptr, nullptr, nullptr};
     std::vector<Chunk> chunks;
@@ -179,7 +179,7 @@ extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     b->own_stream = true;
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev[i]);
-    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&b->mark[i]);
+    for (int i = 0; i < HJD_MARK_SLOTS && e == cudaSuccess; i++) e = cudaEventCreate(&b->mark[i]);
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
@@ -208,7 +208,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     b->d_flag.release();
     b->h_meta.release(); b->h_flag.release();
     for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
-    for (int i = 0; i < 4; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
+    for (int i = 0; i < HJD_MARK_SLOTS; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
     for (int i = 0; i < HJD_NSTREAMS; i++) { if (b->aux[i]) { cudaStreamSynchronize(b->aux[i]); cudaStreamDestroy(b->aux[i]); } if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]); }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
@@ -790,7 +790,7 @@ extern "C" int hjd_batch_get_timings(hjd_batch* b, hjd_timings* t)
 
 extern "C" int hjd_batch_mark(hjd_batch* b, int slot)
 {
-    if (!b || slot < 0 || slot >= 4) return fail(HJD_ERR_ARG, "hjd_batch_mark", "bad arguments");
+    if (!b || slot < 0 || slot >= HJD_MARK_SLOTS) return fail(HJD_ERR_ARG, "hjd_batch_mark", "bad arguments");
     CU(cudaSetDevice(b->device));
     CU(cudaEventRecord(b->mark[slot], b->stream));
     return HJD_OK;
@@ -798,7 +798,7 @@ extern "C" int hjd_batch_mark(hjd_batch* b, int slot)
 
 extern "C" float hjd_batch_elapsed_ms(hjd_batch* b, int slot_a, int slot_b)
 {
-    if (!b || slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4) { fail(HJD_ERR_ARG, "hjd_batch_elapsed_ms", "bad arguments"); return -1.f; }
+    if (!b || slot_a < 0 || slot_a >= HJD_MARK_SLOTS || slot_b < 0 || slot_b >= HJD_MARK_SLOTS) { fail(HJD_ERR_ARG, "hjd_batch_elapsed_ms", "bad arguments"); return -1.f; }
     float ms = -1.f;
     if (cudaSetDevice(b->device) != cudaSuccess || cudaEventSynchronize(b->mark[slot_b]) != cudaSuccess ||
         cudaEventElapsedTime(&ms, b->mark[slot_a], b->mark[slot_b]) != cudaSuccess) {

@@ -152,8 +152,10 @@ int  hjd_batch_num_images(const hjd_batch* b);
 int  hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* out);
 int  hjd_batch_get_status(hjd_batch* b, int32_t* status /* n */);   /* syncs */
 int  hjd_batch_get_timings(hjd_batch* b, hjd_timings* out);          /* syncs */
-/* CUDA-event stopwatch on the batch stream: record event `slot` (0..3); milliseconds between two
- * recorded slots (waits for slot_b).  This is how bench.py times K steps on the launching stream. */
+/* CUDA-event stopwatch on the batch stream: record event `slot` (0..HJD_MARK_SLOTS-1); milliseconds
+ * between two recorded slots (waits for slot_b).  This is how bench.py times K steps, and each of
+ * them, on the launching stream. */
+#define HJD_MARK_SLOTS 130
 int   hjd_batch_mark(hjd_batch* b, int slot);
 float hjd_batch_elapsed_ms(hjd_batch* b, int slot_a, int slot_b);
 uint64_t hjd_batch_rgb_bytes(const hjd_batch* b);     /* size of the RGB slab */
