@@ -694,6 +694,13 @@ __device__ __forceinline__ void hjd_color_apply(const uint32_t* yw, const float4
         out[w] = hjd_pack_sat_u8(ch[4 * w + 1], ch[4 * w], hjd_pack_sat_u8(ch[4 * w + 3], ch[4 * w + 2], 0u));
 }
 
+// Byte idx of a word array as float (idx is a compile-time constant after unrolling: one I2F.U8 with a byte selector).
+__device__ __forceinline__ float hjd_byte_f(const uint32_t* w, int idx)
+{
+    return (float)((w[idx >> 2] >> (8 * (idx & 3))) & 255u);
+}
+
+#ifdef HJD_COLOR_SCALAR
 template <int HS, int NP>
 __device__ __forceinline__ void hjd_color_n(const uint32_t* yw, const uint32_t* cbw, const uint32_t* crw, uint32_t* out)
 {
@@ -701,6 +708,46 @@ __device__ __forceinline__ void hjd_color_n(const uint32_t* yw, const uint32_t* 
     hjd_chroma_terms<(NP >> HS)>(cbw, crw, terms);
     hjd_color_apply<HS, NP>(yw, terms, out);
 }
+#else
+// The same arithmetic as hjd_chroma_terms + hjd_color_apply with packed FP32x2 instructions: chroma
+// samples (2p, 2p+1) share a register pair, and so do the two pixels that use them -- neighbours for
+// 4:4:4, two apart for 2:1 horizontal sampling.  Every lane of a packed add / multiply is the IEEE
+// operation of the scalar code (rounded once, never fused), and -(a*b) == (-a)*b exactly, so
+// G = (y - 0.34414 cb) - 0.71414 cr keeps its two roundings.  A third fewer issue slots than scalar.
+template <int HS, int NP>
+__device__ __forceinline__ void hjd_color_n(const uint32_t* yw, const uint32_t* cbw, const uint32_t* crw, uint32_t* out)
+{
+    constexpr int NC = NP >> HS, D = 1 << HS;
+    static_assert(NC % 2 == 0, "chroma samples are processed in pairs");
+    float2 tx[NC / 2], tyn[NC / 2], tzn[NC / 2], tw[NC / 2];
+    const float2 m128 = make_float2(-128.0f, -128.0f);
+#pragma unroll
+    for (int p = 0; p < NC / 2; p++) {
+        const float2 cb = __fadd2_rn(make_float2(hjd_byte_f(cbw, 2 * p), hjd_byte_f(cbw, 2 * p + 1)), m128);   // (float)(Cb - 128), exact
+        const float2 cr = __fadd2_rn(make_float2(hjd_byte_f(crw, 2 * p), hjd_byte_f(crw, 2 * p + 1)), m128);
+        tx[p]  = __fmul2_rn(make_float2(1.402f, 1.402f), cr);
+        tyn[p] = __fmul2_rn(make_float2(-0.34414f, -0.34414f), cb);
+        tzn[p] = __fmul2_rn(make_float2(-0.71414f, -0.71414f), cr);
+        tw[p]  = __fmul2_rn(make_float2(1.772f, 1.772f), cb);
+    }
+    int ch[3 * NP];                       // R, G, B before clamping
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        if (((i >> HS) & 1) != 0) continue;                  // second pixel of a pair
+        const int j = i + D, p = (i >> HS) >> 1;
+        const float2 y2 = make_float2(hjd_byte_f(yw, i), hjd_byte_f(yw, j));
+        // loadjpg.cpp:873-879 with the argument swap of the call at 918 resolved; (int) truncates
+        const float2 r2 = __fadd2_rn(y2, tx[p]);
+        const float2 g2 = __fadd2_rn(__fadd2_rn(y2, tyn[p]), tzn[p]);
+        const float2 b2 = __fadd2_rn(y2, tw[p]);
+        ch[3 * i] = __float2int_rz(r2.x); ch[3 * i + 1] = __float2int_rz(g2.x); ch[3 * i + 2] = __float2int_rz(b2.x);
+        ch[3 * j] = __float2int_rz(r2.y); ch[3 * j + 1] = __float2int_rz(g2.y); ch[3 * j + 2] = __float2int_rz(b2.y);
+    }
+#pragma unroll
+    for (int w = 0; w < 3 * NP / 4; w++)  // Clamp (loadjpg.cpp:83-91) + pack, two values per instruction
+        out[w] = hjd_pack_sat_u8(ch[4 * w + 1], ch[4 * w], hjd_pack_sat_u8(ch[4 * w + 3], ch[4 * w + 2], 0u));
+}
+#endif
 
 template <int HS>
 __device__ __forceinline__ void hjd_color_16(const uint32_t yw[4], const uint32_t cbw[4], const uint32_t crw[4],
