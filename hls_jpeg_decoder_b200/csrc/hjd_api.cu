@@ -18,6 +18,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <algorithm>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------
@@ -114,6 +115,7 @@ struct hjd_batch {
     std::vector<HjdTableSet> tsets;
     std::vector<HjdQuantSet> qsets;
     std::vector<HjdEntropyWork> work;
+    std::vector<HjdEntropySeg> segs;
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
     std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
@@ -133,7 +135,7 @@ struct hjd_batch {
     bool uploaded = false, decoded = false;
     int launches = 0;
 
-    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_istart, d_coef, d_planes, d_rgb, d_status;
+    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_istart, d_coef, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
     PinBuf h_meta, h_flag;
 };
@@ -201,7 +203,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release();
+    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release();
     b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
     b->d_ss.release(); b->d_sswork.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
@@ -237,7 +239,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->chunks.clear();
     b->imgs.assign(n, HjdImageDesc());
     b->parse_status.assign(n, 0);
-    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear();
+    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear(); b->segs.clear();
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
     b->ss.clear(); b->sswork.clear();
@@ -379,14 +381,12 @@ static int upload_common(hjd_batch* b, bool chunked)
         }
         if (n == 0) b->chunks.clear();
     }
-    // per chunk: extents, grid bounds and the entropy work list (runs of <= HJD_ENT_THREADS consecutive
-    // intervals sharing one table set; a run never crosses a chunk boundary)
+    // per chunk: extents, grid bounds and the entropy work list (never crossing a chunk boundary)
     for (Chunk& c : b->chunks) {
         c.work0 = (uint32_t)b->work.size();
         c.arena_lo = ~0ull; c.arena_hi = 0;
         c.rgb_lo = b->imgs[c.img0].rgb_off;
         c.rgb_hi = (c.img1 < n) ? b->imgs[c.img1].rgb_off : b->rgb_bytes;
-        uint32_t cur_first = 0, cur_n = 0, cur_img = 0, cur_ts = 0;
         for (int i = c.img0; i < c.img1; i++) {
             const HjdImageDesc& d = b->imgs[i];
             if (files[i].ptr && files[i].size > 0) {
@@ -402,18 +402,35 @@ static int upload_common(hjd_batch* b, bool chunked)
                 const uint32_t strips = (d.mcus_x + S - 1) / S * d.mcus_y;
                 if (strips > c.max_strips) c.max_strips = strips;
             }
-            uint32_t left = d.n_intervals, g = d.interval_base;
-            while (left) {
-                if (cur_n && (cur_ts != d.table_set || cur_n == HJD_ENT_THREADS)) {
-                    b->work.push_back(HjdEntropyWork{cur_first, cur_n, cur_img, cur_ts});
-                    cur_n = 0;
-                }
-                if (!cur_n) { cur_first = g; cur_img = (uint32_t)i; cur_ts = d.table_set; }
-                const uint32_t take = left < (HJD_ENT_THREADS - cur_n) ? left : (HJD_ENT_THREADS - cur_n);
-                cur_n += take; g += take; left -= take;
-            }
         }
-        if (cur_n) b->work.push_back(HjdEntropyWork{cur_first, cur_n, cur_img, cur_ts});
+        // entropy work items: the chunk's images grouped by table set (batch order kept inside a group),
+        // their intervals packed into CTAs of HJD_ENT_THREADS as segments
+        {
+            std::vector<int> order;
+            for (int i = c.img0; i < c.img1; i++) if (b->imgs[i].n_intervals) order.push_back(i);
+            std::stable_sort(order.begin(), order.end(),
+                             [&](int x, int y) { return b->imgs[x].table_set < b->imgs[y].table_set; });
+            HjdEntropyWork w{0, 0, 0, 0};
+            auto flush = [&]() {
+                if (w.n_intervals) b->work.push_back(w);
+                w = HjdEntropyWork{(uint32_t)b->segs.size(), 0, 0, 0};
+            };
+            flush();
+            for (int i : order) {
+                const HjdImageDesc& d = b->imgs[i];
+                if (w.n_intervals && w.table_set != d.table_set) flush();
+                uint32_t left = d.n_intervals, g = d.interval_base;
+                while (left) {
+                    if (w.n_intervals == HJD_ENT_THREADS) flush();
+                    w.table_set = d.table_set;
+                    const uint32_t take = left < (HJD_ENT_THREADS - w.n_intervals) ? left : (HJD_ENT_THREADS - w.n_intervals);
+                    b->segs.push_back(HjdEntropySeg{g, w.n_intervals, (uint32_t)i, take});
+                    w.n_segs++;
+                    w.n_intervals += take; g += take; left -= take;
+                }
+            }
+            if (w.n_intervals) b->work.push_back(w);
+        }
         c.work1 = (uint32_t)b->work.size();
         if (c.arena_lo == ~0ull) c.arena_lo = c.arena_hi = 0;
     }
@@ -424,6 +441,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_tsets.ensure(sizeof(HjdTableSet) * (b->tsets.size() + 1)));
     CU(b->d_qsets.ensure(sizeof(HjdQuantSet) * (b->qsets.size() + 1)));
     CU(b->d_work.ensure(sizeof(HjdEntropyWork) * (b->work.size() + 1)));
+    CU(b->d_segs.ensure(sizeof(HjdEntropySeg) * (b->segs.size() + 1)));
     CU(b->d_istart.ensure(sizeof(uint32_t) * ((size_t)b->total_intervals + 2)));
     CU(b->d_coef.ensure(b->total_blocks * 128 + 256));
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
@@ -459,18 +477,21 @@ static int upload_common(hjd_batch* b, bool chunked)
     const size_t sz_ts = sizeof(HjdTableSet) * b->tsets.size();
     const size_t sz_qs = sizeof(HjdQuantSet) * b->qsets.size();
     const size_t sz_wk = sizeof(HjdEntropyWork) * b->work.size();
+    const size_t sz_sg = sizeof(HjdEntropySeg) * b->segs.size();
     const size_t sz_is = sizeof(uint32_t) * b->host_istart.size();
     const size_t sz_ss = sizeof(HjdSsImage) * b->ss.size();
     const size_t sz_sw = sizeof(HjdSsWork) * b->sswork.size();
     size_t o_imgs = 0, o_ts = align_up(o_imgs + sz_imgs, 256), o_qs = align_up(o_ts + sz_ts, 256),
            o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256),
-           o_ss = align_up(o_is + sz_is, 256), o_sw = align_up(o_ss + sz_ss, 256), tot = o_sw + sz_sw;
+           o_ss = align_up(o_is + sz_is, 256), o_sw = align_up(o_ss + sz_ss, 256),
+           o_sg = align_up(o_sw + sz_sw, 256), tot = o_sg + sz_sg;
     CU(b->h_meta.ensure(tot + 256));
     uint8_t* hm = (uint8_t*)b->h_meta.p;
     memcpy(hm + o_imgs, b->imgs.data(), sz_imgs);
     if (sz_ts) memcpy(hm + o_ts, b->tsets.data(), sz_ts);
     if (sz_qs) memcpy(hm + o_qs, b->qsets.data(), sz_qs);
     if (sz_wk) memcpy(hm + o_wk, b->work.data(), sz_wk);
+    if (sz_sg) memcpy(hm + o_sg, b->segs.data(), sz_sg);
     if (sz_is) memcpy(hm + o_is, b->host_istart.data(), sz_is);
     if (sz_ss) memcpy(hm + o_ss, b->ss.data(), sz_ss);
     if (sz_sw) memcpy(hm + o_sw, b->sswork.data(), sz_sw);
@@ -478,6 +499,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_ts) CU(cudaMemcpyAsync(b->d_tsets.p, hm + o_ts, sz_ts, cudaMemcpyHostToDevice, b->stream));
     if (sz_qs) CU(cudaMemcpyAsync(b->d_qsets.p, hm + o_qs, sz_qs, cudaMemcpyHostToDevice, b->stream));
     if (sz_wk) CU(cudaMemcpyAsync(b->d_work.p, hm + o_wk, sz_wk, cudaMemcpyHostToDevice, b->stream));
+    if (sz_sg) CU(cudaMemcpyAsync(b->d_segs.p, hm + o_sg, sz_sg, cudaMemcpyHostToDevice, b->stream));
     if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
     if (sz_ss) CU(cudaMemcpyAsync(b->d_ss.p, hm + o_ss, sz_ss, cudaMemcpyHostToDevice, b->stream));
     if (sz_sw) CU(cudaMemcpyAsync(b->d_sswork.p, hm + o_sw, sz_sw, cudaMemcpyHostToDevice, b->stream));
@@ -636,7 +658,8 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
     }
     if (c.work1 > c.work0) {
         CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
-                                      (const HjdEntropyWork*)b->d_work.p + c.work0, (int)(c.work1 - c.work0),
+                                      (const HjdEntropyWork*)b->d_work.p + c.work0, (const HjdEntropySeg*)b->d_segs.p,
+                                      (int)(c.work1 - c.work0),
                                       b->max_tabs, (int16_t*)b->d_coef.p, status, st));
         b->launches += 1;
     }

@@ -69,12 +69,21 @@ struct HjdImageDesc {
     uint32_t n_subs;             // self-sync path: sub-sequences in this image (0 = restart path)
 };
 
-// One CTA's worth of restart intervals for the entropy kernel; all share one table set.
+// One CTA's worth of restart intervals for the entropy kernel; all share one table set.  They are
+// given as segments (runs of consecutive intervals of one image): images that use the same tables are
+// packed into the same CTAs even when other images lie between them in the batch, so a batch of
+// small images with mixed tables (config 5: gray and colour thumbnails alternate) still fills its CTAs.
 struct HjdEntropyWork {
-    uint32_t first_interval;     // global interval index
-    uint32_t n_intervals;        // <= threads per CTA
-    uint32_t first_image;        // image that owns first_interval
+    uint32_t first_seg;          // index into the segment array
+    uint32_t n_segs;
+    uint32_t n_intervals;        // sum over the segments, <= threads per CTA
     uint32_t table_set;
+};
+struct HjdEntropySeg {
+    uint32_t first_interval;     // global interval index
+    uint32_t tid0;               // thread of the CTA that takes first_interval
+    uint32_t image;
+    uint32_t n;                  // intervals in this segment
 };
 
 // ---- self-synchronising path (restart-free scans) -------------------------------------------

@@ -239,7 +239,8 @@ __device__ __forceinline__ void br_refill(BitReader& r)
 __global__ void __launch_bounds__(HJD_ENT_THREADS, HJD_ENT_MINBLOCKS)
 hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
                       const HjdTableSet* __restrict__ tsets, const uint32_t* __restrict__ interval_start,
-                      const HjdEntropyWork* __restrict__ work, int16_t* __restrict__ coef,
+                      const HjdEntropyWork* __restrict__ work, const HjdEntropySeg* __restrict__ segs,
+                      int16_t* __restrict__ coef,
                       int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
@@ -271,9 +272,15 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     uint32_t blocks_left = 0, gblk = 0;
     int img = 0, bpm = 1, ny = 1;
     if ((uint32_t)tid < wk.n_intervals) {
-        const uint32_t g = wk.first_interval + tid;
-        img = (int)wk.first_image;
-        while (g >= imgs[img].interval_base + imgs[img].n_intervals) img++;
+        // the segment this thread falls into (tid0 is ascending): binary search
+        uint32_t lo = 0, hi = wk.n_segs - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (segs[wk.first_seg + mid].tid0 <= (uint32_t)tid) lo = mid; else hi = mid - 1;
+        }
+        const HjdEntropySeg sg = segs[wk.first_seg + lo];
+        const uint32_t g = sg.first_interval + ((uint32_t)tid - sg.tid0);
+        img = (int)sg.image;
         const HjdImageDesc* d = imgs + img;
         const uint32_t j = g - d->interval_base;
         const uint32_t ri = d->restart_interval;
@@ -388,7 +395,8 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
 }
 
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
-                                       const uint32_t* interval_start, const HjdEntropyWork* work, int n_work,
+                                       const uint32_t* interval_start, const HjdEntropyWork* work,
+                                       const HjdEntropySeg* segs, int n_work,
                                        int max_tabs, int16_t* coef, int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
@@ -402,7 +410,7 @@ cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc*
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    hjd_k_entropy_restart<<<n_work, HJD_ENT_THREADS, smem, st>>>(arena, imgs, tsets, interval_start, work, coef, status);
+    hjd_k_entropy_restart<<<n_work, HJD_ENT_THREADS, smem, st>>>(arena, imgs, tsets, interval_start, work, segs, coef, status);
     return cudaGetLastError();
 }
 

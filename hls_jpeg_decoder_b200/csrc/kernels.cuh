@@ -24,7 +24,8 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
 
 // Kernel 1a: restart-interval-parallel Huffman decode -> int16 coefficients (zig-zag order).
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
-                                       const uint32_t* interval_start, const HjdEntropyWork* work, int n_work,
+                                       const uint32_t* interval_start, const HjdEntropyWork* work,
+                                       const HjdEntropySeg* segs, int n_work,
                                        int max_tabs, int16_t* coef, int32_t* status, cudaStream_t st);
 
 // Kernel 2: dequantise + de-zig-zag + IDCT -> u8 planes (bit-exact with the reference's direct form).
