@@ -119,6 +119,7 @@ struct hjd_batch {
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
     std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
+    std::vector<HjdSsSeg> sssegs;        // their segments
     size_t n_sswork_main = 0;            // entries of the first list
     uint32_t ss_range = 0;               // sub-sequences per warp in the synchronisation rounds
     uint32_t ss_range_req = 0;           // 0 = automatic
@@ -136,7 +137,7 @@ struct hjd_batch {
     int launches = 0;
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_istart, d_coef, d_planes, d_rgb, d_status;
-    DevBuf d_ss, d_sswork, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
+    DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
     PinBuf h_meta, h_flag;
 };
 
@@ -205,7 +206,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release();
     b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
-    b->d_ss.release(); b->d_sswork.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
+    b->d_ss.release(); b->d_sswork.release(); b->d_sssegs.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
     b->d_flag.release();
     b->h_meta.release(); b->h_flag.release();
@@ -242,7 +243,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear(); b->segs.clear();
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
-    b->ss.clear(); b->sswork.clear();
+    b->ss.clear(); b->sswork.clear(); b->sssegs.clear();
     b->ss_subs = b->ss_chunks = 0;
     b->ss_dst_bytes = 0;
     b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
@@ -314,7 +315,6 @@ static int upload_common(hjd_batch* b, bool chunked)
             d.n_intervals = 0;
             d.sub_base = si.sub_base;
             d.n_subs = si.n_subs;
-            for (uint32_t f = 0; f < si.n_subs; f += HJD_SS_THREADS) b->sswork.push_back(HjdSsWork{(uint32_t)b->ss.size(), f});
             b->ss.push_back(si);
             b->ss_subs += si.n_subs;
             b->ss_chunks += si.n_chunks;
@@ -447,13 +447,49 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
     if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
-    // synchronisation rounds: longer ranges make the re-decode lists denser, shorter ones give more
-    // independent warps; pick by the amount of work.  Their work list is staged behind the first one.
-    b->n_sswork_main = b->sswork.size();
-    b->ss_range = b->ss_range_req ? b->ss_range_req : b->ss_subs >= 400000 ? 256 : b->ss_subs >= 150000 ? 128 : 64;
-    for (size_t k = 0; k < b->ss.size(); k++)
-        for (uint32_t f = 0; f < b->ss[k].n_subs; f += HJD_SS_FIX_WARPS * b->ss_range)
-            b->sswork.push_back(HjdSsWork{(uint32_t)k, f});
+    // Work lists of kernel 1b.  Images are grouped by table set (batch order kept inside a group) and their
+    // sub-sequences packed into CTAs as segments, so small restart-free images share CTAs.
+    // Synchronisation rounds: one range per warp; longer ranges make the re-decode lists denser, shorter
+    // ones give more independent warps: pick by the amount of work.  That list is staged behind the first.
+    {
+        std::vector<uint32_t> order(b->ss.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (uint32_t)k;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            return b->imgs[b->ss[x].img].table_set < b->imgs[b->ss[y].img].table_set;
+        });
+        HjdSsWork w{0, 0, 0, 0};
+        auto flush = [&]() {
+            if (w.n_subs) b->sswork.push_back(w);
+            w = HjdSsWork{(uint32_t)b->sssegs.size(), 0, 0, 0};
+        };
+        flush();
+        for (uint32_t k : order) {
+            const uint32_t ts = b->imgs[b->ss[k].img].table_set;
+            if (w.n_subs && w.table_set != ts) flush();
+            uint32_t left = b->ss[k].n_subs, f = 0;
+            while (left) {
+                if (w.n_subs == HJD_SS_THREADS) flush();
+                w.table_set = ts;
+                const uint32_t take = left < (HJD_SS_THREADS - w.n_subs) ? left : (HJD_SS_THREADS - w.n_subs);
+                b->sssegs.push_back(HjdSsSeg{k, f, w.n_subs, take});
+                w.n_segs++; w.n_subs += take; f += take; left -= take;
+            }
+        }
+        flush();
+        b->n_sswork_main = b->sswork.size();
+        b->ss_range = b->ss_range_req ? b->ss_range_req : b->ss_subs >= 400000 ? 256 : b->ss_subs >= 150000 ? 128 : 64;
+        for (uint32_t k : order) {
+            const uint32_t ts = b->imgs[b->ss[k].img].table_set;
+            for (uint32_t f = 0; f < b->ss[k].n_subs; f += b->ss_range) {
+                if (w.n_segs == HJD_SS_FIX_WARPS || (w.n_segs && w.table_set != ts)) flush();
+                w.table_set = ts;
+                const uint32_t take = b->ss[k].n_subs - f < b->ss_range ? b->ss[k].n_subs - f : b->ss_range;
+                b->sssegs.push_back(HjdSsSeg{k, f, 0, take});
+                w.n_segs++; w.n_subs += take;
+            }
+        }
+        flush();
+    }
 
     if (!b->ss.empty()) {
         uint32_t scan_n = b->ss_chunks + 1;
@@ -461,6 +497,7 @@ static int upload_common(hjd_batch* b, bool chunked)
         if (4 * b->ss_subs + 2 > scan_n) scan_n = 4 * b->ss_subs + 2;
         CU(b->d_ss.ensure(sizeof(HjdSsImage) * b->ss.size()));
         CU(b->d_sswork.ensure(sizeof(HjdSsWork) * b->sswork.size()));
+        CU(b->d_sssegs.ensure(sizeof(HjdSsSeg) * (b->sssegs.size() + 1)));
         CU(b->d_destuff.ensure(b->ss_dst_bytes + 256));
         CU(b->d_dlen.ensure(sizeof(uint32_t) * b->ss.size()));
         CU(b->d_counts.ensure(sizeof(uint32_t) * ((size_t)b->ss_chunks + 2)));
@@ -478,13 +515,14 @@ static int upload_common(hjd_batch* b, bool chunked)
     const size_t sz_qs = sizeof(HjdQuantSet) * b->qsets.size();
     const size_t sz_wk = sizeof(HjdEntropyWork) * b->work.size();
     const size_t sz_sg = sizeof(HjdEntropySeg) * b->segs.size();
+    const size_t sz_s2 = sizeof(HjdSsSeg) * b->sssegs.size();
     const size_t sz_is = sizeof(uint32_t) * b->host_istart.size();
     const size_t sz_ss = sizeof(HjdSsImage) * b->ss.size();
     const size_t sz_sw = sizeof(HjdSsWork) * b->sswork.size();
     size_t o_imgs = 0, o_ts = align_up(o_imgs + sz_imgs, 256), o_qs = align_up(o_ts + sz_ts, 256),
            o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256),
            o_ss = align_up(o_is + sz_is, 256), o_sw = align_up(o_ss + sz_ss, 256),
-           o_sg = align_up(o_sw + sz_sw, 256), tot = o_sg + sz_sg;
+           o_sg = align_up(o_sw + sz_sw, 256), o_s2 = align_up(o_sg + sz_sg, 256), tot = o_s2 + sz_s2;
     CU(b->h_meta.ensure(tot + 256));
     uint8_t* hm = (uint8_t*)b->h_meta.p;
     memcpy(hm + o_imgs, b->imgs.data(), sz_imgs);
@@ -492,6 +530,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_qs) memcpy(hm + o_qs, b->qsets.data(), sz_qs);
     if (sz_wk) memcpy(hm + o_wk, b->work.data(), sz_wk);
     if (sz_sg) memcpy(hm + o_sg, b->segs.data(), sz_sg);
+    if (sz_s2) memcpy(hm + o_s2, b->sssegs.data(), sz_s2);
     if (sz_is) memcpy(hm + o_is, b->host_istart.data(), sz_is);
     if (sz_ss) memcpy(hm + o_ss, b->ss.data(), sz_ss);
     if (sz_sw) memcpy(hm + o_sw, b->sswork.data(), sz_sw);
@@ -500,6 +539,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_qs) CU(cudaMemcpyAsync(b->d_qsets.p, hm + o_qs, sz_qs, cudaMemcpyHostToDevice, b->stream));
     if (sz_wk) CU(cudaMemcpyAsync(b->d_work.p, hm + o_wk, sz_wk, cudaMemcpyHostToDevice, b->stream));
     if (sz_sg) CU(cudaMemcpyAsync(b->d_segs.p, hm + o_sg, sz_sg, cudaMemcpyHostToDevice, b->stream));
+    if (sz_s2) CU(cudaMemcpyAsync(b->d_sssegs.p, hm + o_s2, sz_s2, cudaMemcpyHostToDevice, b->stream));
     if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
     if (sz_ss) CU(cudaMemcpyAsync(b->d_ss.p, hm + o_ss, sz_ss, cudaMemcpyHostToDevice, b->stream));
     if (sz_sw) CU(cudaMemcpyAsync(b->d_sswork.p, hm + o_sw, sz_sw, cudaMemcpyHostToDevice, b->stream));
@@ -604,6 +644,7 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     const HjdSsWork* work = (const HjdSsWork*)b->d_sswork.p;
     const int n_ss = (int)b->ss.size(), n_work = (int)b->n_sswork_main;
     const HjdSsWork* work_fix = work + b->n_sswork_main;
+    const HjdSsSeg* segs = (const HjdSsSeg*)b->d_sssegs.p;
     const int n_work_fix = (int)(b->sswork.size() - b->n_sswork_main);
     uint8_t* dst = (uint8_t*)b->d_destuff.p;
     uint32_t* dlen = (uint32_t*)b->d_dlen.p;
@@ -617,14 +658,14 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     CU(hjd_launch_destuff(arena, imgs, ss, n_ss, b->ss_chunks, (uint32_t*)b->d_counts.p, (uint32_t*)b->d_scantmp.p,
                           dst, dlen, st));
     b->launches += 2 + (b->ss_chunks + 1 > 2048 ? 3 : 1);
-    CU(hjd_launch_ss_spec(imgs, tsets, ss, work, n_work, dst, dlen, N, E, X, cnt, st));
+    CU(hjd_launch_ss_spec(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, E, X, cnt, st));
     b->launches += 1;
     const int max_rounds = (int)(N / 32) + 8;
     int r = 1;
     for (;; r++) {
         if (r > max_rounds) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
         CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
-        CU(hjd_launch_ss_fix(imgs, tsets, ss, work_fix, n_work_fix, dst, dlen, b->ss_range, N, E, X, cnt, flag, st));
+        CU(hjd_launch_ss_fix(imgs, tsets, ss, work_fix, segs, n_work_fix, dst, dlen, N, E, X, cnt, flag, st));
         b->launches += 1;
         CU(cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -633,7 +674,7 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     b->ss_rounds = r + 1;
     CU(cudaMemsetAsync(cnt + 4 * (size_t)N, 0, sizeof(uint32_t), st));
     CU(hjd_scan_u32(cnt, 4 * N + 1, (uint32_t*)b->d_scantmp.p, st));              // cnt[] becomes its exclusive prefix
-    CU(hjd_launch_ss_write(imgs, tsets, ss, work, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
+    CU(hjd_launch_ss_write(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
                            (int32_t*)b->d_status.p, st));
     CU(hjd_launch_ss_fill_tail(imgs, ss, n_ss, cnt, (int16_t*)b->d_coef.p, st));
     b->launches += 2 + (4 * N + 1 > 2048 ? 3 : 1);

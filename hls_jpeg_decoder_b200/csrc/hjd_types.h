@@ -108,11 +108,21 @@ struct HjdSsImage {
     uint64_t dst_off;      // offset of the de-stuffed stream in the de-stuff buffer
 };
 
-// One CTA of the speculative / write kernels (HJD_SS_THREADS consecutive sub-sequences of one image)
-// or of the synchronisation rounds (HJD_SS_FIX_WARPS ranges of sub-sequences).
+// One CTA of the speculative / write kernels: segments (runs of consecutive sub-sequences of one image)
+// that add up to at most HJD_SS_THREADS sub-sequences -- or of the synchronisation rounds: at most
+// HJD_SS_FIX_WARPS segments, one range per warp.  All images of a CTA share one table set; images are
+// grouped by table set, so a batch of small restart-free images fills its CTAs.
 struct HjdSsWork {
+    uint32_t first_seg;    // index into the HjdSsSeg array
+    uint32_t n_segs;
+    uint32_t n_subs;       // sum over the segments
+    uint32_t table_set;
+};
+struct HjdSsSeg {
     uint32_t ss;           // index into the HjdSsImage array
-    uint32_t first_sub;    // local index of the CTA's first sub-sequence
+    uint32_t first_sub;    // local index of the segment's first sub-sequence
+    uint32_t tid0;         // thread of the CTA that takes first_sub (speculative / write kernels)
+    uint32_t n;            // sub-sequences in the segment
 };
 
 // Per-image status bits written by kernels (mirrors HJD_IMG_WARN_* in include/hjd.h).

@@ -434,6 +434,21 @@ __device__ __forceinline__ void ss_load_tables(const HjdTableSet* ts, uint8_t* s
     }
 }
 
+// Which sub-sequence a thread of a speculative / write CTA owns: binary search over the CTA's segments
+// (tid0 ascending).  A thread beyond the CTA's sub-sequences gets li = 0xFFFFFFFF (owns nothing).
+__device__ __forceinline__ void ss_locate(const HjdSsWork& wk, const HjdSsSeg* __restrict__ segs, uint32_t tid,
+                                          uint32_t* ssi, uint32_t* li)
+{
+    uint32_t lo = 0, hi = wk.n_segs - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (segs[wk.first_seg + mid].tid0 <= tid) lo = mid; else hi = mid - 1;
+    }
+    const HjdSsSeg sg = segs[wk.first_seg + lo];
+    *ssi = sg.ss;
+    *li = tid < wk.n_subs ? sg.first_sub + (tid - sg.tid0) : 0xFFFFFFFFu;
+}
+
 // ------------------------------------------------------------------------------------------
 // step 1: speculative decode
 // ------------------------------------------------------------------------------------------
@@ -446,19 +461,21 @@ __device__ __forceinline__ void ss_load_tables(const HjdTableSet* ts, uint8_t* s
 __global__ void __launch_bounds__(HJD_SS_THREADS)
 hjd_k_ss_spec(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
               const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
+              const HjdSsSeg* __restrict__ segs,
               const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
               uint64_t* __restrict__ e_arr, uint64_t* __restrict__ x_arr, uint32_t* __restrict__ cnt_arr)
 {
     extern __shared__ __align__(16) uint8_t s_tab[];
     const HjdSsWork wk = work[blockIdx.x];
-    const HjdSsImage s = ss[wk.ss];
-    const HjdImageDesc* d = imgs + s.img;
-    ss_load_tables(tsets + d->table_set, s_tab);
+    ss_load_tables(tsets + wk.table_set, s_tab);
     __syncthreads();
 
-    const uint32_t li = wk.first_sub + threadIdx.x;                  // local sub-sequence index
+    uint32_t ssi, li;                                                // image, local sub-sequence index
+    ss_locate(wk, segs, threadIdx.x, &ssi, &li);
+    const HjdSsImage s = ss[ssi];
+    const HjdImageDesc* d = imgs + s.img;
     if (li >= s.n_subs) return;
-    const uint32_t L = dlen[wk.ss];
+    const uint32_t L = dlen[ssi];
     const uint32_t gi = s.sub_base + li;
     SsCount cnt = {0, 0, 0, 0};
     uint64_t e = 0, x = SS_INVALID;
@@ -482,11 +499,12 @@ hjd_k_ss_spec(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restri
 }
 
 cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                               const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                               const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                               const uint32_t* dlen,
                                uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    hjd_k_ss_spec<<<n_work, HJD_SS_THREADS, 6 * sizeof(HjdHuffTable), st>>>(imgs, tsets, ss, work, dst, dlen,
+    hjd_k_ss_spec<<<n_work, HJD_SS_THREADS, 6 * sizeof(HjdHuffTable), st>>>(imgs, tsets, ss, work, segs, dst, dlen,
                                                                            n_subs_total, e, x, cnt);
     return cudaGetLastError();
 }
@@ -505,7 +523,8 @@ cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tset
 __global__ void __launch_bounds__(HJD_SS_FIX_WARPS * 32)
 hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
              const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
-             const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t range, uint32_t n_subs_total,
+             const HjdSsSeg* __restrict__ segs,
+             const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
              uint64_t* __restrict__ e_arr, uint64_t* __restrict__ x_arr, uint32_t* __restrict__ cnt_arr,
              int* __restrict__ changed)
 {
@@ -518,14 +537,16 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
     uint64_t* sX = sE + kEntries;                                    // entry state it was computed from
     uint16_t* sL = (uint16_t*)(sX + kEntries);                       // sub-sequences to decode again
     const HjdSsWork wk = work[blockIdx.x];
-    const HjdSsImage s = ss[wk.ss];
+    const bool has_range = (uint32_t)warp < wk.n_segs;               // this warp's range (possibly of another image than its neighbours')
+    const HjdSsSeg sg = segs[wk.first_seg + (has_range ? warp : 0)];
+    const HjdSsImage s = ss[sg.ss];
     const HjdImageDesc* d = imgs + s.img;
 
-    const uint32_t L = dlen[wk.ss];
-    const uint32_t first = wk.first_sub + (uint32_t)warp * range;    // local index of the range's first sub-sequence
+    const uint32_t L = dlen[sg.ss];
+    const uint32_t first = sg.first_sub;                             // local index of the range's first sub-sequence
     uint32_t n_have = (L + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES; // sub-sequences that hold data
     if (n_have > s.n_subs) n_have = s.n_subs;
-    const int n_own = first < n_have ? (int)min(range, n_have - first) : 0;
+    const int n_own = has_range && first < n_have ? (int)min(sg.n, n_have - first) : 0;
     // The window starts HJD_SS_FIX_OVERLAP sub-sequences before the range: they are re-checked (and, if
     // need be, re-decoded) privately, never written back -- they belong to the previous warp, which
     // may be correcting them at this very moment.  So the entry state of the range no longer hinges on
@@ -545,7 +566,7 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
     // consistent, including the entry of its range against the previous range's last exit state.
     if (__any_sync(0xffffffffu, any) && lane == 0) *changed = 1;
     if (!__syncthreads_or(any)) return;                              // the usual case in the later rounds
-    ss_load_tables(tsets + d->table_set, s_tab);
+    ss_load_tables(tsets + wk.table_set, s_tab);
     __syncthreads();
 
     SsCtx cx;
@@ -594,14 +615,14 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
 }
 
 cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                              const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                              uint32_t range, uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
+                              const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                              const uint32_t* dlen,
+                              uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
                               int* changed, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    if (range == 0 || range > HJD_SS_FIX_MAXR || (range & 31u)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)HJD_SS_FIX_WARPS * (((HJD_SS_FIX_MAXR + HJD_SS_FIX_OVERLAP) * 18 + 15) & ~15u) + 6 * sizeof(HjdHuffTable);
-    hjd_k_ss_fix<<<n_work, HJD_SS_FIX_WARPS * 32, smem, st>>>(imgs, tsets, ss, work, dst, dlen, range, n_subs_total,
+    hjd_k_ss_fix<<<n_work, HJD_SS_FIX_WARPS * 32, smem, st>>>(imgs, tsets, ss, work, segs, dst, dlen, n_subs_total,
                                                              e, x, cnt, changed);
     return cudaGetLastError();
 }
@@ -621,6 +642,7 @@ cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets
 __global__ void __launch_bounds__(HJD_SS_THREADS)
 hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
                const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
+               const HjdSsSeg* __restrict__ segs,
                const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
                const uint64_t* __restrict__ x_arr, const uint32_t* __restrict__ prefix,
                int16_t* __restrict__ coef, int32_t* __restrict__ status)
@@ -630,9 +652,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     constexpr uint32_t kSlotBytes = HJD_SS_THREADS * 128, kListBytes = HJD_SS_THREADS * 8;
     uint8_t* s_tab = s_raw + kSlotBytes + kListBytes;
     const HjdSsWork wk = work[blockIdx.x];
-    const HjdSsImage s = ss[wk.ss];
-    const HjdImageDesc* d = imgs + s.img;
-    ss_load_tables(tsets + d->table_set, s_tab);
+    ss_load_tables(tsets + wk.table_set, s_tab);
     {
         uint4* z = (uint4*)s_raw;
         for (int i = threadIdx.x; i < HJD_SS_THREADS * 8; i += HJD_SS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
@@ -649,8 +669,11 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     const uint32_t warp_list = sh_list + (uint32_t)(tid & ~31) * 8u;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    const uint32_t li = wk.first_sub + tid;
-    const uint32_t L = dlen[wk.ss];
+    uint32_t ssi, li;                 // image, local sub-sequence index (0xFFFFFFFF: none)
+    ss_locate(wk, segs, (uint32_t)tid, &ssi, &li);
+    const HjdSsImage s = ss[ssi];
+    const HjdImageDesc* d = imgs + s.img;
+    const uint32_t L = dlen[ssi];
     const uint32_t bpm = d->blocks_per_mcu, ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
     const uint32_t n_blocks = (uint32_t)d->n_blocks;
     const uint32_t blk_base = (uint32_t)d->block_base;
@@ -771,7 +794,8 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
 }
 
 cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                                const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                                const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                                const uint32_t* dlen,
                                 uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
                                 int32_t* status, cudaStream_t st)
 {
@@ -783,7 +807,7 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, dst, dlen, n_subs_total, x, prefix,
+    hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, segs, dst, dlen, n_subs_total, x, prefix,
                                                         coef, status);
     return cudaGetLastError();
 }

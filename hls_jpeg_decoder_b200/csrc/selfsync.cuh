@@ -17,21 +17,24 @@ cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, c
 // e: exit states, x: the entry state each exit was computed from, cnt: [4][n_subs_total] blocks
 // started / DC-difference sums per component of each sub-sequence.
 cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                               const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                               const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                               const uint32_t* dlen,
                                uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt, cudaStream_t st);
 
-// One synchronisation round, in place.  `work` here has one entry per HJD_SS_FIX_WARPS * range
-// sub-sequences (range: multiple of 32, <= HJD_SS_FIX_MAXR).  changed is set to 1 when any warp had a
+// One synchronisation round, in place.  `work` here has at most HJD_SS_FIX_WARPS segments per entry, one
+// range (<= HJD_SS_FIX_MAXR sub-sequences) per warp.  changed is set to 1 when any warp had a
 // sub-sequence to decode again; the states are final after a round that leaves it 0.
 cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                              const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
-                              uint32_t range, uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
+                              const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                              const uint32_t* dlen,
+                              uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
                               int* changed, cudaStream_t st);
 
 // Final pass: every thread decodes, from its (now correct) entry state, the blocks that start in its
 // sub-sequence and writes them as whole 128-byte lines, DC un-differenced.  prefix = exclusive scan of cnt.
 cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                                const HjdSsWork* work, int n_work, const uint8_t* dst, const uint32_t* dlen,
+                                const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                                const uint32_t* dlen,
                                 uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
                                 int32_t* status, cudaStream_t st);
 
