@@ -819,27 +819,26 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
 // HJD_ST_OVERRUN).  The slab is not zero-filled beforehand, so the missing blocks are zeroed here to
 // keep the output a function of the input alone.  Nothing to do for a complete scan.
 __global__ void __launch_bounds__(256)
-hjd_k_ss_fill_tail(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __restrict__ ss,
+hjd_k_ss_fill_tail(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __restrict__ ss, int n_ss,
                    const uint32_t* __restrict__ prefix, int16_t* __restrict__ coef)
 {
-    const HjdSsImage s = ss[blockIdx.x];
+    // one warp per image: nothing but two loads for a complete scan
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n_ss) return;
+    const HjdSsImage s = ss[k];
     const HjdImageDesc* d = imgs + s.img;
     const uint64_t started = prefix[s.sub_base + s.n_subs] - prefix[s.sub_base];
     const uint64_t n_blocks = d->n_blocks;
     if (started >= n_blocks) return;
     uint4* out = (uint4*)coef + (d->block_base + started) * 8;
     const uint64_t n16 = (n_blocks - started) * 8;
-    for (uint64_t i = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.y * blockDim.x)
-        out[i] = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = lane; i < n16; i += 32) out[i] = make_uint4(0, 0, 0, 0);
 }
 
 cudaError_t hjd_launch_ss_fill_tail(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, const uint32_t* prefix,
                                     int16_t* coef, cudaStream_t st)
 {
     if (n_ss <= 0) return cudaSuccess;
-    for (int at = 0; at < n_ss; at += 32768) {
-        const int n = n_ss - at < 32768 ? n_ss - at : 32768;
-        hjd_k_ss_fill_tail<<<dim3((unsigned)n, 32), 256, 0, st>>>(imgs, ss + at, prefix, coef);
-    }
+    hjd_k_ss_fill_tail<<<(n_ss + 7) / 8, 256, 0, st>>>(imgs, ss, n_ss, prefix, coef);
     return cudaGetLastError();
 }
