@@ -116,6 +116,7 @@ struct hjd_batch {
     std::vector<HjdQuantSet> qsets;
     std::vector<HjdEntropyWork> work;
     std::vector<HjdEntropySeg> segs;
+    std::vector<uint32_t> mcu_cta;       // exclusive prefix of the per-image CTA counts of the per-MCU kernel (n + 1)
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
     std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
@@ -136,7 +137,7 @@ struct hjd_batch {
     bool uploaded = false, decoded = false;
     int launches = 0;
 
-    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_istart, d_coef, d_planes, d_rgb, d_status;
+    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_istart, d_coef, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
     PinBuf h_meta, h_flag;
 };
@@ -204,7 +205,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release();
+    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release(); b->d_mcucta.release();
     b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
     b->d_ss.release(); b->d_sswork.release(); b->d_sssegs.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
@@ -442,6 +443,10 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_qsets.ensure(sizeof(HjdQuantSet) * (b->qsets.size() + 1)));
     CU(b->d_work.ensure(sizeof(HjdEntropyWork) * (b->work.size() + 1)));
     CU(b->d_segs.ensure(sizeof(HjdEntropySeg) * (b->segs.size() + 1)));
+    b->mcu_cta.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++)
+        b->mcu_cta[i + 1] = b->mcu_cta[i] + (b->imgs[i].blocks_per_mcu ? (b->imgs[i].n_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS : 0);
+    CU(b->d_mcucta.ensure(sizeof(uint32_t) * ((size_t)n + 2)));
     CU(b->d_istart.ensure(sizeof(uint32_t) * ((size_t)b->total_intervals + 2)));
     CU(b->d_coef.ensure(b->total_blocks * 128 + 256));
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
@@ -516,13 +521,14 @@ static int upload_common(hjd_batch* b, bool chunked)
     const size_t sz_wk = sizeof(HjdEntropyWork) * b->work.size();
     const size_t sz_sg = sizeof(HjdEntropySeg) * b->segs.size();
     const size_t sz_s2 = sizeof(HjdSsSeg) * b->sssegs.size();
+    const size_t sz_mc = sizeof(uint32_t) * b->mcu_cta.size();
     const size_t sz_is = sizeof(uint32_t) * b->host_istart.size();
     const size_t sz_ss = sizeof(HjdSsImage) * b->ss.size();
     const size_t sz_sw = sizeof(HjdSsWork) * b->sswork.size();
     size_t o_imgs = 0, o_ts = align_up(o_imgs + sz_imgs, 256), o_qs = align_up(o_ts + sz_ts, 256),
            o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256),
            o_ss = align_up(o_is + sz_is, 256), o_sw = align_up(o_ss + sz_ss, 256),
-           o_sg = align_up(o_sw + sz_sw, 256), o_s2 = align_up(o_sg + sz_sg, 256), tot = o_s2 + sz_s2;
+           o_sg = align_up(o_sw + sz_sw, 256), o_s2 = align_up(o_sg + sz_sg, 256), o_mc = align_up(o_s2 + sz_s2, 256), tot = o_mc + sz_mc;
     CU(b->h_meta.ensure(tot + 256));
     uint8_t* hm = (uint8_t*)b->h_meta.p;
     memcpy(hm + o_imgs, b->imgs.data(), sz_imgs);
@@ -531,6 +537,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_wk) memcpy(hm + o_wk, b->work.data(), sz_wk);
     if (sz_sg) memcpy(hm + o_sg, b->segs.data(), sz_sg);
     if (sz_s2) memcpy(hm + o_s2, b->sssegs.data(), sz_s2);
+    if (sz_mc) memcpy(hm + o_mc, b->mcu_cta.data(), sz_mc);
     if (sz_is) memcpy(hm + o_is, b->host_istart.data(), sz_is);
     if (sz_ss) memcpy(hm + o_ss, b->ss.data(), sz_ss);
     if (sz_sw) memcpy(hm + o_sw, b->sswork.data(), sz_sw);
@@ -540,6 +547,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_wk) CU(cudaMemcpyAsync(b->d_work.p, hm + o_wk, sz_wk, cudaMemcpyHostToDevice, b->stream));
     if (sz_sg) CU(cudaMemcpyAsync(b->d_segs.p, hm + o_sg, sz_sg, cudaMemcpyHostToDevice, b->stream));
     if (sz_s2) CU(cudaMemcpyAsync(b->d_sssegs.p, hm + o_s2, sz_s2, cudaMemcpyHostToDevice, b->stream));
+    if (sz_mc) CU(cudaMemcpyAsync(b->d_mcucta.p, hm + o_mc, sz_mc, cudaMemcpyHostToDevice, b->stream));
     if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
     if (sz_ss) CU(cudaMemcpyAsync(b->d_ss.p, hm + o_ss, sz_ss, cudaMemcpyHostToDevice, b->stream));
     if (sz_sw) CU(cudaMemcpyAsync(b->d_sswork.p, hm + o_sw, sz_sw, cudaMemcpyHostToDevice, b->stream));
@@ -709,8 +717,9 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
         // default: kernels 2+3 fused per MCU, planes never reach HBM
         if (c.blocks) {
             CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
-                                  (uint8_t*)b->d_rgb.p, n, c.max_mcus, st));
-            b->launches += (n + 65534) / 65535;
+                                  (uint8_t*)b->d_rgb.p, (const uint32_t*)b->d_mcucta.p + c.img0, n,
+                                  b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, st));
+            b->launches += 1;
         }
         if (ev) CU(cudaEventRecord(ev[3], st));
     } else if ((b->flags & HJD_FLAG_FUSED) && !(b->flags & HJD_FLAG_KEEP_PLANES)) {
