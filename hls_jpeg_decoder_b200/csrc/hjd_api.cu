@@ -254,7 +254,49 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->any_parse_error = false;
     b->uploaded = b->decoded = false;
 
-    HjdParsed ps;
+    // Header parse and table hashing of every image, in parallel for large batches (8192 thumbnails: 9 ms
+    // of the host's time on one thread).  What the serial pass below needs is kept in a small record;
+    // the few images that bring a new table or quantisation set are parsed once more there.
+    struct Lite {
+        int status;
+        uint32_t width, height, restart_interval;
+        int ncomp, hf, vf;
+        size_t scan_off, scan_len;
+        uint64_t tk, qk;
+    };
+    std::vector<Lite> lite((size_t)n);
+    auto parse_range = [&](int lo, int hi) {
+        HjdParsed p;
+        for (int i = lo; i < hi; i++) {
+            Lite& l = lite[(size_t)i];
+            memset(&l, 0, sizeof l);
+            int st = (files[i].ptr && files[i].size > 0) ? hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &p)
+                                                         : HJD_IMG_ERR_NOT_JPEG;
+            if (st == HJD_IMG_OK && p.scan_len > 0xFFFFFF00ull) st = HJD_IMG_ERR_UNSUPPORTED;
+            l.status = st;
+            if (st != HJD_IMG_OK) continue;
+            l.width = p.width; l.height = p.height; l.restart_interval = p.restart_interval;
+            l.ncomp = p.ncomp; l.hf = p.hf; l.vf = p.vf;
+            l.scan_off = p.scan_off; l.scan_len = p.scan_len;
+            l.tk = hjd_table_key(p); l.qk = hjd_quant_key(p);
+        }
+    };
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int nt = n >= 2048 ? (int)(hw < 2 ? 1 : (hw > 8 ? 8 : hw)) : 1;
+        if (nt <= 1) parse_range(0, n);
+        else {
+            std::vector<std::thread> pool;
+            const int per = (n + nt - 1) / nt;
+            for (int k = 0; k < nt; k++) {
+                const int lo = k * per, hi = lo + per < n ? lo + per : n;
+                if (lo < hi) pool.emplace_back(parse_range, lo, hi);
+            }
+            for (auto& th : pool) th.join();
+        }
+    }
+
+    HjdParsed full;                    // re-parse target for images that bring new tables
     for (int i = 0; i < n; i++) {
         HjdImageDesc& d = b->imgs[i];
         memset(&d, 0, sizeof d);
@@ -262,31 +304,32 @@ static int upload_common(hjd_batch* b, bool chunked)
         d.block_base = b->total_blocks;
         d.rgb_off = b->rgb_bytes;
         d.y_off = d.cb_off = d.cr_off = b->plane_bytes;
-        int st = (files[i].ptr && files[i].size > 0) ? hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &ps)
-                                                     : HJD_IMG_ERR_NOT_JPEG;
-        if (st == HJD_IMG_OK && ps.scan_len > 0xFFFFFF00ull) st = HJD_IMG_ERR_UNSUPPORTED;
+        const Lite& ps = lite[(size_t)i];
+        int st = ps.status;
         uint32_t tset = 0, qset = 0;
+        bool have_full = false;
         if (st == HJD_IMG_OK) {
-            const uint64_t tk = hjd_table_key(ps);
-            auto it = b->tset_of.find(tk);
+            auto it = b->tset_of.find(ps.tk);
             if (it != b->tset_of.end()) tset = it->second;
             else {
+                hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &full);
+                have_full = true;
                 HjdTableSet ts;
-                st = hjd_build_table_set(ps, &ts);
+                st = hjd_build_table_set(full, &ts);
                 if (st == HJD_IMG_OK) {
-                    tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_of[tk] = tset;
+                    tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_of[ps.tk] = tset;
                     if (ts.n_tabs > b->max_tabs) b->max_tabs = ts.n_tabs;
                 }
             }
         }
         if (st == HJD_IMG_OK) {
-            const uint64_t qk = hjd_quant_key(ps);
-            auto it = b->qset_of.find(qk);
+            auto it = b->qset_of.find(ps.qk);
             if (it != b->qset_of.end()) qset = it->second;
             else {
+                if (!have_full) hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &full);
                 HjdQuantSet qs;
-                hjd_build_quant_set(ps, &qs);
-                qset = (uint32_t)b->qsets.size(); b->qsets.push_back(qs); b->qset_of[qk] = qset;
+                hjd_build_quant_set(full, &qs);
+                qset = (uint32_t)b->qsets.size(); b->qsets.push_back(qs); b->qset_of[ps.qk] = qset;
             }
         }
         b->parse_status[i] = st;
