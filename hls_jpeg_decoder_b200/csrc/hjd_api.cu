@@ -116,7 +116,7 @@ struct hjd_batch {
     std::vector<HjdQuantSet> qsets;
     std::vector<HjdEntropyWork> work;
     std::vector<HjdEntropySeg> segs;
-    std::vector<uint32_t> mcu_cta;       // exclusive prefix of the per-image CTA counts of the per-MCU kernel (n + 1)
+    std::vector<uint32_t> mcu_cta;       // exclusive prefix of the per-image MCU counts (n + 1), for the flat grid of the per-MCU kernel
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
     std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
@@ -488,7 +488,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_segs.ensure(sizeof(HjdEntropySeg) * (b->segs.size() + 1)));
     b->mcu_cta.assign((size_t)n + 1, 0);
     for (int i = 0; i < n; i++)
-        b->mcu_cta[i + 1] = b->mcu_cta[i] + (b->imgs[i].blocks_per_mcu ? (b->imgs[i].n_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS : 0);
+        b->mcu_cta[i + 1] = b->mcu_cta[i] + (b->imgs[i].blocks_per_mcu ? b->imgs[i].n_mcus : 0);
     CU(b->d_mcucta.ensure(sizeof(uint32_t) * ((size_t)n + 2)));
     CU(b->d_istart.ensure(sizeof(uint32_t) * ((size_t)b->total_intervals + 2)));
     CU(b->d_coef.ensure(b->total_blocks * 128 + 256));

@@ -968,7 +968,7 @@ template <bool FLAT>     // FLAT: exact 1-D grid with an image look-up (see belo
 __global__ void __launch_bounds__(HJD_MCU_THREADS, HJD_MCU_MINBLOCKS)
 hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
               const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb,
-              const uint32_t* __restrict__ cta_prefix, int n_images, int img_base)
+              const uint32_t* __restrict__ mcu_prefix, int n_images, int img_base)
 {
     __shared__ float s_cos[64];
     __shared__ uint2 s_tile[4][8 * HJD_MCU_THREADS];             // Y (left), Y (right), Cb, Cr: 8 rows x T threads x 8 bytes
@@ -978,22 +978,23 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
 
     // Two grid shapes (two instantiations: the kernel sits at the 128-register cap, and a run-time switch
     // cost 2 %).  Images of similar size: blockIdx.y = image, blockIdx.x = its CTA (no look-up).
-    // Mixed sizes (FLAT): a 1-D grid with exactly as many CTAs as the images need, the image
-    // found by binary search in cta_prefix[i] = CTAs of the images before i -- the 2-D grid is sized for
-    // the largest image and launched 2 M empty CTAs for one 4096x4096 image among 4096 thumbnails
-    // (2.2 ms instead of 0.6), while the search costs similar-sized batches 4 % (a chain of dependent loads
-    // in front of every CTA).
+    // Mixed or tiny sizes (FLAT): a 1-D grid over ALL MCUs of the batch, the image of each thread found by
+    // binary search in mcu_prefix[i] = MCUs of the images before i.  The 2-D grid is sized for the largest
+    // image and launched 2 M empty CTAs for one 4096x4096 image among 4096 thumbnails (2.2 ms instead of
+    // 0.6), and gives a 16x16 image a CTA with one active thread; the search costs similar-sized batches
+    // 4 % (a chain of dependent loads in front of every CTA), an empty CTA next to nothing.
     const HjdImageDesc* d;
     uint32_t m;
     if (FLAT) {
-        const uint32_t key = blockIdx.x + cta_prefix[0];
+        const uint32_t key = blockIdx.x * HJD_MCU_THREADS + t + mcu_prefix[0];
+        if (key >= mcu_prefix[n_images]) return;
         int lo = 0, hi = n_images - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (cta_prefix[mid] <= key) lo = mid; else hi = mid - 1;
+            if (mcu_prefix[mid] <= key) lo = mid; else hi = mid - 1;
         }
         d = imgs + lo;
-        m = (key - cta_prefix[lo]) * HJD_MCU_THREADS + t;
+        m = key - mcu_prefix[lo];
     } else {
         d = imgs + (blockIdx.y + img_base);
         m = blockIdx.x * HJD_MCU_THREADS + t;
@@ -1080,19 +1081,21 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
 }
 
 cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
-                               uint8_t* rgb, const uint32_t* cta_prefix, int n_images, uint32_t n_ctas,
+                               uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
                                uint32_t max_mcus, cudaStream_t st)
 {
-    if (n_images <= 0 || n_ctas == 0 || max_mcus == 0) return cudaSuccess;
+    if (n_images <= 0 || n_mcus == 0 || max_mcus == 0) return cudaSuccess;
     const unsigned gx = (max_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS;
-    // an empty CTA is cheap (config 5, 1.6 x as many CTAs as needed: 1.02 ms against 1.11 ms with the search)
-    if ((uint64_t)gx * (uint64_t)n_images <= (uint64_t)n_ctas * 4) {
+    // thread slots of the 2-D grid against MCUs there are: an idle slot is cheap (config 5 runs at 1.6 x:
+    // 1.02 ms against 1.11 ms with the search), so only clearly skewed or tiny-image batches go flat
+    if ((uint64_t)gx * HJD_MCU_THREADS * (uint64_t)n_images <= (uint64_t)n_mcus * 4) {
         for (int base = 0; base < n_images; base += 65535) {
             const int n = min(65535, n_images - base);
             hjd_k_mcu_rgb<false><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
         }
     } else {
-        hjd_k_mcu_rgb<true><<<n_ctas, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, cta_prefix, n_images, 0);
+        const unsigned g = (unsigned)(((uint64_t)n_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS);
+        hjd_k_mcu_rgb<true><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
     }
     return cudaGetLastError();
 }

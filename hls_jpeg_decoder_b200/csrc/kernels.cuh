@@ -44,9 +44,9 @@ cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs,
                                   uint8_t* rgb, int n_images, uint32_t max_strips, size_t smem, cudaStream_t st);
 
 // Kernels 2+3 fused per MCU: one thread = one MCU, coefficients -> RGB, no plane traffic, no barriers.
-// cta_prefix[i] = number of CTAs (HJD_MCU_THREADS MCUs each) of images 0..i-1 (any common offset);
-// n_ctas = cta_prefix[n_images] - cta_prefix[0]; max_mcus = MCUs of the largest image.  Batches of
-// similar-sized images get an (image, CTA) grid, mixed sizes an exact 1-D grid (see the kernel).
+// mcu_prefix[i] = MCUs of images 0..i-1 (any common offset; n_images + 1 entries);
+// n_mcus = mcu_prefix[n_images] - mcu_prefix[0]; max_mcus = MCUs of the largest image.  Batches of
+// similar-sized images get an (image, CTA) grid, mixed or tiny sizes a flat grid over all MCUs (see the kernel).
 cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
-                               uint8_t* rgb, const uint32_t* cta_prefix, int n_images, uint32_t n_ctas,
+                               uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
                                uint32_t max_mcus, cudaStream_t st);
