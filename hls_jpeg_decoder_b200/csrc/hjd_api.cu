@@ -87,6 +87,7 @@ struct FileRef { const uint8_t* ptr; int64_t size; uint64_t dev_off; };
 struct Chunk {
     int img0 = 0, img1 = 0;
     uint32_t work0 = 0, work1 = 0;
+    uint32_t slice0 = 0, slice1 = 0;          // marker-scan slices of this chunk's long scans
     uint64_t arena_lo = 0, arena_hi = 0;      // device arena byte range holding these files
     uint64_t rgb_lo = 0, rgb_hi = 0;
     uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0, max_mcus = 0;
@@ -116,6 +117,7 @@ struct hjd_batch {
     std::vector<HjdQuantSet> qsets;
     std::vector<HjdEntropyWork> work;
     std::vector<HjdEntropySeg> segs;
+    std::vector<HjdScanSlice> slices;    // marker-scan slices of long restart-marker scans
     std::vector<uint32_t> mcu_cta;       // exclusive prefix of the per-image MCU counts (n + 1), for the flat grid of the per-MCU kernel
     std::vector<uint32_t> host_istart;          // HJD_FLAG_HOST_SCAN only
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
@@ -137,7 +139,7 @@ struct hjd_batch {
     bool uploaded = false, decoded = false;
     int launches = 0;
 
-    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_istart, d_coef, d_planes, d_rgb, d_status;
+    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
     PinBuf h_meta, h_flag;
 };
@@ -205,7 +207,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release(); b->d_mcucta.release();
+    b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release(); b->d_mcucta.release(); b->d_slices.release(); b->d_slicecnt.release();
     b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
     b->d_ss.release(); b->d_sswork.release(); b->d_sssegs.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
@@ -241,7 +243,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->chunks.clear();
     b->imgs.assign(n, HjdImageDesc());
     b->parse_status.assign(n, 0);
-    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear(); b->segs.clear();
+    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear(); b->segs.clear(); b->slices.clear();
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
     b->ss.clear(); b->sswork.clear(); b->sssegs.clear();
@@ -447,6 +449,17 @@ static int upload_common(hjd_batch* b, bool chunked)
                 if (strips > c.max_strips) c.max_strips = strips;
             }
         }
+        // marker-scan slices of long restart-marker scans (kernel 0)
+        c.slice0 = (uint32_t)b->slices.size();
+        for (int i = c.img0; i < c.img1; i++) {
+            const HjdImageDesc& d = b->imgs[i];
+            if (d.restart_interval && d.n_intervals > 1 && d.scan_len > HJD_SCAN_SLICE_MIN) {
+                const uint64_t total = (uint64_t)d.scan_len + (d.scan_off & 15);
+                const uint32_t ns = (uint32_t)((total + HJD_SCAN_SLICE_BYTES - 1) / HJD_SCAN_SLICE_BYTES);
+                for (uint32_t k = 0; k < ns; k++) b->slices.push_back(HjdScanSlice{(uint32_t)i, k, ns, 0});
+            }
+        }
+        c.slice1 = (uint32_t)b->slices.size();
         // entropy work items: the chunk's images grouped by table set (batch order kept inside a group),
         // their intervals packed into CTAs of HJD_ENT_THREADS as segments
         {
@@ -486,6 +499,8 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_qsets.ensure(sizeof(HjdQuantSet) * (b->qsets.size() + 1)));
     CU(b->d_work.ensure(sizeof(HjdEntropyWork) * (b->work.size() + 1)));
     CU(b->d_segs.ensure(sizeof(HjdEntropySeg) * (b->segs.size() + 1)));
+    CU(b->d_slices.ensure(sizeof(HjdScanSlice) * (b->slices.size() + 1)));
+    CU(b->d_slicecnt.ensure(sizeof(uint32_t) * (b->slices.size() + 1)));
     b->mcu_cta.assign((size_t)n + 1, 0);
     for (int i = 0; i < n; i++)
         b->mcu_cta[i + 1] = b->mcu_cta[i] + (b->imgs[i].blocks_per_mcu ? b->imgs[i].n_mcus : 0);
@@ -565,13 +580,14 @@ static int upload_common(hjd_batch* b, bool chunked)
     const size_t sz_sg = sizeof(HjdEntropySeg) * b->segs.size();
     const size_t sz_s2 = sizeof(HjdSsSeg) * b->sssegs.size();
     const size_t sz_mc = sizeof(uint32_t) * b->mcu_cta.size();
+    const size_t sz_sl = sizeof(HjdScanSlice) * b->slices.size();
     const size_t sz_is = sizeof(uint32_t) * b->host_istart.size();
     const size_t sz_ss = sizeof(HjdSsImage) * b->ss.size();
     const size_t sz_sw = sizeof(HjdSsWork) * b->sswork.size();
     size_t o_imgs = 0, o_ts = align_up(o_imgs + sz_imgs, 256), o_qs = align_up(o_ts + sz_ts, 256),
            o_wk = align_up(o_qs + sz_qs, 256), o_is = align_up(o_wk + sz_wk, 256),
            o_ss = align_up(o_is + sz_is, 256), o_sw = align_up(o_ss + sz_ss, 256),
-           o_sg = align_up(o_sw + sz_sw, 256), o_s2 = align_up(o_sg + sz_sg, 256), o_mc = align_up(o_s2 + sz_s2, 256), tot = o_mc + sz_mc;
+           o_sg = align_up(o_sw + sz_sw, 256), o_s2 = align_up(o_sg + sz_sg, 256), o_mc = align_up(o_s2 + sz_s2, 256), o_sl = align_up(o_mc + sz_mc, 256), tot = o_sl + sz_sl;
     CU(b->h_meta.ensure(tot + 256));
     uint8_t* hm = (uint8_t*)b->h_meta.p;
     memcpy(hm + o_imgs, b->imgs.data(), sz_imgs);
@@ -581,6 +597,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_sg) memcpy(hm + o_sg, b->segs.data(), sz_sg);
     if (sz_s2) memcpy(hm + o_s2, b->sssegs.data(), sz_s2);
     if (sz_mc) memcpy(hm + o_mc, b->mcu_cta.data(), sz_mc);
+    if (sz_sl) memcpy(hm + o_sl, b->slices.data(), sz_sl);
     if (sz_is) memcpy(hm + o_is, b->host_istart.data(), sz_is);
     if (sz_ss) memcpy(hm + o_ss, b->ss.data(), sz_ss);
     if (sz_sw) memcpy(hm + o_sw, b->sswork.data(), sz_sw);
@@ -591,6 +608,7 @@ static int upload_common(hjd_batch* b, bool chunked)
     if (sz_sg) CU(cudaMemcpyAsync(b->d_segs.p, hm + o_sg, sz_sg, cudaMemcpyHostToDevice, b->stream));
     if (sz_s2) CU(cudaMemcpyAsync(b->d_sssegs.p, hm + o_s2, sz_s2, cudaMemcpyHostToDevice, b->stream));
     if (sz_mc) CU(cudaMemcpyAsync(b->d_mcucta.p, hm + o_mc, sz_mc, cudaMemcpyHostToDevice, b->stream));
+    if (sz_sl) CU(cudaMemcpyAsync(b->d_slices.p, hm + o_sl, sz_sl, cudaMemcpyHostToDevice, b->stream));
     if (sz_is) CU(cudaMemcpyAsync(b->d_istart.p, hm + o_is, sz_is, cudaMemcpyHostToDevice, b->stream));
     if (sz_ss) CU(cudaMemcpyAsync(b->d_ss.p, hm + o_ss, sz_ss, cudaMemcpyHostToDevice, b->stream));
     if (sz_sw) CU(cudaMemcpyAsync(b->d_sswork.p, hm + o_sw, sz_sw, cudaMemcpyHostToDevice, b->stream));
@@ -740,8 +758,10 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
     int32_t* status = (int32_t*)b->d_status.p;
     const int n = c.img1 - c.img0;
     if (!(b->flags & HJD_FLAG_HOST_SCAN) && n > 0) {
-        CU(hjd_launch_marker_scan(arena, imgs, (uint32_t*)b->d_istart.p, status, c.img0, n, st));
-        b->launches += 1;
+        CU(hjd_launch_marker_scan(arena, imgs, (uint32_t*)b->d_istart.p, status, c.img0, n,
+                                  (const HjdScanSlice*)b->d_slices.p + c.slice0, (int)(c.slice1 - c.slice0),
+                                  (uint32_t*)b->d_slicecnt.p + c.slice0, st));
+        b->launches += 1 + (c.slice1 > c.slice0 ? 2 : 0);
     }
     if (ev) {
         CU(cudaEventRecord(ev[1], st));

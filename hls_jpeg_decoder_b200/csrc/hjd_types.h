@@ -86,6 +86,16 @@ struct HjdEntropySeg {
     uint32_t n;                  // intervals in this segment
 };
 
+// Marker scan of long scans: slices of HJD_SCAN_SLICE_BYTES (a multiple of the 16 KB a CTA scans per step).
+#define HJD_SCAN_SLICE_MIN   (1u << 20)     // scans longer than this are sliced
+#define HJD_SCAN_SLICE_BYTES (1u << 16)
+struct HjdScanSlice {
+    uint32_t image;
+    uint32_t index;       // slice number inside the image; the slices of an image are consecutive in the list
+    uint32_t n_slices;    // of that image
+    uint32_t pad;
+};
+
 // ---- self-synchronising path (restart-free scans) -------------------------------------------
 #define HJD_SS_SUB_BYTES   128          // sub-sequence length in (de-stuffed) bytes = 1024 bits
 #define HJD_SS_MIN_BYTES   1024         // restart-free scans shorter than this stay on the 1-thread path

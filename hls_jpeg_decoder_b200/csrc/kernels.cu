@@ -60,30 +60,18 @@ cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc0
 // One CTA per image.  Every thread inspects 16 bytes per step; RSTn = FF D0..D7 (an FF inside
 // entropy data is always followed by 00, so the pair test is exact).  The marker ordinal comes
 // from a block-wide prefix sum; interval j+1 starts two bytes after marker j.
-__global__ void __launch_bounds__(256)
-hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
-                  uint32_t* __restrict__ interval_start, int32_t* __restrict__ status, int img_base)
+// The markers of bytes [beg, end) of one scan (offsets from the 16-byte aligned origin a0, multiples of the
+// 16 KB step), in order: 64 contiguous bytes per thread and step (four 16-byte loads), one barrier per
+// step (the per-warp counts are double buffered and every thread keeps the running total itself).
+// WRITE: marker number `running`+k starts interval `running`+k+1.  Returns the running total at the end.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t hjd_marker_range(const uint8_t* a0, uint32_t total, uint32_t lead, uint32_t beg,
+                                                     uint32_t end, uint32_t running, uint32_t* out,
+                                                     uint32_t n_intervals, uint32_t (*s_warp)[8])
 {
-    const int img = blockIdx.x + img_base;
-    const HjdImageDesc d = imgs[img];
-    uint32_t* out = interval_start + d.interval_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (d.n_intervals == 0) return;
-    if (tid == 0) out[0] = 0;
-    if (d.restart_interval == 0 || d.n_intervals <= 1) return;
-
-    // 64 contiguous bytes per thread and step (four 16-byte loads), one barrier per step: the per-warp
-    // counts are double buffered and every thread keeps the running total itself
-    __shared__ uint32_t s_warp[2][8];
-    uint32_t running = 0;
-
-    const uint8_t* s = arena + d.scan_off;
-    const uint32_t lead = (uint32_t)((uintptr_t)s & 15);
-    const uint8_t* a0 = s - lead;
-    const uint32_t total = d.scan_len + lead;
-
     int buf = 0;
-    for (uint32_t chunk = 0; chunk < total; chunk += 256 * 64, buf ^= 1) {
+    for (uint32_t chunk = beg; chunk < end && chunk < total; chunk += 256 * 64, buf ^= 1) {
         const uint32_t off0 = chunk + tid * 64;
         uint64_t mask = 0;                       // bit p: an RSTn marker starts at byte off0 + p
         uint4 v[4];
@@ -131,28 +119,107 @@ hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restr
             if (k < warp) before += c;
             block_total += c;
         }
-        uint32_t ord = before + incl - cnt;
-        while (mask) {
-            const int p = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            if (ord + 1 < d.n_intervals) out[ord + 1] = off0 + p + 2 - lead;
-            ord++;
+        if (WRITE) {
+            uint32_t ord = before + incl - cnt;
+            while (mask) {
+                const int p = __ffsll((long long)mask) - 1;
+                mask &= mask - 1;
+                if (ord + 1 < n_intervals) out[ord + 1] = off0 + p + 2 - lead;
+                ord++;
+            }
         }
         running += block_total;
     }
-    const uint32_t found = running;
+    return running;
+}
+
+// Fewer markers than intervals: the missing intervals become empty (the entropy kernel zero-fills them
+// and flags overrun) and the image is flagged.
+__device__ __forceinline__ void hjd_marker_finish(const HjdImageDesc& d, int img, uint32_t found, uint32_t* out,
+                                                  int32_t* status)
+{
     if (found != d.n_intervals - 1) {
-        if (tid == 0) atomicOr(&status[img], HJD_ST_RESTART);
-        // intervals with no marker become empty: the entropy kernel zero-fills them and flags overrun
-        for (uint32_t j = found + 1 + tid; j < d.n_intervals; j += 256) out[j] = d.scan_len;
+        if (threadIdx.x == 0) atomicOr(&status[img], HJD_ST_RESTART);
+        for (uint32_t j = found + 1 + threadIdx.x; j < d.n_intervals; j += 256) out[j] = d.scan_len;
     }
 }
 
+__global__ void __launch_bounds__(256)
+hjd_k_marker_scan(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
+                  uint32_t* __restrict__ interval_start, int32_t* __restrict__ status, int img_base)
+{
+    const int img = blockIdx.x + img_base;
+    const HjdImageDesc d = imgs[img];
+    uint32_t* out = interval_start + d.interval_base;
+    if (d.n_intervals == 0) return;
+    if (threadIdx.x == 0) out[0] = 0;
+    if (d.restart_interval == 0 || d.n_intervals <= 1) return;
+    if (d.scan_len > HJD_SCAN_SLICE_MIN) return;            // long scans: hjd_k_marker_slice_*
+
+    __shared__ uint32_t s_warp[2][8];
+    const uint8_t* s = arena + d.scan_off;
+    const uint32_t lead = (uint32_t)((uintptr_t)s & 15);
+    const uint32_t total = d.scan_len + lead;
+    const uint32_t found = hjd_marker_range<true>(s - lead, total, lead, 0, total, 0, out, d.n_intervals, s_warp);
+    hjd_marker_finish(d, img, found, out, status);
+}
+
+// Long scans (one CTA would walk them alone long after the rest of the batch is done: 0.31 ms for a
+// 4096x4096 image) are cut into slices of HJD_SCAN_SLICE_BYTES: count per slice, then every slice adds up
+// the counts of the slices before it and numbers its markers.
+__global__ void __launch_bounds__(256)
+hjd_k_marker_slice_count(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
+                         const HjdScanSlice* __restrict__ slices, uint32_t* __restrict__ slice_cnt)
+{
+    __shared__ uint32_t s_warp[2][8];
+    const HjdScanSlice sl = slices[blockIdx.x];
+    const HjdImageDesc d = imgs[sl.image];
+    const uint8_t* s = arena + d.scan_off;
+    const uint32_t lead = (uint32_t)((uintptr_t)s & 15);
+    const uint32_t beg = sl.index * HJD_SCAN_SLICE_BYTES;
+    const uint32_t n = hjd_marker_range<false>(s - lead, d.scan_len + lead, lead, beg, beg + HJD_SCAN_SLICE_BYTES, 0,
+                                               nullptr, d.n_intervals, s_warp);
+    if (threadIdx.x == 0) slice_cnt[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(256)
+hjd_k_marker_slice_write(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
+                         const HjdScanSlice* __restrict__ slices, const uint32_t* __restrict__ slice_cnt,
+                         uint32_t* __restrict__ interval_start, int32_t* __restrict__ status)
+{
+    __shared__ uint32_t s_warp[2][8];
+    __shared__ uint32_t s_red[8];
+    const HjdScanSlice sl = slices[blockIdx.x];
+    const HjdImageDesc d = imgs[sl.image];
+    uint32_t* out = interval_start + d.interval_base;
+    // markers in the slices of this image before this one (the slices of an image are consecutive)
+    uint32_t part = 0;
+    for (uint32_t k = threadIdx.x; k < sl.index; k += 256) part += slice_cnt[blockIdx.x - sl.index + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) before += s_red[k];
+    const uint8_t* s = arena + d.scan_off;
+    const uint32_t lead = (uint32_t)((uintptr_t)s & 15);
+    const uint32_t beg = sl.index * HJD_SCAN_SLICE_BYTES;
+    const uint32_t found = hjd_marker_range<true>(s - lead, d.scan_len + lead, lead, beg, beg + HJD_SCAN_SLICE_BYTES,
+                                                  before, out, d.n_intervals, s_warp);
+    if (sl.index + 1 == sl.n_slices) hjd_marker_finish(d, (int)sl.image, found, out, status);
+}
+
 cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* imgs, uint32_t* interval_start,
-                                   int32_t* status, int first_image, int n_images, cudaStream_t st)
+                                   int32_t* status, int first_image, int n_images, const HjdScanSlice* slices,
+                                   int n_slices, uint32_t* slice_cnt, cudaStream_t st)
 {
     if (n_images <= 0) return cudaSuccess;
     hjd_k_marker_scan<<<n_images, 256, 0, st>>>(arena, imgs, interval_start, status, first_image);
+    if (n_slices > 0) {
+        hjd_k_marker_slice_count<<<n_slices, 256, 0, st>>>(arena, imgs, slices, slice_cnt);
+        hjd_k_marker_slice_write<<<n_slices, 256, 0, st>>>(arena, imgs, slices, slice_cnt, interval_start, status);
+    }
     return cudaGetLastError();
 }
 

@@ -18,9 +18,11 @@
 // Upload the IDCT constants (host libm values, loadjpg.cpp:96-102,120).
 cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00);
 
-// Kernel 0: RSTn marker scan -> interval_start[] (one CTA per image), images [first_image, first_image + n).
+// Kernel 0: RSTn marker scan -> interval_start[] (one CTA per image), images [first_image, first_image + n);
+// scans longer than HJD_SCAN_SLICE_MIN are done by the n_slices slice CTAs instead (count, then number).
 cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* imgs, uint32_t* interval_start,
-                                   int32_t* status, int first_image, int n_images, cudaStream_t st);
+                                   int32_t* status, int first_image, int n_images, const HjdScanSlice* slices,
+                                   int n_slices, uint32_t* slice_cnt, cudaStream_t st);
 
 // Kernel 1a: restart-interval-parallel Huffman decode -> int16 coefficients (zig-zag order).
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,

@@ -386,6 +386,34 @@ def test_selfsync_padding_after_the_last_block_is_not_an_error(hjd, port):
             assert np.array_equal(d.rgb(i), o["rgb"]), i
 
 
+def test_long_restart_scans_use_the_sliced_marker_scan(hjd):
+    """Scans above 1 MB are cut into 64 KB slices by kernel 0 (count, then number the markers): the
+    interval table must be what the host scan finds, i.e. the same RGB, for a clean image, for one
+    with a marker removed and in a batch with small images on both sides."""
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    big = encode_jpeg(synth_rgb(3072, 2304, 81), 92, "4:2:0", 8)
+    inf_len = len(big)
+    assert inf_len > (1 << 20) + 4096
+    small = cases.small_cases()["420_100x70_ri2"]
+    broken = bytearray(big)
+    k = broken.find(b"\xff\xd3", len(broken) // 2)
+    assert k > 0
+    del broken[k:k + 2]                                        # one RSTn gone
+    files = [small, big, small, bytes(broken), small]
+    with hjd.BatchDecoder(0) as d1, hjd.BatchDecoder(0, hjd.FLAG_HOST_SCAN) as d2:
+        for d in (d1, d2):
+            d.upload(files)
+            d.decode()
+        s1, s2 = d1.status(), d2.status()
+        assert s1[0] == 0 and s1[1] == 0 and s1[2] == 0 and s1[4] == 0, s1
+        assert s1[3] > 0 and (s1[3] & 8), s1                    # HJD_IMG_WARN_RESTART
+        assert d1.info(1).scan_bytes > (1 << 20)
+        for i in (0, 1, 2, 4):
+            assert np.array_equal(d1.rgb(i), d2.rgb(i)), i
+        assert np.array_equal(d1.coefficients()[:d1.info(2).block_base + d1.info(2).n_blocks],
+                              d2.coefficients()[:d2.info(2).block_base + d2.info(2).n_blocks])
+
+
 def _patch_dqt(jpg: bytes, value: int) -> bytes:
     """Overwrite every 8-bit quantisation table entry with `value`."""
     b = bytearray(jpg)
