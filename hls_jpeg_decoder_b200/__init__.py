@@ -23,9 +23,9 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 
 import numpy as np
 
-__all__ = ["ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
+__all__ = ["probe", "ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_FUSED", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HJD_LIB_PATH") or os.path.join(_HERE, "libhjd.so")   # override: tuning builds only
@@ -33,7 +33,6 @@ INCLUDE_PATH = os.path.join(os.path.dirname(_HERE), "include", "hjd.h")
 
 FLAG_KEEP_PLANES = 1
 FLAG_HOST_SCAN = 2
-FLAG_FUSED = 4
 FLAG_NO_SELFSYNC = 8
 FLAG_FUSED_MCU = 16
 
@@ -112,6 +111,8 @@ _SIGS = {
     "hjd_host_alloc": (c_void_p, [c_size_t]),
     "hjd_host_free": (None, [c_void_p]),
     "hjd_get_idct_tables": (None, [c_void_p, c_void_p]),
+    "hjd_probe_jpeg": (c_int, [c_void_p, c_int64, POINTER(ImageInfo)]),
+    "hjd_huff_lookup_probe": (c_uint32, [c_void_p, c_void_p, c_int, c_int, c_uint32]),
 }
 
 
@@ -182,6 +183,14 @@ def JpegGetImageSize(buf: bytes):
     if not lib().hjd_get_image_size(data.ctypes.data, data.size, ctypes.byref(w), ctypes.byref(h)):
         raise HjdError(f"JpegGetImageSize failed: {_err()}")
     return w.value, h.value
+
+
+def probe(buf: bytes):
+    """Header parse only (no GPU): (status, ImageInfo) -- the per-image status a batch would report."""
+    data = np.frombuffer(buf, dtype=np.uint8)
+    o = ImageInfo()
+    st = lib().hjd_probe_jpeg(data.ctypes.data if data.size else None, data.size, ctypes.byref(o))
+    return int(st), o
 
 
 def WriteBMP24(szBmpFileName: str, Width: int, Height: int, RGB) -> None:

@@ -3,10 +3,8 @@
 #include <stdint.h>
 #include "hjd_types.h"
 
-// Byte offsets inside HjdHuffTable (lut, limit, delta, vals) for 32-bit shared-window addressing.
-#define HJD_TAB_LIMIT_OFF (HJD_LUT_SIZE * 2)
-#define HJD_TAB_DELTA_OFF (HJD_LUT_SIZE * 2 + 68)
-#define HJD_TAB_VALS_OFF  (HJD_LUT_SIZE * 2 + 136)
+// Byte offset of the second-level table inside HjdHuffTable, for 32-bit shared-window addressing.
+#define HJD_TAB_LUT2_OFF (HJD_LUT_SIZE * 2)
 
 // Meaning of a decoded symbol (see HjdHuffTable); also used by the host when it fills the LUT.
 __host__ __device__ __forceinline__ uint32_t hjd_sym_fields(uint32_t len, uint32_t sym, bool is_ac)
@@ -31,14 +29,13 @@ __device__ __forceinline__ uint32_t hjd_shr(uint32_t v, uint32_t n) { uint32_t r
 __device__ __forceinline__ uint32_t hjd_shl(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 
 
-// Slow path of the symbol lookup: codes longer than the first-level table.  t = shared-window address
-// of the table, peek16 = next 16 bits.  Returns the symbol fields, or 0 when no code matches.
-__device__ __forceinline__ uint32_t hjd_long_code(uint32_t t, uint32_t peek16, bool is_ac)
+// Second level of the symbol lookup: codes longer than the first-level table.  t = shared-window address
+// of the table, e1 = the first-level entry (len field 0), peek16 = next 16 bits.  Returns the symbol
+// fields, or 0 when no code matches.  Straight-line: one shared-memory load.
+__device__ __forceinline__ uint32_t hjd_long_code(uint32_t t, uint32_t e1, uint32_t peek16)
 {
-    uint32_t len = HJD_LUT_BITS + 1;
-    while (len <= 16 && peek16 >= hjd_lds_u32(t + HJD_TAB_LIMIT_OFF + len * 4)) len++;
-    if (len > 16) return 0;
-    const uint32_t dl = hjd_lds_u32(t + HJD_TAB_DELTA_OFF + len * 4);
-    const uint32_t sym = hjd_lds_u8(t + HJD_TAB_VALS_OFF + (((peek16 >> (16 - len)) + dl) & 255u));
-    return hjd_sym_fields(len, sym, is_ac);
+    const uint32_t nb = (e1 >> 5) & 7u;                                  // 1..6 more bits decide
+    const uint32_t idx = ((e1 >> 8) << 1) + hjd_shr(peek16 & ((1u << (16 - HJD_LUT_BITS)) - 1u), (16 - HJD_LUT_BITS) - nb);
+    const uint32_t e = hjd_lds_u16(t + HJD_TAB_LUT2_OFF + ((idx & (HJD_LUT2_SIZE - 1)) << 1));
+    return e1 ? e : 0u;
 }

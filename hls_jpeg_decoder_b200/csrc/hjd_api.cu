@@ -90,7 +90,7 @@ struct Chunk {
     uint32_t slice0 = 0, slice1 = 0;          // marker-scan slices of this chunk's long scans
     uint64_t arena_lo = 0, arena_hi = 0;      // device arena byte range holding these files
     uint64_t rgb_lo = 0, rgb_hi = 0;
-    uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0, max_mcus = 0;
+    uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_mcus = 0;
     uint64_t blocks = 0;
 };
 
@@ -109,6 +109,7 @@ struct hjd_batch {
     std::vector<FileRef> files;
     const uint8_t* contig_src = nullptr;      // host address of device-arena offset 0 (arena uploads)
     int overlap = 1;                                               // 0: one chunk, one stream (stage timings)
+    int chunk_images = 0;                                          // > 0: images per chunk asked for by the caller of hjd_batch_decode_host
 
     // host metadata of the uploaded batch
     std::vector<HjdImageDesc> imgs;
@@ -128,12 +129,13 @@ struct hjd_batch {
     uint32_t ss_range_req = 0;           // 0 = automatic
     uint32_t ss_subs = 0, ss_chunks = 0;
     uint64_t ss_dst_bytes = 0;
-    int ss_rounds = 0;                          // sync rounds of the last decode
+    bool ss_ran = false;                        // the last decode ran kernel 1b (its round count is in d_flag)
+    int max_sync_ctas = 1;                      // grid limit of the cooperative synchronisation kernel on this device
     std::vector<uint8_t> host_restart_warn;     // HJD_FLAG_HOST_SCAN only
-    std::unordered_map<uint64_t, uint32_t> tset_of, qset_of;
+    std::unordered_multimap<uint64_t, uint32_t> tset_of, qset_of;   // content hash -> candidate sets (verified byte for byte)
+    std::vector<HjdRawTables> tset_raw, qset_raw;                    // what each set was built from
     uint64_t total_blocks = 0, rgb_bytes = 0, plane_bytes = 0, scan_bytes = 0, pixels = 0, arena_bytes = 0;
-    uint32_t total_intervals = 0, max_blocks = 0, max_w = 0, max_h = 0, max_strips = 0;
-    size_t fused_smem = 0;
+    uint32_t total_intervals = 0, max_blocks = 0, max_w = 0, max_h = 0;
     int max_tabs = 1;
     bool any_parse_error = false;
     bool uploaded = false, decoded = false;
@@ -141,7 +143,7 @@ struct hjd_batch {
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
-    PinBuf h_meta, h_flag;
+    PinBuf h_meta;
 };
 
 static void compute_idct_constants(float cos_tab[64], float* cc0, float* cc00)
@@ -189,6 +191,8 @@ extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = hjd_kernels_init_device();            // function attributes are per device
+    if (e == cudaSuccess) e = hjd_selfsync_init_device(&b->max_sync_ctas);
     if (e == cudaSuccess) {
         float cos_tab[64], c0, c00;
         compute_idct_constants(cos_tab, &c0, &c00);
@@ -212,7 +216,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     b->d_ss.release(); b->d_sswork.release(); b->d_sssegs.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
     b->d_flag.release();
-    b->h_meta.release(); b->h_flag.release();
+    b->h_meta.release();
     for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     for (int i = 0; i < HJD_MARK_SLOTS; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
     for (int i = 0; i < HJD_NSTREAMS; i++) { if (b->aux[i]) { cudaStreamSynchronize(b->aux[i]); cudaStreamDestroy(b->aux[i]); } if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]); }
@@ -243,15 +247,14 @@ static int upload_common(hjd_batch* b, bool chunked)
     b->chunks.clear();
     b->imgs.assign(n, HjdImageDesc());
     b->parse_status.assign(n, 0);
-    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->work.clear(); b->segs.clear(); b->slices.clear();
+    b->tsets.clear(); b->qsets.clear(); b->tset_of.clear(); b->qset_of.clear(); b->tset_raw.clear(); b->qset_raw.clear(); b->work.clear(); b->segs.clear(); b->slices.clear();
     b->host_istart.clear();
     b->host_restart_warn.assign(n, 0);
     b->ss.clear(); b->sswork.clear(); b->sssegs.clear();
     b->ss_subs = b->ss_chunks = 0;
     b->ss_dst_bytes = 0;
     b->total_blocks = b->rgb_bytes = b->plane_bytes = b->scan_bytes = b->pixels = 0;
-    b->total_intervals = b->max_blocks = b->max_w = b->max_h = b->max_strips = 0;
-    b->fused_smem = 0;
+    b->total_intervals = b->max_blocks = b->max_w = b->max_h = 0;
     b->max_tabs = 1;
     b->any_parse_error = false;
     b->uploaded = b->decoded = false;
@@ -259,16 +262,26 @@ static int upload_common(hjd_batch* b, bool chunked)
     // Header parse and table hashing of every image, in parallel for large batches (8192 thumbnails: 9 ms
     // of the host's time on one thread).  What the serial pass below needs is kept in a small record;
     // the few images that bring a new table or quantisation set are parsed once more there.
+    // Table and quantisation sets are shared by images with identical DHT / DQT contents.  The 64-bit
+    // hash only finds candidates: every worker keeps the raw tables of the images that introduced a key
+    // (to that worker) and compares the bytes on a hit, so an image is either byte-identical to an earlier
+    // image of its worker (trep / qrep = that image) or a representative itself; representatives are
+    // compared byte for byte with the sets built so far in the serial pass.  A hash collision therefore
+    // costs a set of its own, never somebody else's tables.
     struct Lite {
         int status;
         uint32_t width, height, restart_interval;
         int ncomp, hf, vf;
         size_t scan_off, scan_len;
         uint64_t tk, qk;
+        int trep, qrep;            // image whose tables / quantisation tables these are byte-identical to (itself: a representative)
     };
     std::vector<Lite> lite((size_t)n);
     auto parse_range = [&](int lo, int hi) {
         HjdParsed p;
+        struct Seen { uint64_t key; int image; HjdRawTables raw; };
+        std::vector<Seen> seen_t, seen_q;
+        HjdRawTables raw;
         for (int i = lo; i < hi; i++) {
             Lite& l = lite[(size_t)i];
             memset(&l, 0, sizeof l);
@@ -281,6 +294,16 @@ static int upload_common(hjd_batch* b, bool chunked)
             l.ncomp = p.ncomp; l.hf = p.hf; l.vf = p.vf;
             l.scan_off = p.scan_off; l.scan_len = p.scan_len;
             l.tk = hjd_table_key(p); l.qk = hjd_quant_key(p);
+            hjd_raw_tables(p, &raw);
+            l.trep = l.qrep = i;
+            bool hit = false;
+            for (const Seen& sn : seen_t)
+                if (sn.key == l.tk && memcmp(sn.raw.huff, raw.huff, sizeof raw.huff) == 0) { l.trep = sn.image; hit = true; break; }
+            if (!hit && seen_t.size() < 64) seen_t.push_back(Seen{l.tk, i, raw});
+            hit = false;
+            for (const Seen& sn : seen_q)
+                if (sn.key == l.qk && memcmp(sn.raw.quant, raw.quant, sizeof raw.quant) == 0) { l.qrep = sn.image; hit = true; break; }
+            if (!hit && seen_q.size() < 64) seen_q.push_back(Seen{l.qk, i, raw});
         }
     };
     {
@@ -298,7 +321,9 @@ static int upload_common(hjd_batch* b, bool chunked)
         }
     }
 
-    HjdParsed full;                    // re-parse target for images that bring new tables
+    HjdParsed full;                    // re-parse target for the representatives
+    HjdRawTables full_raw;
+    std::vector<uint32_t> tset_of_img((size_t)n, 0), qset_of_img((size_t)n, 0);
     for (int i = 0; i < n; i++) {
         HjdImageDesc& d = b->imgs[i];
         memset(&d, 0, sizeof d);
@@ -311,29 +336,45 @@ static int upload_common(hjd_batch* b, bool chunked)
         uint32_t tset = 0, qset = 0;
         bool have_full = false;
         if (st == HJD_IMG_OK) {
-            auto it = b->tset_of.find(ps.tk);
-            if (it != b->tset_of.end()) tset = it->second;
-            else {
+            if (ps.trep != i) {                                     // byte-identical to an earlier image of its worker
+                if (b->parse_status[ps.trep] != HJD_IMG_OK) st = b->parse_status[ps.trep];      // e.g. an over-subscribed DHT
+                tset = tset_of_img[(size_t)ps.trep];
+            } else {
                 hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &full);
+                hjd_raw_tables(full, &full_raw);
                 have_full = true;
-                HjdTableSet ts;
-                st = hjd_build_table_set(full, &ts);
-                if (st == HJD_IMG_OK) {
-                    tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_of[ps.tk] = tset;
-                    if (ts.n_tabs > b->max_tabs) b->max_tabs = ts.n_tabs;
+                bool found = false;
+                auto range = b->tset_of.equal_range(ps.tk);
+                for (auto it = range.first; it != range.second && !found; ++it)
+                    if (memcmp(b->tset_raw[it->second].huff, full_raw.huff, sizeof full_raw.huff) == 0) { tset = it->second; found = true; }
+                if (!found) {
+                    HjdTableSet ts;
+                    st = hjd_build_table_set(full, &ts);
+                    if (st == HJD_IMG_OK) {
+                        tset = (uint32_t)b->tsets.size(); b->tsets.push_back(ts); b->tset_raw.push_back(full_raw);
+                        b->tset_of.emplace(ps.tk, tset);
+                        if (ts.n_tabs > b->max_tabs) b->max_tabs = ts.n_tabs;
+                    }
                 }
             }
         }
         if (st == HJD_IMG_OK) {
-            auto it = b->qset_of.find(ps.qk);
-            if (it != b->qset_of.end()) qset = it->second;
+            if (ps.qrep != i) qset = qset_of_img[(size_t)ps.qrep];
             else {
-                if (!have_full) hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &full);
-                HjdQuantSet qs;
-                hjd_build_quant_set(full, &qs);
-                qset = (uint32_t)b->qsets.size(); b->qsets.push_back(qs); b->qset_of[ps.qk] = qset;
+                if (!have_full) { hjd_parse_jpeg(files[i].ptr, (size_t)files[i].size, &full); hjd_raw_tables(full, &full_raw); }
+                bool found = false;
+                auto range = b->qset_of.equal_range(ps.qk);
+                for (auto it = range.first; it != range.second && !found; ++it)
+                    if (memcmp(b->qset_raw[it->second].quant, full_raw.quant, sizeof full_raw.quant) == 0) { qset = it->second; found = true; }
+                if (!found) {
+                    HjdQuantSet qs;
+                    hjd_build_quant_set(full, &qs);
+                    qset = (uint32_t)b->qsets.size(); b->qsets.push_back(qs); b->qset_raw.push_back(full_raw);
+                    b->qset_of.emplace(ps.qk, qset);
+                }
             }
         }
+        tset_of_img[(size_t)i] = tset; qset_of_img[(size_t)i] = qset;
         b->parse_status[i] = st;
         if (st != HJD_IMG_OK) { b->any_parse_error = true; continue; }   // n_intervals = n_blocks = 0: skipped
 
@@ -384,13 +425,6 @@ static int upload_common(hjd_batch* b, bool chunked)
         if (d.n_blocks > b->max_blocks) b->max_blocks = (uint32_t)d.n_blocks;
         if (ps.width > b->max_w) b->max_w = ps.width;
         if (ps.height > b->max_h) b->max_h = ps.height;
-        {
-            const uint32_t S = HJD_FUSED_THREADS / d.blocks_per_mcu;
-            const uint32_t strips = (d.mcus_x + S - 1) / S * d.mcus_y;
-            if (strips > b->max_strips) b->max_strips = strips;
-            const size_t sm = hjd_fused_smem_bytes(ps.ncomp, ps.hf, ps.vf);
-            if (sm > b->fused_smem) b->fused_smem = sm;
-        }
 
         if ((b->flags & HJD_FLAG_HOST_SCAN) && d.n_intervals) {
             const size_t at = b->host_istart.size();
@@ -413,12 +447,13 @@ static int upload_common(hjd_batch* b, bool chunked)
             if (want < 1) want = 1;
         }
         const uint64_t target = (b->total_blocks + want - 1) / (uint64_t)want;
+        const int per = (chunked && b->chunk_images > 0) ? b->chunk_images : 0;   // caller-chosen chunk length (hjd_batch_decode_host)
         Chunk c;
         c.img0 = 0;
         for (int i = 0; i < n; i++) {
             c.blocks += b->imgs[i].n_blocks;
             const bool last = (i == n - 1);
-            if (last || (c.blocks >= target && (int)b->chunks.size() < want - 1)) {
+            if (last || (per ? (i + 1 - c.img0 >= per) : (c.blocks >= target && (int)b->chunks.size() < want - 1))) {
                 c.img1 = i + 1;
                 b->chunks.push_back(c);
                 c = Chunk();
@@ -443,11 +478,6 @@ static int upload_common(hjd_batch* b, bool chunked)
             if (d.n_mcus > c.max_mcus) c.max_mcus = d.n_mcus;
             if (d.width > c.max_w) c.max_w = d.width;
             if (d.height > c.max_h) c.max_h = d.height;
-            if (d.blocks_per_mcu) {
-                const uint32_t S = HJD_FUSED_THREADS / d.blocks_per_mcu;
-                const uint32_t strips = (d.mcus_x + S - 1) / S * d.mcus_y;
-                if (strips > c.max_strips) c.max_strips = strips;
-            }
         }
         // marker-scan slices of long restart-marker scans (kernel 0)
         c.slice0 = (uint32_t)b->slices.size();
@@ -568,8 +598,7 @@ static int upload_common(hjd_batch* b, bool chunked)
         CU(b->d_ssE0.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssX.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssnb.ensure(sizeof(uint32_t) * (4 * (size_t)b->ss_subs + 4)));
-        CU(b->d_flag.ensure(sizeof(int) * 4));
-        CU(b->h_flag.ensure(sizeof(int) * 4));
+        CU(b->d_flag.ensure(sizeof(uint32_t) * 4));
     }
 
     // metadata: one pinned staging block, then async copies
@@ -701,8 +730,8 @@ extern "C" int hjd_batch_set_selfsync_range(hjd_batch* b, int range)
     return HJD_OK;
 }
 
-// Kernel 1b for all restart-free images of the batch (see selfsync.cu).  Runs on `st`; the
-// synchronisation rounds need the host to look at a flag, so this call blocks on the stream.
+// Kernel 1b for all restart-free images of the batch (see selfsync.cu).  Everything is enqueued on `st`;
+// the synchronisation rounds terminate on the device, so the host never waits here.
 static int run_selfsync(hjd_batch* b, cudaStream_t st)
 {
     if (b->ss.empty()) return HJD_OK;
@@ -720,33 +749,25 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
     uint64_t* E = (uint64_t*)b->d_ssE0.p;
     uint64_t* X = (uint64_t*)b->d_ssX.p;
     uint32_t* cnt = (uint32_t*)b->d_ssnb.p;                       // [4][ss_subs] (+1): starts, DC sums Y/Cb/Cr
-    int* flag = (int*)b->d_flag.p;
-    int* hflag = (int*)b->h_flag.p;
+    uint32_t* ctl = (uint32_t*)b->d_flag.p;                       // barrier count, last round with work, rounds run
     const uint32_t N = b->ss_subs;
 
+    CU(cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(cnt + 4 * (size_t)N, 0, sizeof(uint32_t), st));
     CU(hjd_launch_destuff(arena, imgs, ss, n_ss, b->ss_chunks, (uint32_t*)b->d_counts.p, (uint32_t*)b->d_scantmp.p,
                           dst, dlen, st));
     b->launches += 2 + (b->ss_chunks + 1 > 2048 ? 3 : 1);
     CU(hjd_launch_ss_spec(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, E, X, cnt, st));
-    b->launches += 1;
-    const int max_rounds = (int)(N / 32) + 8;
-    int r = 1;
-    for (;; r++) {
-        if (r > max_rounds) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
-        CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
-        CU(hjd_launch_ss_fix(imgs, tsets, ss, work_fix, segs, n_work_fix, dst, dlen, N, E, X, cnt, flag, st));
-        b->launches += 1;
-        CU(cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (*hflag == 0) break;
-    }
-    b->ss_rounds = r + 1;
-    CU(cudaMemsetAsync(cnt + 4 * (size_t)N, 0, sizeof(uint32_t), st));
+    // a chain of wrong entry states can cross one range per round at worst: ranges + a confirming round
+    const uint32_t max_rounds = N / 32 + 8;
+    CU(hjd_launch_ss_sync(imgs, tsets, ss, work_fix, segs, n_work_fix, dst, dlen, N, E, X, cnt, ctl, max_rounds,
+                          b->max_sync_ctas, st));
     CU(hjd_scan_u32(cnt, 4 * N + 1, (uint32_t*)b->d_scantmp.p, st));              // cnt[] becomes its exclusive prefix
     CU(hjd_launch_ss_write(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
                            (int32_t*)b->d_status.p, st));
     CU(hjd_launch_ss_fill_tail(imgs, ss, n_ss, cnt, (int16_t*)b->d_coef.p, st));
-    b->launches += 2 + (4 * N + 1 > 2048 ? 3 : 1);
+    b->launches += 4 + (4 * N + 1 > 2048 ? 3 : 1);
+    b->ss_ran = true;
     return HJD_OK;
 }
 
@@ -776,20 +797,13 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
         b->launches += 1;
     }
     if (ev) CU(cudaEventRecord(ev[2], st));
-    if (!(b->flags & (HJD_FLAG_KEEP_PLANES | HJD_FLAG_FUSED))) {
+    if (!(b->flags & HJD_FLAG_KEEP_PLANES)) {
         // default: kernels 2+3 fused per MCU, planes never reach HBM
         if (c.blocks) {
             CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                   (uint8_t*)b->d_rgb.p, (const uint32_t*)b->d_mcucta.p + c.img0, n,
                                   b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, st));
             b->launches += 1;
-        }
-        if (ev) CU(cudaEventRecord(ev[3], st));
-    } else if ((b->flags & HJD_FLAG_FUSED) && !(b->flags & HJD_FLAG_KEEP_PLANES)) {
-        if (c.blocks) {
-            CU(hjd_launch_idct_color((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
-                                     (uint8_t*)b->d_rgb.p, n, c.max_strips, b->fused_smem, st));
-            b->launches += (n + 65534) / 65535;
         }
         if (ev) CU(cudaEventRecord(ev[3], st));
     } else {
@@ -812,6 +826,7 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
 {
     cudaStream_t main = b->stream;
     b->launches = 0;
+    b->ss_ran = false;
     if (b->any_parse_error && b->rgb_bytes) CU(cudaMemsetAsync(b->d_rgb.p, 0, b->rgb_bytes, main));
     CU(cudaEventRecord(b->ev[0], main));
     if (b->chunks.size() <= 1) {
@@ -840,20 +855,30 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
     }
     CU(cudaEventRecord(b->ev_fork, main));
     for (int s = 0; s < HJD_NSTREAMS; s++) CU(cudaStreamWaitEvent(b->aux[s], b->ev_fork, 0));
-    for (size_t k = 0; k < b->chunks.size(); k++) {
+    // From here on work is in flight on the chunk streams: whatever fails below, they are joined back into
+    // the main stream before returning, so that the next upload (which synchronises only the main
+    // stream before it rewrites the slabs) cannot overtake them.
+    int rc_all = HJD_OK;
+    for (size_t k = 0; k < b->chunks.size() && rc_all == HJD_OK; k++) {
         const Chunk& c = b->chunks[k];
         cudaStream_t st = b->aux[k % HJD_NSTREAMS];
-        if (h2d) { int rc = copy_files(b, c, st); if (rc) return rc; }
-        int rc = launch_chunk(b, c, st, nullptr);
-        if (rc) return rc;
-        if (rgb_host && c.rgb_hi > c.rgb_lo)
-            CU(cudaMemcpyAsync(rgb_host + c.rgb_lo, (const uint8_t*)b->d_rgb.p + c.rgb_lo, c.rgb_hi - c.rgb_lo,
-                               cudaMemcpyDeviceToHost, st));
+        if (h2d) rc_all = copy_files(b, c, st);
+        if (rc_all == HJD_OK) rc_all = launch_chunk(b, c, st, nullptr);
+        if (rc_all == HJD_OK && rgb_host && c.rgb_hi > c.rgb_lo) {
+            cudaError_t e = cudaMemcpyAsync(rgb_host + c.rgb_lo, (const uint8_t*)b->d_rgb.p + c.rgb_lo, c.rgb_hi - c.rgb_lo,
+                                            cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc_all = fail(HJD_ERR_CUDA, "cudaMemcpyAsync (RGB chunk)", cudaGetErrorString(e));
+        }
     }
     for (int s = 0; s < HJD_NSTREAMS; s++) {
-        CU(cudaEventRecord(b->ev_join[s], b->aux[s]));
-        CU(cudaStreamWaitEvent(main, b->ev_join[s], 0));
+        cudaError_t e = cudaEventRecord(b->ev_join[s], b->aux[s]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(main, b->ev_join[s], 0);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(b->aux[s]);                    // last resort: wait here
+            if (rc_all == HJD_OK) rc_all = fail(HJD_ERR_CUDA, "joining the chunk streams", cudaGetErrorString(e));
+        }
     }
+    if (rc_all != HJD_OK) return rc_all;
     CU(cudaEventRecord(b->ev[4], main));
     return HJD_OK;
 }
@@ -878,7 +903,15 @@ extern "C" int hjd_batch_sync(hjd_batch* b)
 }
 
 extern "C" int hjd_batch_num_images(const hjd_batch* b) { return b ? (int)b->imgs.size() : 0; }
-extern "C" int hjd_batch_selfsync_rounds(const hjd_batch* b) { return b ? b->ss_rounds : 0; }
+extern "C" int hjd_batch_selfsync_rounds(hjd_batch* b)
+{
+    // rounds the device-side loop ran in the last decode (working rounds + the one that confirmed); syncs
+    if (!b || !b->ss_ran || !b->d_flag.p) return 0;
+    uint32_t ctl[4] = {0, 0, 0, 0};
+    if (cudaSetDevice(b->device) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess ||
+        cudaMemcpy(ctl, b->d_flag.p, sizeof ctl, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int)(ctl[2] & 0x7FFFFFFFu);
+}
 
 extern "C" int hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* o)
 {
@@ -902,6 +935,11 @@ extern "C" int hjd_batch_get_status(hjd_batch* b, int32_t* status)
     if (n == 0) return HJD_OK;
     CU(cudaMemcpyAsync(status, b->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
+    if (b->ss_ran) {       // the device-side synchronisation loop reports here if it ever hit its round limit
+        uint32_t ctl[4] = {0, 0, 0, 0};
+        CU(cudaMemcpy(ctl, b->d_flag.p, sizeof ctl, cudaMemcpyDeviceToHost));
+        if (ctl[2] & 0x80000000u) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
+    }
     for (size_t i = 0; i < n; i++) {
         if (b->parse_status[i] != 0) status[i] = b->parse_status[i];
         else if (b->host_restart_warn[i]) status[i] |= HJD_IMG_WARN_RESTART;
@@ -1001,10 +1039,11 @@ extern "C" int hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const i
                                      int n, uint8_t* rgb_out, uint64_t rgb_capacity, uint64_t* rgb_offsets_out,
                                      int32_t* status_out, int chunk_images)
 {
-    (void)chunk_images;   // chunking is planned from the block counts (see upload_common)
-    if (!b || !arena || !offsets || !sizes || !rgb_out || n < 0) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "bad arguments");
+    if (!b || !arena || !offsets || !sizes || !rgb_out || n < 0 || chunk_images < 0) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "bad arguments");
     CU(cudaSetDevice(b->device));
+    b->chunk_images = chunk_images;                               // 0: chunks planned from the block counts (see upload_common)
     int rc = prepare_arena(b, arena, offsets, sizes, n, true);    // parse + metadata; files not copied yet
+    b->chunk_images = 0;
     if (rc) return rc;
     if (b->rgb_bytes > rgb_capacity) return fail(HJD_ERR_ARG, "hjd_batch_decode_host", "rgb_out too small");
     rc = run_chunks(b, true, rgb_out);                            // per chunk: H2D, kernels, D2H
@@ -1049,6 +1088,55 @@ extern "C" int hjd_get_image_size(const uint8_t* buf, int size, unsigned* width,
     if (width) *width = ps.width;
     if (height) *height = ps.height;
     return 1;
+}
+
+static void fill_info_from_parse(const HjdParsed& ps, hjd_image_info* o)
+{
+    memset(o, 0, sizeof *o);
+    o->status = ps.status;
+    if (ps.status != HJD_IMG_OK) return;
+    o->width = ps.width; o->height = ps.height; o->ncomp = (uint8_t)ps.ncomp; o->hf = (uint8_t)ps.hf; o->vf = (uint8_t)ps.vf;
+    o->blocks_per_mcu = (uint8_t)(ps.ncomp == 3 ? ps.hf * ps.vf + 2 : 1);
+    o->mcus_x = (ps.width + 8 * ps.hf - 1) / (8 * ps.hf);
+    o->mcus_y = (ps.height + 8 * ps.vf - 1) / (8 * ps.vf);
+    o->restart_interval = ps.restart_interval;
+    const uint32_t n_mcus = o->mcus_x * o->mcus_y;
+    o->n_intervals = ps.restart_interval ? (n_mcus + ps.restart_interval - 1) / ps.restart_interval : 1;
+    o->scan_bytes = (uint32_t)ps.scan_len;
+    o->n_blocks = (uint64_t)n_mcus * o->blocks_per_mcu;
+}
+
+extern "C" int hjd_probe_jpeg(const uint8_t* buf, int64_t size, hjd_image_info* out)
+{
+    HjdParsed ps;
+    const int st = (buf && size > 0) ? hjd_parse_jpeg(buf, (size_t)size, &ps) : HJD_IMG_ERR_NOT_JPEG;
+    if (buf && size > 0 && st == HJD_IMG_OK) {
+        HjdTableSet ts;
+        ps.status = hjd_build_table_set(ps, &ts);                  // an over-subscribed DHT is a per-image error too
+    } else ps.status = st;
+    if (out) fill_info_from_parse(ps, out);
+    return ps.status;
+}
+
+extern "C" uint32_t hjd_huff_lookup_probe(const uint8_t bits[16], const uint8_t* vals, int nvals, int is_ac, uint32_t peek16)
+{
+    static thread_local HjdHuffTable tab;
+    static thread_local HjdRawHuff cached;
+    static thread_local int cached_ac = -1;
+    HjdRawHuff raw;
+    memset(&raw, 0, sizeof raw);
+    if (!bits || !vals || nvals < 0 || nvals > 256) return 0xFFFFFFFFu;
+    memcpy(raw.bits, bits, 16);
+    memcpy(raw.vals, vals, (size_t)nvals);
+    raw.nvals = nvals;
+    raw.present = 1;
+    if (cached_ac != is_ac || memcmp(&cached, &raw, sizeof raw) != 0) {
+        cached_ac = -1;
+        if (!hjd_build_huff_table(raw, is_ac != 0, &tab)) return 0xFFFFFFFFu;
+        cached = raw;
+        cached_ac = is_ac;
+    }
+    return hjd_host_huff_lookup(&tab, peek16);
 }
 
 extern "C" int hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsigned* width, unsigned* height)

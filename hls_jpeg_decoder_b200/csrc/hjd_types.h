@@ -20,14 +20,16 @@
 //     kadv  advance of the zig-zag index: DC 1; AC run+1; EOB 64; ZRL 16; other size-0 symbols 0 (ignored)
 //   A coefficient is written at (k + kadv - 1) iff size != 0: a DC symbol with size 0 adds nothing to
 //   the predictor, and the output block is zero-filled beforehand.
-//   longer codes: the first L in (LUT_BITS, 16] with peek16 < limit[L]; symbol = vals[(peek16 >> (16-L)) + delta[L]]
+//   longer codes (second level): a first-level entry with len == 0 and the rest non-zero points at a
+//     sub-table: nb << 5 | (offset / 2) << 8, nb = 1..6 further bits to look at;
+//     lut2[offset + (the next nb bits)] has the same layout as a first-level entry (len = full length).
+//     0 (either level) = no such code.  One more shared-memory load instead of a search over the lengths:
+//     with ~12 symbols per block some lane of a warp holds a long code on every other step.
 #define HJD_SYM_FIELDS(len, size, kadv) ((uint32_t)(len) | (uint32_t)(size) << 5 | (uint32_t)(kadv) << 9)
+#define HJD_LUT2_SIZE   512                   // canonical codes: at most 256 (one entry per long code) + 126 (sub-tables that straddle a change of length)
 struct HjdHuffTable {
     uint16_t lut[HJD_LUT_SIZE];
-    uint32_t limit[17];      // exclusive upper bound of left-aligned codes of length <= L (0x10000 possible)
-    int32_t  delta[17];      // valptr[L] - mincode[L]
-    uint8_t  vals[256];
-    uint32_t pad[2];         // sizeof == 2448, a multiple of 16 (copied to shared memory as uint4)
+    uint16_t lut2[HJD_LUT2_SIZE];   // sizeof == 3072, a multiple of 16 (copied to shared memory as uint4)
 };
 
 // Huffman tables of one image (or of many images that share identical DHT segments).

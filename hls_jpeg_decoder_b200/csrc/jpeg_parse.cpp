@@ -59,6 +59,29 @@ int parse_dht(Reader& r, size_t end, HjdParsed* o)
 
 } // namespace
 
+size_t hjd_scan_length(const uint8_t* scan, size_t avail)
+{
+    // Large file that ends with EOI: taken as "nothing follows the scan" without walking it (a memchr walk
+    // over 1024 x 0.36 MB would cost the host tens of milliseconds per batch, on the critical path of the
+    // host-buffer decode).  A large file with a second image appended after its EOI (MPF) is therefore sized
+    // as before: decoded correctly, its trailer merely counted as scan bytes.
+    if (avail >= HJD_SCAN_WALK_MAX && scan[avail - 2] == 0xFF && scan[avail - 1] == 0xD9) return avail - 2;
+    // Otherwise (small files; trailer, padding, a caller's oversized buffer): the scan ends at the first
+    // marker that is neither a stuffed FF00 nor RSTn, so that what follows EOI is neither counted as
+    // restart markers nor sized and decoded as entropy data.
+    const uint8_t* p = scan;
+    const uint8_t* e = scan + avail;
+    while (p + 1 < e) {
+        p = (const uint8_t*)memchr(p, 0xFF, (size_t)(e - 1 - p));
+        if (!p) break;
+        const uint8_t m = p[1];
+        if (m == 0x00 || (m & 0xF8) == 0xD0) p += 2;
+        else if (m == 0xFF) p += 1;                                  // fill byte
+        else return (size_t)(p - scan);
+    }
+    return avail;
+}
+
 int hjd_parse_jpeg(const uint8_t* buf, size_t size, HjdParsed* o)
 {
     memset(o, 0, sizeof *o);
@@ -134,7 +157,7 @@ int hjd_parse_jpeg(const uint8_t* buf, size_t size, HjdParsed* o)
             uint8_t ss = r.u8(), se = r.u8(), ahal = r.u8();
             if (ss != 0 || se != 63 || ahal != 0) return o->status = HJD_IMG_ERR_UNSUPPORTED;
             o->scan_off = end;
-            o->scan_len = size - end;
+            o->scan_len = hjd_scan_length(buf + end, size - end);
             break;
         }
         // APPn, COM and anything else with a length: skipped (openjpg.cpp:448-461)
@@ -169,29 +192,73 @@ static uint32_t sym_fields(uint32_t len, uint32_t sym, bool is_ac)
 bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)
 {
     memset(t, 0, sizeof *t);
-    memcpy(t->vals, raw.vals, 256);
     // Canonical code assignment (what GenHuffCodes does, openjpg.cpp:48-66): codes of one length
     // are consecutive; the counter doubles when the length grows.
-    uint32_t code = 0;
-    int valptr = 0;
-    for (int L = 1; L <= 16; L++) {
-        int cnt = raw.bits[L - 1];
-        if (code + (uint32_t)cnt > (1u << L)) return false;          // over-subscribed
-        t->delta[L] = valptr - (int32_t)code;
-        if (L <= HJD_LUT_BITS) {
-            for (int k = 0; k < cnt; k++) {
-                uint32_t first = (code + (uint32_t)k) << (HJD_LUT_BITS - L);
-                const uint16_t e = (uint16_t)sym_fields((uint32_t)L, raw.vals[valptr + k], is_ac);
-                for (uint32_t j = 0; j < (1u << (HJD_LUT_BITS - L)); j++) t->lut[first + j] = e;
-            }
+    uint32_t first_code[17];
+    {
+        uint32_t code = 0;
+        for (int L = 1; L <= 16; L++) {
+            const uint32_t cnt = raw.bits[L - 1];
+            if (code + cnt > (1u << L)) return false;                // over-subscribed
+            first_code[L] = code;
+            code = (code + cnt) << 1;
         }
-        code += (uint32_t)cnt;
-        valptr += cnt;
-        t->limit[L] = code << (16 - L);
-        code <<= 1;
     }
-    t->limit[0] = 0;
+    // first level: every code of up to LUT_BITS bits, replicated over the bits that follow it
+    int valptr = 0;
+    for (int L = 1; L <= HJD_LUT_BITS; L++) {
+        for (int k = 0; k < raw.bits[L - 1]; k++) {
+            const uint32_t first = (first_code[L] + (uint32_t)k) << (HJD_LUT_BITS - L);
+            const uint16_t e = (uint16_t)sym_fields((uint32_t)L, raw.vals[valptr + k], is_ac);
+            for (uint32_t j = 0; j < (1u << (HJD_LUT_BITS - L)); j++) t->lut[first + j] = e;
+        }
+        valptr += raw.bits[L - 1];
+    }
+    // second level: per LUT_BITS-bit prefix that starts longer codes, a sub-table indexed by the next
+    // nb = (longest code under the prefix) - LUT_BITS bits
+    const int valptr_long = valptr;
+    uint8_t nb_of[HJD_LUT_SIZE];
+    memset(nb_of, 0, sizeof nb_of);
+    for (int L = HJD_LUT_BITS + 1; L <= 16; L++)
+        for (int k = 0; k < raw.bits[L - 1]; k++) {
+            const uint32_t prefix = (first_code[L] + (uint32_t)k) >> (L - HJD_LUT_BITS);
+            nb_of[prefix] = (uint8_t)(L - HJD_LUT_BITS);                // lengths ascend: the last one wins
+        }
+    uint32_t used = 0;
+    for (uint32_t p = 0; p < HJD_LUT_SIZE; p++) {
+        if (!nb_of[p]) continue;
+        if (used + (1u << nb_of[p]) > HJD_LUT2_SIZE) return false;      // cannot happen for canonical codes (see HJD_LUT2_SIZE)
+        t->lut[p] = (uint16_t)((uint32_t)nb_of[p] << 5 | (used >> 1) << 8);
+        used += 1u << nb_of[p];
+    }
+    valptr = valptr_long;
+    for (int L = HJD_LUT_BITS + 1; L <= 16; L++) {
+        for (int k = 0; k < raw.bits[L - 1]; k++) {
+            const uint32_t code = first_code[L] + (uint32_t)k;
+            const uint32_t prefix = code >> (L - HJD_LUT_BITS);
+            const uint32_t nb = nb_of[prefix], off = (uint32_t)(t->lut[prefix] >> 8) << 1;
+            const uint32_t rest = code & ((1u << (L - HJD_LUT_BITS)) - 1u);   // the bits after the prefix
+            const uint32_t rep = nb - (uint32_t)(L - HJD_LUT_BITS);          // bits that follow the code
+            const uint16_t e = (uint16_t)sym_fields((uint32_t)L, raw.vals[valptr + k], is_ac);
+            for (uint32_t j = 0; j < (1u << rep); j++) t->lut2[off + (rest << rep) + j] = e;
+        }
+        valptr += raw.bits[L - 1];
+    }
     return true;
+}
+
+uint32_t hjd_host_huff_lookup(const HjdHuffTable* t, uint32_t peek16)
+{
+    // host mirror of the kernels' symbol lookup (first level, then hjd_long_code in device_common.cuh)
+    peek16 &= 0xFFFFu;
+    uint32_t e = t->lut[peek16 >> (16 - HJD_LUT_BITS)];
+    if ((e & 31u) == 0) {
+        if (e == 0) return 0;
+        const uint32_t nb = (e >> 5) & 7u;
+        const uint32_t idx = ((e >> 8) << 1) + ((peek16 & ((1u << (16 - HJD_LUT_BITS)) - 1u)) >> ((16 - HJD_LUT_BITS) - nb));
+        e = t->lut2[idx & (HJD_LUT2_SIZE - 1)];
+    }
+    return e;
 }
 
 int hjd_build_table_set(const HjdParsed& p, HjdTableSet* out)
@@ -225,6 +292,22 @@ void hjd_build_quant_set(const HjdParsed& p, HjdQuantSet* out)
         for (int k = 0; k < 64; k++) out->q[c][k] = p.qt[p.tq[src]][k];
         for (int k = 0; k < 32; k++)
             out->qp[c][k] = (uint32_t)p.qt[p.tq[src]][2 * k] | ((uint32_t)p.qt[p.tq[src]][2 * k + 1] << 24);
+    }
+}
+
+void hjd_raw_tables(const HjdParsed& p, HjdRawTables* out)
+{
+    memset(out, 0, sizeof *out);
+    out->huff[0] = out->quant[0] = (uint8_t)p.ncomp;
+    for (int c = 0; c < p.ncomp; c++) {
+        uint8_t* h = out->huff + 4 + c * 2 * (16 + 256);
+        const HjdRawHuff* t[2] = {&p.dc[p.td[c]], &p.ac[p.ta[c]]};
+        for (int k = 0; k < 2; k++, h += 16 + 256) {
+            memcpy(h, t[k]->bits, 16);
+            memcpy(h + 16, t[k]->vals, (size_t)(t[k]->nvals < 256 ? t[k]->nvals : 256));
+        }
+        const int src = (p.ncomp == 3 && c == 1) ? 2 : c;           // Cb is de-quantised with Cr's table (loadjpg.cpp:984)
+        memcpy(out->quant + 4 + c * 64, p.qt[p.tq[src]], 64);
     }
 }
 

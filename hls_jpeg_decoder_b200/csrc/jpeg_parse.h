@@ -34,13 +34,30 @@ struct HjdParsed {
 // Header parse only (no table building).  Returns HJD_IMG_OK or a negative HJD_IMG_ERR_*.
 int hjd_parse_jpeg(const uint8_t* buf, size_t size, HjdParsed* out);
 
+// Length of the entropy-coded segment that starts at `scan` (avail bytes to the end of the file): up to
+// the first marker that is neither FF00 nor RSTn (EOI normally).  Scans of HJD_SCAN_WALK_MAX bytes or
+// more whose file ends with EOI are not walked.
+#define HJD_SCAN_WALK_MAX (64u * 1024u)
+size_t hjd_scan_length(const uint8_t* scan, size_t avail);
+
 // Flattened lookup table from BITS/HUFFVAL.  Returns false if the code is over-subscribed.
 bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* out);
+
+// Host mirror of the kernels' two-level symbol lookup: the entry for the next 16 bits (0: no such code).
+uint32_t hjd_host_huff_lookup(const HjdHuffTable* t, uint32_t peek16);
 
 // Resolve the per-component tables of a parsed image into a device table set / quant set.
 // Returns HJD_IMG_OK or HJD_IMG_ERR_BAD_TABLE.
 int hjd_build_table_set(const HjdParsed& p, HjdTableSet* out);
 void hjd_build_quant_set(const HjdParsed& p, HjdQuantSet* out);
+
+// The bytes a table set / quantisation set is built from, in canonical form (per component, in scan
+// order: BITS + HUFFVAL of its DC and AC table; its quantisation table): equal bytes <=> equal sets.
+struct HjdRawTables {
+    uint8_t huff[4 + 3 * 2 * (16 + 256)];
+    uint8_t quant[4 + 3 * 64];
+};
+void hjd_raw_tables(const HjdParsed& p, HjdRawTables* out);
 
 // 64-bit content key of the tables an image uses (for sharing table sets across a batch).
 uint64_t hjd_table_key(const HjdParsed& p);

@@ -397,7 +397,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                     // the entry says what the symbol means: code length, value bits, zig-zag advance, store or not
                     uint32_t e = hjd_lds_u16(t + ((br.hi >> (32 - HJD_LUT_BITS)) << 1));
                     if ((e & 31u) == 0) {                // code longer than the first-level table
-                        e = hjd_long_code(t, br.hi >> 16, is_ac);
+                        e = hjd_long_code(t, e, br.hi >> 16);
                         if (e == 0) { dead = true; flags |= HJD_ST_BAD_CODE; }
                     }
                     const uint32_t len = e & 31u, size = (e >> 5) & 15u, kadv = (e >> 9) & 127u;
@@ -461,6 +461,15 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     if (flags) atomicOr(&status[img], flags);
 }
 
+// Function attributes are per device: hjd_batch_create calls this after cudaSetDevice, for every batch
+// (a process-wide "done once" flag would leave the second GPU of a process without the larger
+// shared-memory window, and six distinct Huffman tables need more than the default 48 KB).
+cudaError_t hjd_kernels_init_device(void)
+{
+    return cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(HJD_ENT_THREADS * (128 + 8) + HJD_MAX_TABLES * sizeof(HjdHuffTable)));
+}
+
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
                                        const uint32_t* interval_start, const HjdEntropyWork* work,
                                        const HjdEntropySeg* segs, int n_work,
@@ -470,13 +479,6 @@ cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc*
     if (max_tabs < 1) max_tabs = 1;
     if (max_tabs > HJD_MAX_TABLES) max_tabs = HJD_MAX_TABLES;
     const size_t smem = HJD_ENT_THREADS * (128 + 8) + (size_t)max_tabs * sizeof(HjdHuffTable);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(HJD_ENT_THREADS * (128 + 8) + HJD_MAX_TABLES * sizeof(HjdHuffTable)));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     hjd_k_entropy_restart<<<n_work, HJD_ENT_THREADS, smem, st>>>(arena, imgs, tsets, interval_start, work, segs, coef, status);
     return cudaGetLastError();
 }
@@ -894,132 +896,7 @@ cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// kernels 2+3 fused: dequant + IDCT -> shared-memory planes -> upsample + colour -> RGB
-// ------------------------------------------------------------------------------------------
-// One CTA = one strip of consecutive MCUs of one MCU row (loadjpg.cpp:1179-1180 couples DecodeMCU
-// and YCrCB_to_RGB24_Block8x8 per MCU in the same way).  Phase A: one thread per 8x8 block writes
-// its samples into shared-memory Y/Cb/Cr tiles (never to HBM).  Phase B: 16-pixel runs are colour
-// converted from the tiles into a shared RGB tile.  Phase C: the RGB tile is copied out with
-// linear 128-bit stores, each warp store covering 512 contiguous bytes of an image row.
-// HBM traffic per image: coefficients in (once), RGB out (once).
-
-__global__ void __launch_bounds__(HJD_FUSED_THREADS, 4)
-hjd_k_idct_color(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
-                 const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb, int img_base)
-{
-    extern __shared__ __align__(16) uint8_t s_fused[];
-    const HjdImageDesc* d = imgs + (blockIdx.y + img_base);
-    const uint32_t bpm = d->blocks_per_mcu;
-    if (bpm == 0) return;                                      // image skipped by the parser
-    const uint32_t hf = d->hf, vf = d->vf;
-    const uint32_t S = HJD_FUSED_THREADS / bpm;                // MCUs per strip
-    const uint32_t strips_x = (d->mcus_x + S - 1) / S;
-    if (blockIdx.x >= strips_x * d->mcus_y) return;            // uniform per CTA
-    const uint32_t my = blockIdx.x / strips_x, sx = blockIdx.x - my * strips_x;
-    const uint32_t mcu0 = sx * S, nm = min(S, d->mcus_x - mcu0);
-    const uint32_t ny = d->ncomp == 3 ? hf * vf : 1u;
-    const bool gray = d->ncomp == 1;
-
-    const uint32_t yw = S * 8 * hf, yh = 8 * vf, cw = S * 8;   // tile geometry (pitches)
-    float* s_cos = (float*)s_fused;
-    uint8_t* tY = s_fused + 256;
-    uint8_t* tCb = tY + yw * yh;
-    uint8_t* tCr = tCb + (gray ? 0u : cw * 8u);
-    uint8_t* tRGB = tCr + (gray ? 0u : cw * 8u);
-    const uint32_t rgb_pitch = yw * 3;
-
-    const uint32_t t = threadIdx.x;
-    if (t < 64) s_cos[t] = c_cos[t];
-    __syncthreads();
-
-    // ---- phase A: IDCT, one thread per block -------------------------------------------------
-    if (t < nm * bpm) {
-        const uint32_t mcu = t / bpm, bi = t - mcu * bpm;
-        int comp; uint8_t* dst; uint32_t pitch;
-        if (bi < ny) { comp = 0; pitch = yw; dst = tY + (bi / hf) * 8 * yw + (mcu * hf + bi % hf) * 8; }
-        else { comp = (bi == ny) ? 1 : 2; pitch = cw; dst = (comp == 1 ? tCb : tCr) + mcu * 8; }
-        const uint64_t blk = d->block_base + ((uint64_t)my * d->mcus_x + mcu0) * bpm + t;
-        hjd_idct_block((const uint4*)(coef + blk * 64), (const uint4*)(qsets[d->quant_set].qp[comp]), s_cos, dst, pitch);
-    }
-    __syncthreads();
-
-    // ---- phase B: upsample + colour, 16 pixels per unit ------------------------------------------
-    const uint32_t x0 = mcu0 * 8 * hf, y0 = my * 8 * vf;
-    const uint32_t pw = min(nm * 8 * hf, d->width - x0);       // valid pixels of this strip (loadjpg.cpp:907-908)
-    const uint32_t ph = min(yh, d->height - y0);
-    const uint32_t segs = (pw + 15) >> 4;
-    const int hs = (int)hf - 1, vs = (int)vf - 1;
-    for (uint32_t u = t; u < segs * ph; u += HJD_FUSED_THREADS) {
-        const uint32_t row = u / segs, seg = u - row * segs;
-        const uint4 yv = *(const uint4*)(tY + row * yw + seg * 16);
-        const uint32_t yw4[4] = {yv.x, yv.y, yv.z, yv.w};
-        uint32_t cbw[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
-        uint32_t crw[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
-        if (!gray) {
-            const uint32_t coff = (row >> vs) * cw + ((seg * 16) >> hs);
-            const uint2 b0 = *(const uint2*)(tCb + coff), r0 = *(const uint2*)(tCr + coff);
-            cbw[0] = b0.x; cbw[1] = b0.y; crw[0] = r0.x; crw[1] = r0.y;
-            if (hs == 0) {
-                const uint2 b1 = *(const uint2*)(tCb + coff + 8), r1 = *(const uint2*)(tCr + coff + 8);
-                cbw[2] = b1.x; cbw[3] = b1.y; crw[2] = r1.x; crw[3] = r1.y;
-            }
-        }
-        uint32_t out[12];
-        if (hs) hjd_color_16<1>(yw4, cbw, crw, out); else hjd_color_16<0>(yw4, cbw, crw, out);
-        uint4* o = (uint4*)(tRGB + row * rgb_pitch + seg * 48);
-        o[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        o[1] = make_uint4(out[4], out[5], out[6], out[7]);
-        o[2] = make_uint4(out[8], out[9], out[10], out[11]);
-    }
-    __syncthreads();
-
-    // ---- phase C: linear copy-out (loadjpg.cpp:921-925 layout) ------------------------------------
-    const uint32_t row_bytes = pw * 3;
-    const uint64_t img_pitch = (uint64_t)d->width * 3;
-    uint8_t* g0 = rgb + d->rgb_off + (uint64_t)y0 * img_pitch + (uint64_t)x0 * 3;
-    if (((row_bytes | (uint32_t)img_pitch | (x0 * 3)) & 15u) == 0 && (d->rgb_off & 15u) == 0) {
-        const uint32_t chunks = row_bytes >> 4;
-        for (uint32_t i = t; i < chunks * ph; i += HJD_FUSED_THREADS) {
-            const uint32_t row = i / chunks, c = i - row * chunks;
-            *(uint4*)(g0 + row * img_pitch + c * 16) = *(const uint4*)(tRGB + row * rgb_pitch + c * 16);
-        }
-    } else {
-        for (uint32_t i = t; i < row_bytes * ph; i += HJD_FUSED_THREADS) {
-            const uint32_t row = i / row_bytes, c = i - row * row_bytes;
-            g0[row * img_pitch + c] = tRGB[row * rgb_pitch + c];
-        }
-    }
-}
-
-size_t hjd_fused_smem_bytes(int ncomp, int hf, int vf)
-{
-    // cos table + Y tile + Cb/Cr tiles + RGB tile for a strip of S = floor(threads / blocks_per_mcu) MCUs
-    const size_t bpm = ncomp == 3 ? (size_t)hf * vf + 2 : 1;
-    const size_t S = HJD_FUSED_THREADS / bpm;
-    const size_t ypix = S * 64 * (ncomp == 3 ? (size_t)hf * vf : 1);
-    return 256 + ypix + (ncomp == 3 ? 2 * S * 64 : 0) + 3 * ypix;
-}
-
-cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
-                                  uint8_t* rgb, int n_images, uint32_t max_strips, size_t smem, cudaStream_t st)
-{
-    if (n_images <= 0 || max_strips == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(hjd_k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)hjd_fused_smem_bytes(1, 1, 1));   // grayscale is the largest tile
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    for (int base = 0; base < n_images; base += 65535) {
-        const int n = min(65535, n_images - base);
-        hjd_k_idct_color<<<dim3(max_strips, n), HJD_FUSED_THREADS, smem, st>>>(coef, imgs, qsets, rgb, base);
-    }
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
-// kernels 2+3 fused per MCU (HJD_FLAG_FUSED_MCU): one thread decodes a whole MCU to RGB
+// kernels 2+3 fused per MCU (the default path): one thread decodes a whole MCU to RGB
 // ------------------------------------------------------------------------------------------
 // The reference couples DecodeMCU and YCrCB_to_RGB24_Block8x8 per MCU (loadjpg.cpp:1179-1180); so
 // does this kernel, with no barrier at all: a thread runs the IDCT of its MCU's Cb and Cr blocks into

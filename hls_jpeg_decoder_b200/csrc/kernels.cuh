@@ -13,7 +13,9 @@
 #define HJD_IDCT_THREADS  128   // unfused IDCT kernel: one 8x8 block per thread
 #define HJD_COLOR_THREADS 128   // unfused colour kernel: 16 pixels of one row per thread
 #define HJD_MCU_THREADS   128   // per-MCU fused kernel: one MCU (all its blocks -> RGB) per thread
-#define HJD_FUSED_THREADS 128   // fused IDCT+colour kernel: one strip of floor(128 / blocks_per_mcu) MCUs per CTA
+
+// Per-device function attributes (shared-memory windows); call after cudaSetDevice, once per batch handle.
+cudaError_t hjd_kernels_init_device(void);
 
 // Upload the IDCT constants (host libm values, loadjpg.cpp:96-102,120).
 cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00);
@@ -37,13 +39,6 @@ cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs
 // Kernel 3: chroma upsample + YCbCr->RGB + clamp -> packed RGB24.
 cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, uint8_t* rgb, int n_images,
                              uint32_t max_width, uint32_t max_height, cudaStream_t st);
-
-// Kernels 2+3 fused (default path): coefficients -> RGB without the plane round trip.
-// max_strips = max over images of ceil(mcus_x / floor(HJD_FUSED_THREADS / blocks_per_mcu)) * mcus_y.
-// smem = max over the batch of hjd_fused_smem_bytes(ncomp, hf, vf).
-size_t hjd_fused_smem_bytes(int ncomp, int hf, int vf);
-cudaError_t hjd_launch_idct_color(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
-                                  uint8_t* rgb, int n_images, uint32_t max_strips, size_t smem, cudaStream_t st);
 
 // Kernels 2+3 fused per MCU: one thread = one MCU, coefficients -> RGB, no plane traffic, no barriers.
 // mcu_prefix[i] = MCUs of images 0..i-1 (any common offset; n_images + 1 entries);

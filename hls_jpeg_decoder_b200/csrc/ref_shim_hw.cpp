@@ -14,10 +14,33 @@
 // Restart intervals cannot be expressed through this struct: the reference stores Lr, not Ri, in
 // m_restart_interval (openjpg.cpp:441-446), so like the reference itself this entry point is for
 // restart-free files; use the file/memory entry points for everything else.
+//
+// JpegGetImageSize(stJpegData*, unsigned*, unsigned*) (loadjpg.h:183) is declared by the reference and never
+// defined; its stJpegData carries no dimensions (they live in stImageInfo, openjpg.h:11-17), so the only
+// meaning the signature can have is implemented here: the width and height this jdata was last decoded
+// with by JpegDecodeHW (0 x 0 if it never was).
 #include "loadjpg.h"
 #include "../../include/hjd.h"
 #include <string.h>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
 #include <vector>
+
+static std::mutex g_size_mutex;
+static std::unordered_map<const stJpegData*, std::pair<unsigned, unsigned> > g_size_of;
+
+void JpegGetImageSize(stJpegData* jdata, unsigned int* width, unsigned int* height)
+{
+    unsigned w = 0, h = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_size_mutex);
+        auto it = g_size_of.find(jdata);
+        if (it != g_size_of.end()) { w = it->second.first; h = it->second.second; }
+    }
+    if (width) *width = w;
+    if (height) *height = h;
+}
 
 static void put16(std::vector<unsigned char>& o, unsigned v) { o.push_back((unsigned char)(v >> 8)); o.push_back((unsigned char)v); }
 
@@ -43,6 +66,11 @@ int JpegDecodeHW(stJpegData* jdata, unsigned int jpeg_img_height, unsigned int j
                  unsigned char hFactor, unsigned char vFactor)
 {
     if (!jdata || !jpeg_img_width || !jpeg_img_height) return 0;
+    {
+        std::lock_guard<std::mutex> lock(g_size_mutex);
+        if (g_size_of.size() > 4096) g_size_of.clear();            // callers that churn through jdata objects
+        g_size_of[jdata] = std::make_pair(jpeg_img_width, jpeg_img_height);
+    }
     std::vector<unsigned char> o;
     o.reserve(2048 + STREAM_SIZE);
     o.push_back(0xFF); o.push_back(0xD8);

@@ -13,9 +13,10 @@
 //   2. sync rounds: a sub-sequence is decoded again from its left neighbour's exit state whenever that
 //      state differs from the one it was last decoded from.  A warp owns a range of sub-sequences,
 //      collects the ones to redo in shared memory and decodes them 32 at a time until the range is
-//      stable; between ranges the states travel through HBM and the host repeats the round until one
-//      passes with nothing to redo.  Sub-sequence 0 starts from the true state, so by induction the
-//      fixed point is exactly the sequential decode;
+//      stable; between ranges the states travel through L2 and ONE persistent kernel repeats the round
+//      (grid-wide barrier in between) until one passes with nothing to redo -- the host is not in the
+//      loop.  Sub-sequence 0 starts from the true state, so by induction the fixed point is exactly
+//      the sequential decode;
 //   3. an exclusive prefix sum of, per sub-sequence, the number of blocks that start in it and the sums
 //      of their DC differences gives every thread its first output block and its DC predictors
 //      (DCT[0] = data + prevDC in int16, loadjpg.cpp:664-665);
@@ -354,7 +355,7 @@ __device__ __forceinline__ SsSym ss_symbol(uint32_t t, uint32_t hi, uint32_t lo,
     uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
     s.bad = false;
     if ((e & 31u) == 0) {
-        e = hjd_long_code(t, hi >> 16, is_ac);
+        e = hjd_long_code(t, e, hi >> 16);
         if (e == 0) { e = hjd_sym_fields(1, 0, is_ac); s.bad = true; }
     }
     const uint32_t len = e & 31u;
@@ -512,21 +513,32 @@ cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tset
 // ------------------------------------------------------------------------------------------
 // step 2: synchronisation rounds
 // ------------------------------------------------------------------------------------------
-// One WARP owns `range` consecutive sub-sequences of one image (a CTA = HJD_SS_FIX_WARPS such warps
-// sharing the image's tables).  A sub-sequence whose left neighbour's exit state differs from the
+// One WARP owns `range` consecutive sub-sequences of one image (a work item = HJD_SS_FIX_WARPS such
+// ranges sharing a table set).  A sub-sequence whose left neighbour's exit state differs from the
 // entry state it was decoded from goes on the warp's list in shared memory; the list is decoded 32
 // entries at a time, so the few sub-sequences still wrong cost a few dense warp passes instead of one
 // mostly idle pass per 32 sub-sequences; repeat until the range is consistent.  The states before the
-// range come from HBM, where the previous warp may still be correcting them: whichever values the
-// reads return, the host repeats the round until one passes in which no warp had anything to decode.
+// range come from L2, where the previous warp may still be correcting them: whichever values the
+// reads return, the rounds go on until one passes in which no warp had anything to decode.
 // Sub-sequence 0 starts from the true state, so the fixed point is the sequential decode.
+//
+// The rounds run inside ONE persistent kernel (cooperative launch: every CTA is resident), the CTAs
+// striding over the work items, with a grid-wide barrier between rounds; the round in which some warp
+// last had anything to decode is kept in ctl[1], and everybody leaves after the first round that did
+// not raise it.  (The first version launched one kernel per round and had the host read a flag after
+// each: a stream synchronisation per round, in the middle of the hot path.)
+// ctl[0] barrier arrivals, ctl[1] last round (1-based) with work, ctl[2] rounds executed (bit 31: the
+// round limit was hit, which the induction argument above rules out), all zero at launch.
+__device__ __forceinline__ uint64_t ss_ld64(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+__device__ __forceinline__ void ss_st64(uint64_t* p, uint64_t v) { __stcg((unsigned long long*)p, (unsigned long long)v); }
+
 __global__ void __launch_bounds__(HJD_SS_FIX_WARPS * 32)
-hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
-             const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
-             const HjdSsSeg* __restrict__ segs,
-             const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
-             uint64_t* __restrict__ e_arr, uint64_t* __restrict__ x_arr, uint32_t* __restrict__ cnt_arr,
-             int* __restrict__ changed)
+hjd_k_ss_sync(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
+              const HjdSsImage* __restrict__ ss, const HjdSsWork* __restrict__ work,
+              const HjdSsSeg* __restrict__ segs, int n_work,
+              const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
+              uint64_t* e_arr, uint64_t* x_arr, uint32_t* __restrict__ cnt_arr,
+              uint32_t* ctl, uint32_t max_rounds)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
     constexpr uint32_t kEntries = HJD_SS_FIX_MAXR + HJD_SS_FIX_OVERLAP;
@@ -536,95 +548,127 @@ hjd_k_ss_fix(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restric
     uint64_t* sE = (uint64_t*)(s_raw + warp * kWarpBytes);           // exit state per sub-sequence of the window
     uint64_t* sX = sE + kEntries;                                    // entry state it was computed from
     uint16_t* sL = (uint16_t*)(sX + kEntries);                       // sub-sequences to decode again
-    const HjdSsWork wk = work[blockIdx.x];
-    const bool has_range = (uint32_t)warp < wk.n_segs;               // this warp's range (possibly of another image than its neighbours')
-    const HjdSsSeg sg = segs[wk.first_seg + (has_range ? warp : 0)];
-    const HjdSsImage s = ss[sg.ss];
-    const HjdImageDesc* d = imgs + s.img;
-
-    const uint32_t L = dlen[sg.ss];
-    const uint32_t first = sg.first_sub;                             // local index of the range's first sub-sequence
-    uint32_t n_have = (L + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES; // sub-sequences that hold data
-    if (n_have > s.n_subs) n_have = s.n_subs;
-    const int n_own = has_range && first < n_have ? (int)min(sg.n, n_have - first) : 0;
-    // The window starts HJD_SS_FIX_OVERLAP sub-sequences before the range: they are re-checked (and, if
-    // need be, re-decoded) privately, never written back -- they belong to the previous warp, which
-    // may be correcting them at this very moment.  So the entry state of the range no longer hinges on
-    // one exit state of the speculative pass, and the round after this one is normally a pure check.
-    const uint32_t lo = first >= HJD_SS_FIX_OVERLAP ? first - HJD_SS_FIX_OVERLAP : 0u;
-    const int kov = n_own ? (int)(first - lo) : 0;
-    const int n_act = n_own ? kov + n_own : 0;
-    const uint32_t g0 = s.sub_base + lo;
-    for (int j = lane; j < n_act; j += 32) { sE[j] = e_arr[g0 + j]; sX[j] = x_arr[g0 + j]; }
-    uint64_t boundary = ss_pack(0, 0, 0);
-    if (n_act && lo != 0) boundary = e_arr[g0 - 1];
-    __syncwarp();
-    bool any = false;
-    for (int j = lane; j < n_act; j += 32) any |= (j == 0 ? boundary : sE[j - 1]) != sX[j];
-    // A warp that has anything to decode again raises `changed`.  The host stops after a round in which
-    // no warp did: every warp then found its window -- read from HBM while nobody was writing --
-    // consistent, including the entry of its range against the previous range's last exit state.
-    if (__any_sync(0xffffffffu, any) && lane == 0) *changed = 1;
-    if (!__syncthreads_or(any)) return;                              // the usual case in the later rounds
-    ss_load_tables(tsets + wk.table_set, s_tab);
-    __syncthreads();
-
-    SsCtx cx;
-    cx.D = dst + s.dst_off;
-    cx.sh_tab = (uint32_t)__cvta_generic_to_shared(s_tab);
-    cx.bpm = d->blocks_per_mcu;
-    cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
     const uint64_t sub_bits = (uint64_t)HJD_SS_SUB_BYTES * 8;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int iter = 0; iter < n_act + 2; iter++) {
-        int n = 0;
-        for (int j0 = 0; j0 < n_act; j0 += 32) {
-            const int j = j0 + lane;
-            const bool need = j < n_act && (j == 0 ? boundary : sE[j - 1]) != sX[j];
-            const uint32_t bal = __ballot_sync(0xffffffffu, need);
-            if (need) sL[n + __popc(bal & lt_mask)] = (uint16_t)j;
-            n += __popc(bal);
-        }
-        __syncwarp();
-        if (n == 0) break;
-        for (int q0 = 0; q0 < n; q0 += 32) {
-            int t = -1;
-            uint64_t txin = 0;
-            if (q0 + lane < n) {
-                t = sL[q0 + lane];
-                txin = t == 0 ? boundary : sE[t - 1];
-            }
-            __syncwarp();                                            // entry states read before any is rewritten
-            if (t >= 0) {
-                SsCount cnt;
-                const uint64_t te = ss_scan_decode<true>(cx, txin, (uint64_t)(lo + t + 1) * sub_bits, &cnt);
-                if (t >= kov) {
-                    const uint32_t g = g0 + (uint32_t)t;
-                    cnt_arr[g] = cnt.ns;
-                    cnt_arr[n_subs_total + g] = cnt.dc0;
-                    cnt_arr[2 * n_subs_total + g] = cnt.dc1;
-                    cnt_arr[3 * n_subs_total + g] = cnt.dc2;
-                }
-                sE[t] = te;
-                sX[t] = txin;
-            }
+    uint32_t loaded_set = 0xFFFFFFFFu;                               // table set in s_tab (CTA-uniform)
+
+    for (uint32_t round = 1;; round++) {
+        for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+            const HjdSsWork wk = work[wi];
+            const bool has_range = (uint32_t)warp < wk.n_segs;       // this warp's range (possibly of another image than its neighbours')
+            const HjdSsSeg sg = segs[wk.first_seg + (has_range ? warp : 0)];
+            const HjdSsImage s = ss[sg.ss];
+            const HjdImageDesc* d = imgs + s.img;
+
+            const uint32_t L = dlen[sg.ss];
+            const uint32_t first = sg.first_sub;                     // local index of the range's first sub-sequence
+            uint32_t n_have = (L + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES;   // sub-sequences that hold data
+            if (n_have > s.n_subs) n_have = s.n_subs;
+            const int n_own = has_range && first < n_have ? (int)min(sg.n, n_have - first) : 0;
+            // The window starts HJD_SS_FIX_OVERLAP sub-sequences before the range: they are re-checked (and, if
+            // need be, re-decoded) privately, never written back -- they belong to the previous warp, which
+            // may be correcting them at this very moment.  So the entry state of the range does not hinge on
+            // one exit state of the speculative pass, and the round after this one is normally a pure check.
+            const uint32_t lo = first >= HJD_SS_FIX_OVERLAP ? first - HJD_SS_FIX_OVERLAP : 0u;
+            const int kov = n_own ? (int)(first - lo) : 0;
+            const int n_act = n_own ? kov + n_own : 0;
+            const uint32_t g0 = s.sub_base + lo;
+            for (int j = lane; j < n_act; j += 32) { sE[j] = ss_ld64(e_arr + g0 + j); sX[j] = ss_ld64(x_arr + g0 + j); }
+            uint64_t boundary = ss_pack(0, 0, 0);
+            if (n_act && lo != 0) boundary = ss_ld64(e_arr + g0 - 1);
             __syncwarp();
+            bool any = false;
+            for (int j = lane; j < n_act; j += 32) any |= (j == 0 ? boundary : sE[j - 1]) != sX[j];
+            // A warp that has anything to decode again marks the round.  The rounds stop after one in which
+            // no warp did: every warp then found its window -- read while nobody was writing --
+            // consistent, including the entry of its range against the previous range's last exit state.
+            if (__any_sync(0xffffffffu, any) && lane == 0) atomicMax(&ctl[1], round);
+            if (!__syncthreads_or(any)) continue;                    // the usual case in the later rounds (CTA-uniform)
+            if (loaded_set != wk.table_set) {
+                ss_load_tables(tsets + wk.table_set, s_tab);
+                loaded_set = wk.table_set;
+            }
+            __syncthreads();
+
+            SsCtx cx;
+            cx.D = dst + s.dst_off;
+            cx.sh_tab = (uint32_t)__cvta_generic_to_shared(s_tab);
+            cx.bpm = d->blocks_per_mcu;
+            cx.ny = d->ncomp == 3 ? (uint32_t)d->hf * d->vf : 1u;
+            for (int iter = 0; iter < n_act + 2; iter++) {
+                int n = 0;
+                for (int j0 = 0; j0 < n_act; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool need = j < n_act && (j == 0 ? boundary : sE[j - 1]) != sX[j];
+                    const uint32_t bal = __ballot_sync(0xffffffffu, need);
+                    if (need) sL[n + __popc(bal & lt_mask)] = (uint16_t)j;
+                    n += __popc(bal);
+                }
+                __syncwarp();
+                if (n == 0) break;
+                for (int q0 = 0; q0 < n; q0 += 32) {
+                    int t = -1;
+                    uint64_t txin = 0;
+                    if (q0 + lane < n) {
+                        t = sL[q0 + lane];
+                        txin = t == 0 ? boundary : sE[t - 1];
+                    }
+                    __syncwarp();                                    // entry states read before any is rewritten
+                    if (t >= 0) {
+                        SsCount cnt;
+                        const uint64_t te = ss_scan_decode<true>(cx, txin, (uint64_t)(lo + t + 1) * sub_bits, &cnt);
+                        if (t >= kov) {
+                            const uint32_t g = g0 + (uint32_t)t;
+                            cnt_arr[g] = cnt.ns;
+                            cnt_arr[n_subs_total + g] = cnt.dc0;
+                            cnt_arr[2 * n_subs_total + g] = cnt.dc1;
+                            cnt_arr[3 * n_subs_total + g] = cnt.dc2;
+                        }
+                        sE[t] = te;
+                        sX[t] = txin;
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int j = kov + lane; j < n_act; j += 32) { ss_st64(e_arr + g0 + j, sE[j]); ss_st64(x_arr + g0 + j, sX[j]); }
+            __syncthreads();                                         // s_tab / windows are reused by the next item
+        }
+        // ---- grid-wide barrier, then: did anybody have work in this round? ---------------------
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&ctl[0], 1u);
+            const uint32_t want = round * gridDim.x;
+            while (*(volatile uint32_t*)&ctl[0] < want) __nanosleep(64);
+            __threadfence();
+        }
+        __syncthreads();
+        const uint32_t last = *(volatile uint32_t*)&ctl[1];
+        if (last < round || round >= max_rounds) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl[2] = round | (last < round ? 0u : 0x80000000u);
+            break;
         }
     }
-    for (int j = kov + lane; j < n_act; j += 32) { e_arr[g0 + j] = sE[j]; x_arr[g0 + j] = sX[j]; }
 }
 
-cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                              const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
-                              const uint32_t* dlen,
-                              uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
-                              int* changed, cudaStream_t st)
+static size_t ss_sync_smem(void)
+{
+    return (size_t)HJD_SS_FIX_WARPS * (((HJD_SS_FIX_MAXR + HJD_SS_FIX_OVERLAP) * 18 + 15) & ~15u) + 6 * sizeof(HjdHuffTable);
+}
+
+cudaError_t hjd_launch_ss_sync(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                               const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                               const uint32_t* dlen,
+                               uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
+                               uint32_t* ctl, uint32_t max_rounds, int max_resident_ctas, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
-    const size_t smem = (size_t)HJD_SS_FIX_WARPS * (((HJD_SS_FIX_MAXR + HJD_SS_FIX_OVERLAP) * 18 + 15) & ~15u) + 6 * sizeof(HjdHuffTable);
-    hjd_k_ss_fix<<<n_work, HJD_SS_FIX_WARPS * 32, smem, st>>>(imgs, tsets, ss, work, segs, dst, dlen, n_subs_total,
-                                                             e, x, cnt, changed);
-    return cudaGetLastError();
+    int grid = n_work < max_resident_ctas ? n_work : max_resident_ctas;
+    if (grid < 1) grid = 1;
+    void* args[] = {(void*)&imgs, (void*)&tsets, (void*)&ss, (void*)&work, (void*)&segs, (void*)&n_work, (void*)&dst,
+                    (void*)&dlen, (void*)&n_subs_total, (void*)&e, (void*)&x, (void*)&cnt, (void*)&ctl, (void*)&max_rounds};
+    return cudaLaunchCooperativeKernel((const void*)hjd_k_ss_sync, dim3((unsigned)grid), dim3(HJD_SS_FIX_WARPS * 32), args,
+                                       ss_sync_smem(), st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -638,6 +682,12 @@ cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets
 // last round: first owned block and, per component, the DC predictor at it
 // (DCT[0] = data + prevDC in int16, loadjpg.cpp:664-665).
 #define SS_WRITE_SYMS 4
+// Bounds of an owned block (a crafted table whose AC symbols never advance the zig-zag index would
+// otherwise keep its owner decoding forever, past the stream, the slack and the buffer): at most
+// SS_WRITE_MAX_STEPS rounds of SS_WRITE_SYMS symbols per block -- 16 times what a block of 64
+// coefficients can need -- and no bit position beyond the zeroed slack.  A thread that hits either
+// flags the image and zero-fills the blocks it still owed.
+#define SS_WRITE_MAX_STEPS 256
 
 __global__ void __launch_bounds__(HJD_SS_THREADS)
 hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restrict__ tsets,
@@ -690,9 +740,17 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     SsBits br;
     br.hi = br.lo = br.wa = br.wb = br.wc = 0; br.nbits = 64; br.wp = (const uint32_t*)D;
     int flags = 0;
+    int steps = 0;                    // rounds spent on the current owned block
+    int rem_min = 0;                  // rem below this: the bit position has left the zeroed slack
+    uint32_t own_end = 0;             // image-local index one past the last block this thread owns
     if (li < s.n_subs && (uint64_t)li * HJD_SS_SUB_BYTES < L) {
         const uint32_t gi = s.sub_base + li;
         const uint64_t xs = x_arr[gi];
+        {
+            const long long lim = ((long long)L + HJD_SS_SLACK - 64) * 8 - (long long)end_bit;   // bits past my sub-sequence that exist
+            rem_min = lim > (1ll << 30) ? -(1 << 30) : -(int)(lim < 0 ? 0 : lim);
+            own_end = min(prefix[gi + 1] - prefix[s.sub_base], n_blocks);
+        }
         if (xs == SS_INVALID) flags |= HJD_ST_BAD_CODE;
         else {
             const uint64_t p = xs & 0xFFFFFFFFFFull;
@@ -753,9 +811,18 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                 }
             }
         }
+        // ---- bounds (see SS_WRITE_MAX_STEPS) ---------------------------------------------------
+        if (!finished && !done_block && owned && (++steps > SS_WRITE_MAX_STEPS || rem < rem_min)) {
+            flags |= steps > SS_WRITE_MAX_STEPS ? HJD_ST_BAD_CODE : HJD_ST_OVERRUN;
+            for (uint32_t bz = blk; bz < own_end; bz++)
+                for (int q = 0; q < 8; q++) ((uint4*)coef)[(size_t)(blk_base + bz) * 8u + q] = make_uint4(0, 0, 0, 0);
+            blk = own_end;
+            finished = true;
+        }
         // ---- block hand-over ---------------------------------------------------------------
         uint32_t flush_blk = 0;
         if (done_block) {
+            steps = 0;
             p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
             hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
             flush_blk = blk_base + blk;
@@ -793,6 +860,23 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     if (flags) atomicOr(&status[s.img], flags);
 }
 
+// Per-device function attributes and limits (see hjd_kernels_init_device): the write pass needs more than
+// the default 48 KB of shared memory; *max_sync_ctas = CTAs of the synchronisation kernel that can be
+// resident together (its cooperative launch must not ask for more).
+cudaError_t hjd_selfsync_init_device(int* max_sync_ctas)
+{
+    cudaError_t e = cudaFuncSetAttribute(hjd_k_ss_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable)));
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hjd_k_ss_sync, HJD_SS_FIX_WARPS * 32, ss_sync_smem())) != cudaSuccess) return e;
+    if (per_sm > 4) per_sm = 4;        // the rounds are latency-bound chains: more resident CTAs only make the barrier slower
+    *max_sync_ctas = sms * (per_sm < 1 ? 1 : per_sm);
+    return cudaSuccess;
+}
+
 cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
                                 const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
                                 const uint32_t* dlen,
@@ -801,12 +885,6 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
 {
     if (n_work <= 0) return cudaSuccess;
     const size_t smem = HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(hjd_k_ss_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, segs, dst, dlen, n_subs_total, x, prefix,
                                                         coef, status);
     return cudaGetLastError();

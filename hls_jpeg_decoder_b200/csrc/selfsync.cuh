@@ -21,14 +21,20 @@ cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tset
                                const uint32_t* dlen,
                                uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt, cudaStream_t st);
 
-// One synchronisation round, in place.  `work` here has at most HJD_SS_FIX_WARPS segments per entry, one
-// range (<= HJD_SS_FIX_MAXR sub-sequences) per warp.  changed is set to 1 when any warp had a
-// sub-sequence to decode again; the states are final after a round that leaves it 0.
-cudaError_t hjd_launch_ss_fix(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
-                              const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
-                              const uint32_t* dlen,
-                              uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
-                              int* changed, cudaStream_t st);
+// The synchronisation rounds, in place, all of them in one persistent cooperative kernel (grid-wide barrier
+// between rounds, termination decided on the device).  `work` here has at most HJD_SS_FIX_WARPS segments per
+// entry, one range (<= HJD_SS_FIX_MAXR sub-sequences) per warp.  ctl: three zeroed words (barrier count,
+// last round with work, rounds executed | bit 31 if max_rounds was hit).  max_resident_ctas: from
+// hjd_selfsync_init_device.
+cudaError_t hjd_launch_ss_sync(const HjdImageDesc* imgs, const HjdTableSet* tsets, const HjdSsImage* ss,
+                               const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
+                               const uint32_t* dlen,
+                               uint32_t n_subs_total, uint64_t* e, uint64_t* x, uint32_t* cnt,
+                               uint32_t* ctl, uint32_t max_rounds, int max_resident_ctas, cudaStream_t st);
+
+// Per-device function attributes (call after cudaSetDevice, once per batch handle); *max_sync_ctas = grid
+// limit of the cooperative synchronisation kernel on this device.
+cudaError_t hjd_selfsync_init_device(int* max_sync_ctas);
 
 // Final pass: every thread decodes, from its (now correct) entry state, the blocks that start in its
 // sub-sequence and writes them as whole 128-byte lines, DC un-differenced.  prefix = exclusive scan of cnt.

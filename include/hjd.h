@@ -61,7 +61,6 @@ extern "C" {
 /* hjd_batch_create flags */
 #define HJD_FLAG_KEEP_PLANES   1u   /* unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap, hjd_batch_download_planes) */
 #define HJD_FLAG_HOST_SCAN     2u   /* find RSTn markers on the host instead of the GPU pre-pass */
-#define HJD_FLAG_FUSED         4u   /* kernels 2+3 fused per MCU strip with CTA-wide phases (slower than the default; kept for comparison) */
 #define HJD_FLAG_FUSED_MCU    16u   /* (default behaviour) kernels 2+3 fused per MCU: one thread decodes a whole MCU to RGB */
 #define HJD_FLAG_NO_SELFSYNC   8u   /* restart-free scans: one thread per scan (kernel 1a) instead of kernel 1b */
 
@@ -107,6 +106,13 @@ int  hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsig
 void hjd_free(void* p);
 /* loadjpg.h:183 JpegGetImageSize, from the file bytes (header parse only, no GPU). */
 int  hjd_get_image_size(const uint8_t* buf, int size, unsigned* width, unsigned* height);
+/* Header parse only (no GPU): the per-image status a batch would report for this file (HJD_IMG_OK or a
+ * negative HJD_IMG_ERR_*) and, when it is decodable, its geometry (offsets in *out stay 0).
+ * Not decodable, by design: progressive / lossless / arithmetic (SOF2..SOF15), 12-bit samples (SOF1 with
+ * P != 8), 16-bit DQT, 4 components, chroma sampling other than 1x1, luma factors other than 1 or 2, and
+ * NON-INTERLEAVED baseline files (one scan per component): the reference's decode loop is one interleaved
+ * scan of all three components (loadjpg.cpp:945-997), so such files get HJD_IMG_ERR_UNSUPPORTED. */
+int  hjd_probe_jpeg(const uint8_t* buf, int64_t size, hjd_image_info* out);
 /* openjpg.cpp:504 WriteBMP24. */
 int  hjd_write_bmp24(const char* path, unsigned width, unsigned height, const uint8_t* rgb);
 /* Same bytes as hjd_write_bmp24 into memory; returns the BMP size (call with out = NULL to size it). */
@@ -144,7 +150,7 @@ int  hjd_batch_sync(hjd_batch* b);
 int  hjd_batch_set_overlap(hjd_batch* b, int on);
 
 /* Synchronisation rounds the self-synchronising kernel (restart-free scans) needed in the last decode. */
-int  hjd_batch_selfsync_rounds(const hjd_batch* b);
+int  hjd_batch_selfsync_rounds(hjd_batch* b);                        /* syncs */
 /* Sub-sequences per warp in those rounds: 0 = pick by batch size (default), else a multiple of 32 up
  * to 256 (testing / tuning; results do not depend on it).  Takes effect at the next upload. */
 int  hjd_batch_set_selfsync_range(hjd_batch* b, int range);
@@ -187,6 +193,11 @@ uint64_t hjd_rgb_slab_bytes(const uint8_t* arena, const int64_t* offsets, const 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA binding. */
 void* hjd_host_alloc(size_t bytes);
 void  hjd_host_free(void* p);
+
+/* Testing aid: build the kernels' two-level lookup table from BITS / HUFFVAL (as in a DHT segment) and look
+ * up the next 16 bits of a stream: returns len | size << 5 | zig-zag advance << 9 (0: no such code;
+ * 0xFFFFFFFF: the table is over-subscribed).  tests/ compare it with the canonical code walk. */
+uint32_t hjd_huff_lookup_probe(const uint8_t bits[16], const uint8_t* vals, int nvals, int is_ac, uint32_t peek16);
 
 /* The float constants the kernels use (computed on the host with the libm expressions of
  * loadjpg.cpp:96-102,120): cos_tab[p*8+k] = cosf(((2p+1)*k*3.14f)/16), cc[u*8+v] = C(u)*C(v). */

@@ -239,13 +239,21 @@ static unsigned take_bits(bits_t* b, unsigned n)
     return v;
 }
 
+/* The reference searches DC codes of 1..15 bits only (loadjpg.cpp:562: "for k = 1; k < 16"), so a legal
+   16-bit DC code is undecodable for it (it prints an error and leaves the bitstream where it was).  The
+   product decodes such files correctly -- a DELIBERATE DEVIATION on input the reference cannot handle.
+   hjdo_set_dc16(1) lets this oracle search k = 1..16 so that those files have a checker at all; the
+   default (0) is the reference's behaviour and is what every parity test against the reference uses. */
+static int g_dc_last_len = 15;
+void hjdo_set_dc16(int on) { g_dc_last_len = on ? 16 : 15; }
+
 static int process_huffman_block(int16_t dct[64], int16_t* prev_dc, const huff_t* htdc,
                                  const huff_t* htac, bits_t* b)
 {
     /* loadjpg.cpp:497-863 with restart sniffing removed (m_restart_interval == 0). */
     int k, found = 0, value = 0, nr = 1, eob = 0, err = 0;
     memset(dct, 0, 128);                                                         /* 523-527 */
-    for (k = 1; k < 16; k++) {                                                   /* 562: DC, k = 1..15 */
+    for (k = 1; k <= g_dc_last_len; k++) {                                       /* 562: DC, k = 1..15 (16 only with hjdo_set_dc16) */
         int code;
         fill_nbits(b, k);
         code = (int)(b->reservoir >> (b->nbits - k));                            /* 584 */

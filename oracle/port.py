@@ -45,8 +45,15 @@ def lib() -> ctypes.CDLL:
         L.hjdo_bmp24_size.argtypes = [ctypes.c_uint, ctypes.c_uint]
         L.hjdo_bmp24_encode.restype = None
         L.hjdo_bmp24_encode.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p]
+        L.hjdo_set_dc16.restype = None
+        L.hjdo_set_dc16.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
+
+
+def set_dc16(on: bool) -> None:
+    """Deviation switch (default off = the reference, loadjpg.cpp:562): search DC codes of up to 16 bits."""
+    lib().hjdo_set_dc16(1 if on else 0)
 
 
 def info(jpg: bytes):

@@ -30,12 +30,11 @@ def golden_files():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.jpg")))
 
 
-@pytest.fixture(scope="module", params=["fused", "planes", "fused_mcu"])
+@pytest.fixture(scope="module", params=["planes", "fused_mcu"])
 def dec(hjd, request):
     """fused_mcu: the default product path (kernels 2+3 fused per MCU, planes in shared memory only);
-    planes: HJD_FLAG_KEEP_PLANES, unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap);
-    fused: HJD_FLAG_FUSED, the strip-fused variant."""
-    d = hjd.BatchDecoder(0, {"fused": hjd.FLAG_FUSED, "fused_mcu": 0, "planes": hjd.FLAG_KEEP_PLANES}[request.param])
+    planes: HJD_FLAG_KEEP_PLANES, unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap)."""
+    d = hjd.BatchDecoder(0, {"fused_mcu": 0, "planes": hjd.FLAG_KEEP_PLANES}[request.param])
     d.keeps_planes = request.param == "planes"
     yield d
     d.close()

@@ -1,0 +1,163 @@
+"""GPU tests added in round 2 (pytest -m gpu, through the C ABI): inputs beyond the reference
+(SURVEY.md 8(f) rank 4), the advisor's crafted-table case, per-device kernel attributes, the honoured
+chunk_images argument."""
+import numpy as np
+import pytest
+
+from tests import cases
+from tests import jpeg_writer as jw
+
+pytestmark = pytest.mark.gpu
+
+
+def six_table_image(port, name="420_100x70_ri2", restart_interval=2):
+    """A colour image whose three components select three DC and three AC tables (ids 0, 1, 2): six tables
+    in shared memory, which is more than the default 48 KB window of the entropy kernels."""
+    src = cases.small_cases()[name]
+    o = port.decode(src, entropy_only=True)
+    segs, _ = jw.segments(src)
+    t = jw.dht_tables(segs)
+    tables = {(0, 2): t[(0, 1)], (1, 2): t[(1, 1)]}
+    sos = bytes([3, 1, 0x00, 2, 0x11, 3, 0x22, 0, 63, 0])
+    return jw.rewrite(src, o["coef"], o["geometry"], tables=tables, restart_interval=restart_interval, sos_override=sos), src
+
+
+def test_sixteen_bit_dc_code(hjd, port):
+    """A legal 16-bit DC code (hand-built DHT): the reference searches k = 1..15 only (loadjpg.cpp:562) and
+    cannot decode the file -- a deliberate deviation; the oracle's k <= 16 switch is the checker.
+    Restart-marker path, restart-free path (kernel 1b) and the single-thread path."""
+    src = cases.small_cases()["420_100x70_ri2"]
+    o = port.decode(src)
+    big = cases.small_cases()["444_gradient_q95"]
+    ob = port.decode(big)
+    t16 = {(0, 0): (jw.DC16_BITS, jw.DC16_VALS)}
+    files = [jw.rewrite(src, o["coef"], o["geometry"], tables=t16, restart_interval=2),
+             jw.rewrite(src, o["coef"], o["geometry"], tables=t16, restart_interval=0),
+             jw.rewrite(big, ob["coef"], ob["geometry"], tables=t16, restart_interval=0)]
+    want = [o, o, ob]
+    assert hjd.probe(files[2])[1].scan_bytes >= 1024            # long enough for kernel 1b
+    for flags in (0, hjd.FLAG_NO_SELFSYNC):
+        with hjd.BatchDecoder(0, flags) as d:
+            d.upload(files)
+            d.decode()
+            assert (d.status() == 0).all(), d.status()
+            coef = d.coefficients()
+            for i, w in enumerate(want):
+                assert np.array_equal(d.image_coefficients(i, coef), w["coef"]), (flags, i)
+                assert np.array_equal(d.rgb(i), w["rgb"]), (flags, i)
+    try:                                                        # and the oracle, with its deviation switch, agrees
+        port.set_dc16(True)
+        for f, w in zip(files, want):
+            assert np.array_equal(port.decode(f)["rgb"], w["rgb"])
+    finally:
+        port.set_dc16(False)
+
+
+@pytest.mark.timeout(120)
+def test_ac_table_that_never_advances_terminates(hjd, port):
+    """a DHT in which every AC code is a size-0 symbol with a run other than 0 / 15 never
+    completes a block; the reference spins forever (loadjpg.cpp:700-829).  Every kernel must return, flag the
+    image, leave good neighbours alone and produce output that depends on the input alone."""
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    good = cases.small_cases()["420_64x48_q85"]
+    stuck = {(1, 0): (jw.STUCK_AC_BITS, jw.STUCK_AC_VALS), (1, 1): (jw.STUCK_AC_BITS, jw.STUCK_AC_VALS)}
+    free = jw.replace_tables(encode_jpeg(synth_rgb(320, 240, 61), 90, "4:2:0"), stuck)           # kernel 1b
+    rst = jw.replace_tables(encode_jpeg(synth_rgb(320, 240, 62), 90, "4:2:0", restart_blocks=4), stuck)   # kernel 1a
+    big = jw.replace_tables(encode_jpeg(cases.noise_rgb(512, 512, 63), 95, "4:4:4"), stuck)      # many sub-sequences
+    assert hjd.probe(free)[1].scan_bytes > 4096
+    want = port.decode(good)["rgb"]
+    for flags in (0, hjd.FLAG_NO_SELFSYNC):
+        with hjd.BatchDecoder(0, flags) as d:
+            outs = []
+            for rep in range(2):
+                d.upload([big, good, good])                     # different slab contents in between
+                d.decode()
+                d.status()
+                files = [good, free, rst, big, good]
+                d.upload(files)
+                d.decode()
+                st = d.status()
+                assert st[0] == 0 and st[4] == 0, st
+                assert st[1] > 0 and st[2] > 0 and st[3] > 0, st
+                assert np.array_equal(d.rgb(0), want) and np.array_equal(d.rgb(4), want)
+                outs.append((st.copy(), d.coefficients().copy()))
+            assert np.array_equal(outs[0][0], outs[1][0])
+            assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_trailer_after_eoi_is_not_entropy_data(hjd, port):
+    """bytes after EOI (padding, RSTn look-alikes, a second image) raise no restart warning and do
+    not change the pixels."""
+    a = cases.small_cases()["420_100x70_ri2"]
+    b = cases.small_cases()["444_gradient_q95"]                  # restart-free, kernel 1b
+    files = [a + b"\x00" * 300 + b"\xff\xd1\xff\xd2\xff\xd3" + a, b + b"\xff\xd0" * 40 + b]
+    with hjd.BatchDecoder(0) as d:
+        d.upload(files)
+        d.decode()
+        assert (d.status() == 0).all(), d.status()
+        assert np.array_equal(d.rgb(0), port.decode(a)["rgb"])
+        assert np.array_equal(d.rgb(1), port.decode(b)["rgb"])
+
+
+def test_six_tables_and_every_device_of_the_process(hjd, port):
+    """Function attributes are per device: six distinct Huffman tables need more than 48 KB of
+    shared memory in kernel 1a, the write pass of kernel 1b always does.  One process, one batch handle per
+    visible GPU, the same batch on each: identical to device 0 and to the oracle."""
+    six, src = six_table_image(port)
+    six_free, _ = six_table_image(port, restart_interval=0)
+    big = cases.small_cases()["444_gradient_q95"]
+    files = [six, big, six_free, cases.small_cases()["gray_64x64"]]
+    want = [port.decode(src), port.decode(big), port.decode(src), port.decode(files[3])]
+    n_dev = hjd.lib().hjd_device_count()
+    ref = None
+    for dev in range(n_dev):
+        with hjd.BatchDecoder(dev) as d:
+            d.upload(files)
+            d.decode()
+            assert (d.status() == 0).all(), (dev, d.status())
+            coef = d.coefficients()
+            for i, w in enumerate(want):
+                assert np.array_equal(d.image_coefficients(i, coef), w["coef"]), (dev, i)
+                assert np.array_equal(d.rgb(i), w["rgb"]), (dev, i)
+            slab = d.rgb_slab().copy()
+            if ref is None:
+                ref = slab
+            assert np.array_equal(slab, ref), dev
+
+
+def test_chunk_images_is_honoured(hjd, port):
+    """hjd_batch_decode_host(chunk_images = k): k images per chunk; the bytes do not depend on k."""
+    files = list(cases.small_cases().values())[:11]
+    arena = hjd.PinnedArena(files)
+    need = hjd.rgb_slab_bytes(arena)
+    outs = []
+    with hjd.BatchDecoder(0) as d:
+        for k in (0, 1, 2, 5, 100):
+            out = np.zeros(need, dtype=np.uint8)
+            offs, st = d.decode_host(arena, out.ctypes.data, need, chunk_images=k)
+            assert (st == 0).all()
+            outs.append(out)
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])
+        with pytest.raises(hjd.HjdError):
+            d.decode_host(arena, outs[0].ctypes.data, need, chunk_images=-1)
+    o = port.decode(files[3])
+    n = o["rgb"].size
+    assert np.array_equal(outs[0][int(offs[3]):int(offs[3]) + n].reshape(o["rgb"].shape), o["rgb"])
+    arena.close()
+
+
+def test_equal_hash_keys_do_not_share_tables(hjd, port):
+    """table sets are shared by content, compared byte for byte -- not by hash alone.  Two images
+    with different tables (standard vs optimised) and one pair with identical ones, interleaved."""
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    a = encode_jpeg(synth_rgb(96, 64, 71), 85, "4:2:0", 4)
+    b = encode_jpeg(synth_rgb(96, 64, 72), 85, "4:2:0", 4, optimize=True)
+    c = encode_jpeg(synth_rgb(96, 64, 73), 40, "4:2:0", 4)     # a's Huffman tables, other quantisation tables
+    files = [a, b, c, a, b, c, b, a]
+    with hjd.BatchDecoder(0) as d:
+        d.upload(files)
+        d.decode()
+        assert (d.status() == 0).all()
+        for i, f in enumerate(files):
+            assert np.array_equal(d.rgb(i), port.decode(f)["rgb"]), i

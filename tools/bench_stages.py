@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import hls_jpeg_decoder_b200 as hjd  # noqa: E402
 
-VARIANTS = (("default", 0, 0), ("planes", hjd.FLAG_KEEP_PLANES, 0), ("strip", hjd.FLAG_FUSED, 0),
+VARIANTS = (("default", 0, 0), ("planes", hjd.FLAG_KEEP_PLANES, 0), 
             ("default-chunked", 0, 1500000), ("planes-chunked", hjd.FLAG_KEEP_PLANES, 1500000))
 
 
