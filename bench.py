@@ -44,6 +44,11 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records that follow the timed headline (strong scaling of one batch = configs[2], "
+                         "configs[3] and configs[4], the oracle-checked parity block)")
+    ap.add_argument("--extra-steps", type=int, default=5)
+    ap.add_argument("--parity-images", type=int, default=8, help="images per rank checked against the oracle after the timed region")
     return ap.parse_args()
 
 
@@ -72,7 +77,7 @@ WORKLOADS = {
 }
 
 
-def load_images(n: int, rank: int, world: int, config: str = "c2", scaling: str = "weak") -> list[bytes]:
+def load_images(n: int, rank: int, world: int, config: str = "c2", scaling: str = "weak", with_ids: bool = False):
     """Seeded images of one BASELINE.json workload (tools/gen_jpegs), cached on local disk so that
     the ranks of one run (and the reference arm) generate them only once."""
     from tools import gen_jpegs
@@ -106,10 +111,11 @@ def load_images(n: int, rank: int, world: int, config: str = "c2", scaling: str 
         # config 3: ONE batch cut into contiguous image ranges balanced by compressed bytes
         from hls_jpeg_decoder_b200.sharding import shard_range
         lo, hi = shard_range(sizes, rank, world)
-        return files[lo:hi]
+        return (files[lo:hi], list(range(lo, hi))) if with_ids else files[lo:hi]
     # weak: every rank owns a different rotation of the same seeded set (independent shards)
     k = (rank * 131) % max(len(files), 1)
-    return files[k:] + files[:k]
+    ids = list(range(k, len(files))) + list(range(k))
+    return (files[k:] + files[:k], ids) if with_ids else files[k:] + files[:k]
 
 
 class ClockSampler:
@@ -240,6 +246,120 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
+# sub-records measured AFTER the timed headline (never inside it)
+# ---------------------------------------------------------------------------------------------
+def timed_resident(dec, steps, barrier):
+    """K resident decodes bracketed by barriers; CUDA events on the launching stream.  Returns ms for the K steps
+    and the stage times of the last one."""
+    for _ in range(3):
+        dec.decode()
+    dec.sync()
+    barrier()
+    dec.mark(0)
+    for _ in range(steps):
+        dec.decode()
+    dec.mark(1)
+    dec.sync()
+    barrier()
+    return dec.elapsed_ms(0, 1), dec.timings()
+
+
+def reduce_max_sum(dist, ms, sums):
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    v = torch.tensor([float(x) for x in sums], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    return float(t.item()), [float(x) for x in v.tolist()]
+
+
+def sub_record(hjd, dist, barrier, local_rank, rank, world, config, scaling, steps, peak):
+    """One BASELINE.json workload, resident in HBM, K steps: whole-job MP/s, stage times, roofline fractions."""
+    wl = WORKLOADS[config]
+    files = load_images(wl["n"], rank, world, config, scaling)
+    arena = hjd.PinnedArena(files)
+    dec = hjd.BatchDecoder(local_rank)
+    try:
+        dec.upload_arena(arena)
+        dec.sync()
+        ms, t = timed_resident(dec, steps, barrier)
+        st = dec.status()
+        ok = bool((st == 0).all())
+        alg = dec.scan_bytes + 3 * dec.pixels
+        ms_max, (pix, scan, algs, imgs) = reduce_max_sum(dist, ms, [dec.pixels, dec.scan_bytes, alg, len(files)])
+        stage = {k: round(t[k], 4) for k in ("scan_ms", "entropy_ms", "idct_ms", "color_ms")}
+        dom = max(stage, key=stage.get)
+        rec = {"workload": f"{int(imgs)} x {wl['desc']}", "scaling": scaling, "images_per_gpu_rank0": len(files),
+               "steps": steps, "ms_per_step": round(ms_max / steps, 4),
+               "MP_per_s": round(pix / 1e6 * steps / (ms_max / 1e3), 1),
+               "compressed_GB_per_s": round(scan * steps / (ms_max / 1e3) / 1e9, 2),
+               "stage_ms_rank0": stage, "status_ok": ok,
+               "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""),
+                            "frac": round(alg / (max(stage[dom], 1e-6) / 1e3) / 1e9 / peak, 4),
+                            "whole_step_frac": round(algs / (ms_max / steps / 1e3) / 1e9 / peak / world, 4),
+                            "algorithmic_bytes_per_step": int(algs)}}
+        if config in ("c4", "c2nr"):
+            rec["selfsync_rounds"] = dec.selfsync_rounds
+        return rec
+    finally:
+        dec.close()
+        arena.close()
+
+
+def parity_block(hjd, dist, dec, files, file_ids, rank, world, k):
+    """Result check of the TIMED batch, outside the timed region.  Per rank: k images of its batch, spread over
+    it, are (a) entropy-decoded by the oracle and compared coefficient for coefficient with what the GPU left
+    in the slab, (b) for one of them, decoded in full by the oracle and compared pixel for pixel; (c) the sha256
+    of every checked image's RGB is gathered, and rank 0 -- which holds every file -- decodes the same file
+    ids itself and compares: rank r's image equals rank 0's decode of the same file."""
+    import hashlib
+    import numpy as np
+    from oracle import port
+    n = len(files)
+    pick = sorted(set(int(round(j * (n - 1) / max(k - 1, 1))) for j in range(min(k, n))))
+    coef_bad = blocks = rgb_bad = 0
+    shas = []
+    for j, i in enumerate(pick):
+        o = port.decode(files[i], entropy_only=(j != 0), want_planes=False)
+        got = dec.image_coefficients_direct(i)
+        coef_bad += int((got != o["coef"]).any(axis=1).sum())
+        blocks += got.shape[0]
+        rgb = dec.rgb(i)
+        if j == 0:
+            rgb_bad += int((rgb != o["rgb"]).sum())
+        shas.append((int(file_ids[i]), hashlib.sha256(rgb.tobytes()).hexdigest()))
+    gathered = [shas]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, shas)
+    cross_bad = cross = 0
+    if rank == 0:
+        want = {}
+        todo = sorted({fid for g in gathered for fid, _ in g})
+        all_files = load_images(WORKLOADS["c2"]["n"], 0, 1)
+        with hjd.BatchDecoder(dec.device) as d2:
+            d2.upload([all_files[fid] for fid in todo])
+            d2.decode()
+            for q, fid in enumerate(todo):
+                want[fid] = hashlib.sha256(d2.rgb(q).tobytes()).hexdigest()
+        for g in gathered:
+            for fid, h in g:
+                cross += 1
+                cross_bad += int(want[fid] != h)
+    import torch
+    v = torch.tensor([float(len(pick)), float(blocks), float(coef_bad), float(rgb_bad)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    imgs, blocks, coef_bad, rgb_bad = (int(x) for x in v.tolist())
+    return {"checker": "oracle/jpeg_oracle.c (restatement pinned to the reference, tests/test_oracle.py)",
+            "images_checked": imgs, "coef_blocks_checked": blocks, "coef_block_mismatches": coef_bad,
+            "rgb_full_compares": world, "rgb_sample_mismatches": rgb_bad,
+            "cross_rank_sha_checked": cross, "cross_rank_sha_mismatches": cross_bad,
+            "mismatches": coef_bad + rgb_bad + cross_bad}
+
+
+# ---------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
@@ -261,13 +381,14 @@ def run_ours(args, rank, local_rank, world):
 
     wl = WORKLOADS[args.config]
     n_req = args.images or wl["n"]
-    files = load_images(n_req, rank, world, args.config, args.scaling)
+    files, file_ids = load_images(n_req, rank, world, args.config, args.scaling, with_ids=True)
     n = len(files)
     arena = hjd.PinnedArena(files)
     dec = hjd.BatchDecoder(local_rank)
     dec.upload_arena(arena)
     dec.sync()
     pixels, scan_bytes = dec.pixels, dec.scan_bytes
+    working_set = dec.coef_bytes + dec.rgb_bytes
     alg_bytes = scan_bytes + 3 * pixels                   # B_alg = scan bytes in + RGB out
 
     for _ in range(max(args.warmup, 3)):
@@ -342,6 +463,22 @@ def run_ours(args, rank, local_rank, world):
                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()), "steps": args.e2e_steps}
         hjd.lib().hjd_host_free(out_ptr)
 
+    # sub-records after the timed regions: parity of the timed batch, then the other BASELINE.json configs
+    extras = {}
+    if not args.no_extras and args.config == "c2" and args.scaling == "weak":
+        peak0 = measured_peak()[0]
+        extras["parity"] = parity_block(hjd, dist, dec, files, file_ids, rank, world, args.parity_images)
+        dec.close()
+        arena.close()
+        strong = sub_record(hjd, dist, barrier, local_rank, rank, world, "c2", "strong", args.extra_steps, peak0)
+        # every rank of the weak headline decoded the whole 1024-image batch on one GPU: its step time is t(1)
+        strong["efficiency_vs_1gpu"] = round((ms_max / args.steps) / (world * strong["ms_per_step"]), 4)
+        strong["ms_per_step_1gpu"] = round(ms_max / args.steps, 4)
+        extras["strong"] = strong
+        extras["c4"] = sub_record(hjd, dist, barrier, local_rank, rank, world, "c4", "weak", args.extra_steps, peak0)
+        extras["c5"] = sub_record(hjd, dist, barrier, local_rank, rank, world, "c5", "weak", args.extra_steps, peak0)
+        dec = arena = None
+
     if rank == 0:
         peak, peak_src = measured_peak()
         dom = max(stage, key=stage.get)
@@ -361,7 +498,7 @@ def run_ours(args, rank, local_rank, world):
                 "data": "synthetic",
                 "config": {"workload": f"{int(job_images)} x {wl['desc']}; inputs resident in HBM",
                            "images_per_gpu": n, "scan_bytes_per_image": scan_bytes // max(n, 1),
-                           "l2_policy": f"per-step working set (coefficient + RGB slabs, {(dec.coef_bytes + dec.rgb_bytes) / 1e9:.2f} GB on rank 0) "
+                           "l2_policy": f"per-step working set (coefficient + RGB slabs, {working_set / 1e9:.2f} GB on rank 0) "
                                         "against a 126 MB L2; every step rewrites all of it",
                            "parallelism": f"{world} independent shards ({args.scaling} scaling), no collective"},
                 "compressed_GB_per_s": round(job_scan * args.steps / (ms_max / 1e3) / 1e9, 2),
@@ -377,6 +514,7 @@ def run_ours(args, rank, local_rank, world):
             line["ms_per_step_median"] = round(step_ms[len(step_ms) // 2], 4)
         if e2e:
             line["e2e"] = e2e
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(load_images(WORKLOADS["c2"]["n"], 0, 1) if args.config != "c2" else files, per_core=1)
             ref.step()
@@ -385,8 +523,9 @@ def run_ours(args, rank, local_rank, world):
                                     "cores": ref.cores, "kind": ref.kind, "sample": ref.describe()}
             ref.close()
         print(json.dumps(line), flush=True)
-    dec.close()
-    arena.close()
+    if dec is not None:
+        dec.close()
+        arena.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

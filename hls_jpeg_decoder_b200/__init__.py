@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = ["probe", "ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU", "FLAG_BMP_OUT"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HJD_LIB_PATH") or os.path.join(_HERE, "libhjd.so")   # override: tuning builds only
@@ -35,6 +35,7 @@ FLAG_KEEP_PLANES = 1
 FLAG_HOST_SCAN = 2
 FLAG_NO_SELFSYNC = 8
 FLAG_FUSED_MCU = 16
+FLAG_BMP_OUT = 32
 
 IMG_WARN_BAD_CODE, IMG_WARN_COEF_RANGE, IMG_WARN_OVERRUN, IMG_WARN_RESTART = 1, 2, 4, 8
 
@@ -105,6 +106,13 @@ _SIGS = {
     "hjd_batch_download_image": (c_int, [c_void_p, c_int, c_void_p]),
     "hjd_batch_download_coef": (c_int, [c_void_p, c_void_p]),
     "hjd_batch_download_planes": (c_int, [c_void_p, c_void_p]),
+    "hjd_batch_download_image_coef": (c_int, [c_void_p, c_int, c_void_p]),
+    "hjd_batch_download_block_last": (c_int, [c_void_p, c_void_p]),
+    "hjd_batch_bmp_bytes": (c_uint64, [c_void_p, c_int]),
+    "hjd_batch_download_bmp": (c_int, [c_void_p, c_int, c_void_p]),
+    "hjd_batch_densify_coef": (c_int, [c_void_p]),
+    "hjd_batch_device_block_last": (c_void_p, [c_void_p]),
+    "hjd_out_slab_bytes": (c_uint64, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_uint]),
     "hjd_batch_decode_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_void_p,
                                       c_uint64, POINTER(c_uint64), c_void_p, c_int]),
     "hjd_rgb_slab_bytes": (c_uint64, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int]),
@@ -364,6 +372,13 @@ class BatchDecoder:
         _check(lib().hjd_batch_download_image(self._h, i, out.ctypes.data), "hjd_batch_download_image")
         return out
 
+    def bmp(self, i: int) -> bytes:
+        """The BMP file of image i (batch created with FLAG_BMP_OUT): what WriteBMP24 would have written."""
+        n = lib().hjd_batch_bmp_bytes(self._h, i)
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(lib().hjd_batch_download_bmp(self._h, i, out.ctypes.data), "hjd_batch_download_bmp")
+        return out[:n].tobytes()
+
     def rgb_slab(self) -> np.ndarray:
         out = np.zeros(max(self.rgb_bytes, 1), dtype=np.uint8)
         _check(lib().hjd_batch_download_rgb(self._h, out.ctypes.data), "hjd_batch_download_rgb")
@@ -380,6 +395,20 @@ class BatchDecoder:
         inf = self.info(i)
         c = self.coefficients() if all_coef is None else all_coef
         return c[inf.block_base:inf.block_base + inf.n_blocks]
+
+    def block_last(self) -> np.ndarray:
+        """Per block, the zig-zag index of its last stored coefficient (what the sparse IDCT goes by)."""
+        n = self.coef_bytes // 128
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(lib().hjd_batch_download_block_last(self._h, out.ctypes.data), "hjd_batch_download_block_last")
+        return out[:n]
+
+    def image_coefficients_direct(self, i: int) -> np.ndarray:
+        """Blocks of image i only (int16 [n_blocks, 64]), without downloading the whole slab."""
+        inf = self.info(i)
+        out = np.zeros((max(inf.n_blocks, 1), 64), dtype=np.int16)
+        _check(lib().hjd_batch_download_image_coef(self._h, i, out.ctypes.data), "hjd_batch_download_image_coef")
+        return out[:inf.n_blocks]
 
     def planes(self, i: int, slab: np.ndarray | None = None):
         """(Y, Cb, Cr) uint8 planes of image i (MCU-padded); requires FLAG_KEEP_PLANES."""

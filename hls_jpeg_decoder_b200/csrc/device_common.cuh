@@ -29,13 +29,15 @@ __device__ __forceinline__ uint32_t hjd_shr(uint32_t v, uint32_t n) { uint32_t r
 __device__ __forceinline__ uint32_t hjd_shl(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 
 
-// Second level of the symbol lookup: codes longer than the first-level table.  t = shared-window address
-// of the table, e1 = the first-level entry (len field 0), peek16 = next 16 bits.  Returns the symbol
-// fields, or 0 when no code matches.  Straight-line: one shared-memory load.
-__device__ __forceinline__ uint32_t hjd_long_code(uint32_t t, uint32_t e1, uint32_t peek16)
+// The symbol whose code starts the 32-bit window `hi` (MSB first): len | size << 5 | advance << 9 (see
+// HjdHuffTable).  t = shared-window address of the table.  Codes longer than the first-level table take
+// one more load; an unassigned code yields HJD_BAD_ENTRY (advance 127).
+__device__ __forceinline__ uint32_t hjd_lookup(uint32_t t, uint32_t hi)
 {
-    const uint32_t nb = (e1 >> 5) & 7u;                                  // 1..6 more bits decide
-    const uint32_t idx = ((e1 >> 8) << 1) + hjd_shr(peek16 & ((1u << (16 - HJD_LUT_BITS)) - 1u), (16 - HJD_LUT_BITS) - nb);
-    const uint32_t e = hjd_lds_u16(t + HJD_TAB_LUT2_OFF + ((idx & (HJD_LUT2_SIZE - 1)) << 1));
-    return e1 ? e : 0u;
+    uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
+    if ((e & 31u) == 0) {
+        const uint32_t idx = hjd_shr((hi >> 16) & ((1u << (16 - HJD_LUT_BITS)) - 1u), (e >> 5) & 7u);
+        e = hjd_lds_u16(t + HJD_TAB_LUT2_OFF + ((e >> 8) << 2) + (idx << 1));
+    }
+    return e;
 }

@@ -20,12 +20,16 @@
 //     kadv  advance of the zig-zag index: DC 1; AC run+1; EOB 64; ZRL 16; other size-0 symbols 0 (ignored)
 //   A coefficient is written at (k + kadv - 1) iff size != 0: a DC symbol with size 0 adds nothing to
 //   the predictor, and the output block is zero-filled beforehand.
-//   longer codes (second level): a first-level entry with len == 0 and the rest non-zero points at a
-//     sub-table: nb << 5 | (offset / 2) << 8, nb = 1..6 further bits to look at;
-//     lut2[offset + (the next nb bits)] has the same layout as a first-level entry (len = full length).
-//     0 (either level) = no such code.  One more shared-memory load instead of a search over the lengths:
-//     with ~12 symbols per block some lane of a warp holds a long code on every other step.
+//   longer codes (second level): a first-level entry with len == 0 points at a sub-table:
+//     sh << 5 | (offset / 2) << 8, where 6 - sh = 1..6 further bits decide;
+//     lut2[offset + (the next 6 bits >> sh)] has the same layout as a first-level entry (len = full length).
+//     One more shared-memory load instead of a search over the lengths: with ~12 symbols per block some
+//     lane of a warp holds a long code on every other step.
+//   no such code (either level): HJD_BAD_ENTRY = one bit consumed, no value, zig-zag advance 127 -- the
+//     block ends there; an advance above 64 is how the kernels recognise it (kernel 1a stops the interval,
+//     kernel 1b flags the image and carries on, identically in all of its passes).
 #define HJD_SYM_FIELDS(len, size, kadv) ((uint32_t)(len) | (uint32_t)(size) << 5 | (uint32_t)(kadv) << 9)
+#define HJD_BAD_ENTRY   HJD_SYM_FIELDS(1, 0, 127)
 #define HJD_LUT2_SIZE   512                   // canonical codes: at most 256 (one entry per long code) + 126 (sub-tables that straddle a change of length)
 struct HjdHuffTable {
     uint16_t lut[HJD_LUT_SIZE];
@@ -104,7 +108,9 @@ struct HjdScanSlice {
 #define HJD_SS_SLACK       512          // zeroed bytes after every de-stuffed stream: a block that starts in the last
                                         // sub-sequence may run 63 x 26 bits past it, plus the words in flight
 #define HJD_SS_THREADS     256
+#ifndef HJD_SS_FIX_WARPS
 #define HJD_SS_FIX_WARPS   4     // warps per CTA of the synchronisation rounds, one range of sub-sequences each
+#endif
 #define HJD_SS_FIX_MAXR    256   // largest range
 #define HJD_SS_FIX_OVERLAP 4     // sub-sequences before a range that its warp re-checks privately
 

@@ -191,7 +191,8 @@ static uint32_t sym_fields(uint32_t len, uint32_t sym, bool is_ac)
 
 bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)
 {
-    memset(t, 0, sizeof *t);
+    for (int i = 0; i < HJD_LUT_SIZE; i++) t->lut[i] = (uint16_t)HJD_BAD_ENTRY;
+    for (int i = 0; i < HJD_LUT2_SIZE; i++) t->lut2[i] = (uint16_t)HJD_BAD_ENTRY;
     // Canonical code assignment (what GenHuffCodes does, openjpg.cpp:48-66): codes of one length
     // are consecutive; the counter doubles when the length grows.
     uint32_t first_code[17];
@@ -228,7 +229,7 @@ bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)
     for (uint32_t p = 0; p < HJD_LUT_SIZE; p++) {
         if (!nb_of[p]) continue;
         if (used + (1u << nb_of[p]) > HJD_LUT2_SIZE) return false;      // cannot happen for canonical codes (see HJD_LUT2_SIZE)
-        t->lut[p] = (uint16_t)((uint32_t)nb_of[p] << 5 | (used >> 1) << 8);
+        t->lut[p] = (uint16_t)((uint32_t)((16 - HJD_LUT_BITS) - nb_of[p]) << 5 | (used >> 1) << 8);
         used += 1u << nb_of[p];
     }
     valptr = valptr_long;
@@ -251,12 +252,11 @@ uint32_t hjd_host_huff_lookup(const HjdHuffTable* t, uint32_t peek16)
 {
     // host mirror of the kernels' symbol lookup (first level, then hjd_long_code in device_common.cuh)
     peek16 &= 0xFFFFu;
+    // host mirror of hjd_lookup() in device_common.cuh
     uint32_t e = t->lut[peek16 >> (16 - HJD_LUT_BITS)];
     if ((e & 31u) == 0) {
-        if (e == 0) return 0;
-        const uint32_t nb = (e >> 5) & 7u;
-        const uint32_t idx = ((e >> 8) << 1) + ((peek16 & ((1u << (16 - HJD_LUT_BITS)) - 1u)) >> ((16 - HJD_LUT_BITS) - nb));
-        e = t->lut2[idx & (HJD_LUT2_SIZE - 1)];
+        const uint32_t idx = (peek16 & ((1u << (16 - HJD_LUT_BITS)) - 1u)) >> ((e >> 5) & 7u);
+        e = t->lut2[(((e >> 8) << 1) + idx) & (HJD_LUT2_SIZE - 1)];
     }
     return e;
 }

@@ -26,6 +26,7 @@
 #include "selfsync.cuh"
 #include "device_common.cuh"
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------
 // device-wide exclusive scan (uint32, wrap-around arithmetic)
@@ -345,22 +346,18 @@ struct SsBits {
 };
 
 // One Huffman symbol from the window (hi:lo): the fields of hjd_sym_fields plus the extended value.
-// An undecodable code consumes one bit (as a size-0 symbol) so that every path makes progress; the
-// synchronisation rounds and the write pass must agree on this rule, which is why they share this code.
+// An undecodable code consumes one bit and ends the block (HJD_BAD_ENTRY) so that every path makes progress;
+// the synchronisation rounds and the write pass must agree on this rule, which is why they share this code.
 struct SsSym { uint32_t used, size, kadv; int val; bool bad; };
 
 __device__ __forceinline__ SsSym ss_symbol(uint32_t t, uint32_t hi, uint32_t lo, bool is_ac)
 {
     SsSym s;
-    uint32_t e = hjd_lds_u16(t + ((hi >> (32 - HJD_LUT_BITS)) << 1));
-    s.bad = false;
-    if ((e & 31u) == 0) {
-        e = hjd_long_code(t, e, hi >> 16);
-        if (e == 0) { e = hjd_sym_fields(1, 0, is_ac); s.bad = true; }
-    }
+    const uint32_t e = hjd_lookup(t, hi);
     const uint32_t len = e & 31u;
     s.size = (e >> 5) & 15u;
     s.kadv = (e >> 9) & 127u;
+    s.bad = s.kadv > 64u;
     const uint32_t after = __funnelshift_l(lo, hi, len);
     const uint32_t v = hjd_shr(after, 32u - s.size);
     const int neg = ~((int)after >> 31);
@@ -695,7 +692,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                const HjdSsSeg* __restrict__ segs,
                const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
                const uint64_t* __restrict__ x_arr, const uint32_t* __restrict__ prefix,
-               int16_t* __restrict__ coef, int32_t* __restrict__ status)
+               int16_t* __restrict__ coef, uint8_t* __restrict__ blk_last, int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
     constexpr uint32_t kTabBytes = (uint32_t)sizeof(HjdHuffTable);
@@ -740,6 +737,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     SsBits br;
     br.hi = br.lo = br.wa = br.wb = br.wc = 0; br.nbits = 64; br.wp = (const uint32_t*)D;
     int flags = 0;
+    uint32_t klast = 0;               // zig-zag index of the last coefficient stored in the current block
     int steps = 0;                    // rounds spent on the current owned block
     int rem_min = 0;                  // rem below this: the bit position has left the zeroed slack
     uint32_t own_end = 0;             // image-local index one past the last block this thread owns
@@ -789,7 +787,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                     rem -= (int)sy.used;
                     const uint32_t kpos = (uint32_t)k + sy.kadv - 1u;
                     if (owned && sy.size) {
-                        if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)sy.val);
+                        if (kpos <= 63u) { hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)sy.val); klast = kpos; }
                         else flags |= HJD_ST_COEF_RANGE;
                     }
                     k += (int)sy.kadv;
@@ -814,15 +812,19 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
         // ---- bounds (see SS_WRITE_MAX_STEPS) ---------------------------------------------------
         if (!finished && !done_block && owned && (++steps > SS_WRITE_MAX_STEPS || rem < rem_min)) {
             flags |= steps > SS_WRITE_MAX_STEPS ? HJD_ST_BAD_CODE : HJD_ST_OVERRUN;
-            for (uint32_t bz = blk; bz < own_end; bz++)
-                for (int q = 0; q < 8; q++) ((uint4*)coef)[(size_t)(blk_base + bz) * 8u + q] = make_uint4(0, 0, 0, 0);
+            for (uint32_t bz = blk; bz < own_end; bz++) {            // zero blocks: first sector + "ends at index 0"
+                for (int q = 0; q < 2; q++) ((uint4*)coef)[(size_t)(blk_base + bz) * 8u + q] = make_uint4(0, 0, 0, 0);
+                blk_last[blk_base + bz] = 0;
+            }
             blk = own_end;
             finished = true;
         }
         // ---- block hand-over ---------------------------------------------------------------
-        uint32_t flush_blk = 0;
+        uint32_t flush_blk = 0, flush_last = 0;
         if (done_block) {
             steps = 0;
+            flush_last = klast;
+            klast = 0;
             p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
             hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
             flush_blk = blk_base + blk;
@@ -838,18 +840,22 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
         // ---- cooperative flush, four blocks per step (as in kernel 1a) ----------------------
         const uint32_t m = __ballot_sync(0xffffffffu, done_block);
         if (m) {
-            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane);
+            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane | flush_last << 8);
             __syncwarp();
             const int n_done = __popc(m);
             const uint32_t chunk = (uint32_t)lane & 7u;
             for (int base = 0; base < n_done; base += 4) {
                 const int idx = base + (lane >> 3);
                 if (idx < n_done) {
-                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);
-                    const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
-                    const uint4 w = hjd_lds_v4_sync(src);
-                    hjd_sts_zero16_sync(src);
-                    ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
+                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);     // {block, owner lane | last index << 8}
+                    const uint32_t owner = ent.y & 255u, last = ent.y >> 8;
+                    if ((chunk >> 1) <= (last >> 4)) {                                     // only the sectors that hold coefficients
+                        const uint32_t src = warp_slots + owner * 128u + ((chunk ^ (owner & 7u)) << 4);
+                        const uint4 w = hjd_lds_v4_sync(src);
+                        hjd_sts_zero16_sync(src);
+                        ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
+                    }
+                    if (chunk == 0) blk_last[ent.x] = (uint8_t)last;
                 }
             }
             __syncwarp();
@@ -868,11 +874,13 @@ cudaError_t hjd_selfsync_init_device(int* max_sync_ctas)
     cudaError_t e = cudaFuncSetAttribute(hjd_k_ss_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable)));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(hjd_k_ss_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_sync_smem());
+    if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hjd_k_ss_sync, HJD_SS_FIX_WARPS * 32, ss_sync_smem())) != cudaSuccess) return e;
-    if (per_sm > 4) per_sm = 4;        // the rounds are latency-bound chains: more resident CTAs only make the barrier slower
+    if (const char* env = getenv("HJD_SS_SYNC_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning
     *max_sync_ctas = sms * (per_sm < 1 ? 1 : per_sm);
     return cudaSuccess;
 }
@@ -881,12 +889,12 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
                                 const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
                                 const uint32_t* dlen,
                                 uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
-                                int32_t* status, cudaStream_t st)
+                                uint8_t* blk_last, int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
     const size_t smem = HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
     hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, segs, dst, dlen, n_subs_total, x, prefix,
-                                                        coef, status);
+                                                        coef, blk_last, status);
     return cudaGetLastError();
 }
 
@@ -898,7 +906,7 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
 // keep the output a function of the input alone.  Nothing to do for a complete scan.
 __global__ void __launch_bounds__(256)
 hjd_k_ss_fill_tail(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __restrict__ ss, int n_ss,
-                   const uint32_t* __restrict__ prefix, int16_t* __restrict__ coef)
+                   const uint32_t* __restrict__ prefix, int16_t* __restrict__ coef, uint8_t* __restrict__ blk_last)
 {
     // one warp per image: nothing but two loads for a complete scan
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -908,15 +916,19 @@ hjd_k_ss_fill_tail(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __re
     const uint64_t started = prefix[s.sub_base + s.n_subs] - prefix[s.sub_base];
     const uint64_t n_blocks = d->n_blocks;
     if (started >= n_blocks) return;
-    uint4* out = (uint4*)coef + (d->block_base + started) * 8;
-    const uint64_t n16 = (n_blocks - started) * 8;
-    for (uint64_t i = lane; i < n16; i += 32) out[i] = make_uint4(0, 0, 0, 0);
+    // a zero block = a zero first sector and "ends at index 0"
+    for (uint64_t bz = started + lane; bz < n_blocks; bz += 32) {
+        uint4* out = (uint4*)coef + (d->block_base + bz) * 8;
+        out[0] = make_uint4(0, 0, 0, 0);
+        out[1] = make_uint4(0, 0, 0, 0);
+        blk_last[d->block_base + bz] = 0;
+    }
 }
 
 cudaError_t hjd_launch_ss_fill_tail(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, const uint32_t* prefix,
-                                    int16_t* coef, cudaStream_t st)
+                                    int16_t* coef, uint8_t* blk_last, cudaStream_t st)
 {
     if (n_ss <= 0) return cudaSuccess;
-    hjd_k_ss_fill_tail<<<(n_ss + 7) / 8, 256, 0, st>>>(imgs, ss, n_ss, prefix, coef);
+    hjd_k_ss_fill_tail<<<(n_ss + 7) / 8, 256, 0, st>>>(imgs, ss, n_ss, prefix, coef, blk_last);
     return cudaGetLastError();
 }

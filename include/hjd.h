@@ -62,6 +62,10 @@ extern "C" {
 #define HJD_FLAG_KEEP_PLANES   1u   /* unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap, hjd_batch_download_planes) */
 #define HJD_FLAG_HOST_SCAN     2u   /* find RSTn markers on the host instead of the GPU pre-pass */
 #define HJD_FLAG_FUSED_MCU    16u   /* (default behaviour) kernels 2+3 fused per MCU: one thread decodes a whole MCU to RGB */
+#define HJD_FLAG_BMP_OUT      32u   /* the output slab holds, per image, the BMP FILE WriteBMP24 would write (openjpg.cpp:504-570:
+                                       54-byte header, bottom-up B G R rows padded to 4 bytes) instead of top-down RGB24: written by
+                                       the colour kernel's epilogue, so a file writer only has to fwrite it.  The file of image i
+                                       is hjd_batch_bmp_bytes(i) bytes from rgb_offset + 10 of the slab (pixel array 64-byte aligned). */
 #define HJD_FLAG_NO_SELFSYNC   8u   /* restart-free scans: one thread per scan (kernel 1a) instead of kernel 1b */
 
 typedef struct hjd_batch hjd_batch;
@@ -170,15 +174,24 @@ uint64_t hjd_batch_plane_bytes(const hjd_batch* b);
 uint64_t hjd_batch_scan_bytes(const hjd_batch* b);    /* sum of entropy-coded bytes */
 uint64_t hjd_batch_pixels(const hjd_batch* b);        /* sum of width*height */
 
-/* Device pointers of the result slabs (valid until the next upload / destroy). */
+/* Device pointers of the result slabs (valid until the next upload / destroy).
+ * The coefficient slab is int16 [block][64] in zig-zag order, but a block is WRITTEN only up to the 32-byte
+ * sector of its last non-zero coefficient, whose zig-zag index is block_last[block] (one byte per block);
+ * the bytes behind it are undefined until hjd_batch_densify_coef() zeroes them (the downloads below do). */
 void* hjd_batch_device_rgb(hjd_batch* b);
 void* hjd_batch_device_coef(hjd_batch* b);
+void* hjd_batch_device_block_last(hjd_batch* b);
+int   hjd_batch_densify_coef(hjd_batch* b);            /* asynchronous on the batch stream */
 void* hjd_batch_device_planes(hjd_batch* b);
 
 /* Device -> host copies (synchronous with respect to the batch stream). */
 int  hjd_batch_download_rgb(hjd_batch* b, uint8_t* dst /* hjd_batch_rgb_bytes */);
 int  hjd_batch_download_image(hjd_batch* b, int i, uint8_t* dst /* w*h*3 */);
 int  hjd_batch_download_coef(hjd_batch* b, int16_t* dst /* hjd_batch_coef_bytes */);
+uint64_t hjd_batch_bmp_bytes(const hjd_batch* b, int i);            /* HJD_FLAG_BMP_OUT: size of image i's BMP file (0: none) */
+int  hjd_batch_download_bmp(hjd_batch* b, int i, uint8_t* dst /* hjd_batch_bmp_bytes(i) */);
+int  hjd_batch_download_block_last(hjd_batch* b, uint8_t* dst /* one byte per block: last zig-zag index */);
+int  hjd_batch_download_image_coef(hjd_batch* b, int i, int16_t* dst /* n_blocks*64 */);   /* one image of the slab */
 int  hjd_batch_download_planes(hjd_batch* b, uint8_t* dst /* hjd_batch_plane_bytes */);
 
 /* End to end with host buffers: upload, decode and download in overlapped chunks
@@ -187,15 +200,17 @@ int  hjd_batch_download_planes(hjd_batch* b, uint8_t* dst /* hjd_batch_plane_byt
 int  hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes,
                            int n, uint8_t* rgb_out, uint64_t rgb_capacity, uint64_t* rgb_offsets_out,
                            int32_t* status_out, int chunk_images);
-/* Bytes hjd_batch_decode_host needs in rgb_out for these files (header parse only). */
+/* Bytes hjd_batch_decode_host needs in rgb_out for these files (header parse only); hjd_out_slab_bytes: the
+ * same for a batch created with `flags` (HJD_FLAG_BMP_OUT changes the layout). */
 uint64_t hjd_rgb_slab_bytes(const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n);
+uint64_t hjd_out_slab_bytes(const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n, unsigned flags);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA binding. */
 void* hjd_host_alloc(size_t bytes);
 void  hjd_host_free(void* p);
 
 /* Testing aid: build the kernels' two-level lookup table from BITS / HUFFVAL (as in a DHT segment) and look
- * up the next 16 bits of a stream: returns len | size << 5 | zig-zag advance << 9 (0: no such code;
+ * up the next 16 bits of a stream: returns len | size << 5 | zig-zag advance << 9 (0xFE01: no such code;
  * 0xFFFFFFFF: the table is over-subscribed).  tests/ compare it with the canonical code walk. */
 uint32_t hjd_huff_lookup_probe(const uint8_t bits[16], const uint8_t* vals, int nvals, int is_ac, uint32_t peek16);
 

@@ -161,3 +161,64 @@ def test_equal_hash_keys_do_not_share_tables(hjd, port):
         assert (d.status() == 0).all()
         for i, f in enumerate(files):
             assert np.array_equal(d.rgb(i), port.decode(f)["rgb"]), i
+
+
+def test_bmp_output_mode_is_writebmp24_byte_for_byte(hjd, port):
+    """HJD_FLAG_BMP_OUT: the colour kernel's epilogue writes the file WriteBMP24 writes (openjpg.cpp:504-570):
+    header, bottom-up B G R rows, row padding -- for every committed fixture (odd widths: every padding
+    length), Lenna (the survey's BMP sha256) and a mixed batch on the flat grid."""
+    import glob
+    import hashlib
+    import os
+    from oracle import refbind
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    files = [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(gdir, "*.jpg")))]
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    for w in (1, 2, 3, 5, 17, 30, 63):                          # every (3w mod 4), sub-MCU and multi-MCU widths
+        files.append(encode_jpeg(synth_rgb(w, 9, 300 + w), 85, "4:2:0", 2))
+        files.append(encode_jpeg(synth_rgb(w, 21, 400 + w), 85, "4:4:4"))
+        files.append(encode_jpeg(synth_rgb(w, 8, 500 + w), 85, gray=True))
+    lenna = refbind.lenna_path()
+    if lenna:
+        files.append(open(lenna, "rb").read())
+    with hjd.BatchDecoder(0, hjd.FLAG_BMP_OUT) as d:
+        for rep in range(2):                                    # second pass: stale slab contents underneath
+            d.upload(files if rep == 0 else files[::-1])
+            d.decode()
+            assert (d.status() == 0).all()
+            order = files if rep == 0 else files[::-1]
+            for i, f in enumerate(order):
+                want = port.bmp24_bytes(port.decode(f)["rgb"])
+                got = d.bmp(i)
+                assert len(got) == len(want), i
+                assert got == want, (rep, i, d.info(i).width, d.info(i).height)
+        if lenna:
+            assert hashlib.sha256(d.bmp(0)).hexdigest() == "af6996f7f0cb092f8282bd661f95869d6c2c983b364d8722f6ff581eaf5d12e0"
+        with pytest.raises(hjd.HjdError):
+            d.rgb(0)
+    with pytest.raises(hjd.HjdError):
+        hjd.BatchDecoder(0, hjd.FLAG_BMP_OUT | hjd.FLAG_KEEP_PLANES)
+
+
+def test_sparse_coefficient_slab_and_block_ends(hjd, port):
+    """The entropy kernels write a block up to the sector of its last coefficient and record that index; the
+    dense download is the oracle's [block][64] dump, and the recorded ends are the true ones -- for blocks
+    of every length class (flat, gradients, q10 ... q100 noise), on both entropy kernels."""
+    names = ["420_flat128", "420_noise_q100", "420_noise_q10", "444_gradient_q95", "420_100x70_ri2", "gray_64x64", "444_noise_q100_ri2"]
+    files = [cases.small_cases()[n] for n in names]
+    with hjd.BatchDecoder(0) as d:
+        d.upload(files)
+        d.decode()
+        assert (d.status() == 0).all()
+        coef = d.coefficients()
+        last = d.block_last()
+        for i, f in enumerate(files):
+            o = port.decode(f, entropy_only=True)
+            c = d.image_coefficients(i, coef)
+            assert np.array_equal(c, o["coef"]), names[i]
+            nz = o["coef"] != 0
+            want = np.where(nz.any(1), 63 - np.argmax(nz[:, ::-1], axis=1), 0)
+            inf = d.info(i)
+            got = last[inf.block_base:inf.block_base + inf.n_blocks]
+            # a stored zero value (size > 0 never encodes 0) cannot occur, so the recorded end is the last non-zero
+            assert np.array_equal(got, want), names[i]
