@@ -183,6 +183,19 @@ def _ref_worker(jpg: bytes) -> float:
     return time.perf_counter() - t
 
 
+def _ref_file_worker(paths) -> float:
+    """The reference's ConvertJpgFile sequence for one file (openjpg.cpp:593-684): read, parse + JpegDecodeHW,
+    WriteBMP24 -- its own code for every step (oracle/_ref), heap buffers instead of the 105 KB stack buffer."""
+    from oracle import refbind
+    src, dst = paths
+    t = time.perf_counter()
+    jpg = open(src, "rb").read()
+    r = refbind.decode(jpg, mode=0, variant="hd", want_planes=False)
+    assert r["rc"] == 0
+    refbind.write_bmp24(dst, r["rgb"])
+    return time.perf_counter() - t
+
+
 def _port_worker(jpg: bytes) -> float:
     from oracle import port
     t = time.perf_counter()
@@ -248,6 +261,62 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 # sub-records measured AFTER the timed headline (never inside it)
 # ---------------------------------------------------------------------------------------------
+def file_to_bmp_record(hjd, files, local_rank, rank, n_images=256, with_reference=False):
+    """.jpg files on disk -> .bmp files on disk through hjd_convert_jpg_files_multi
+    (readers -> chunked GPU decodes in BMP layout -> writers), on a tmpfs so that the number is the
+    pipeline's, not a disk's.  One file is checked against the oracle's WriteBMP24 bytes."""
+    import shutil
+    import numpy as np
+    from oracle import port
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    n = min(n_images, len(files))
+    need = n * (W * H * 3 + 54) + sum(len(f) for f in files[:n])
+    free = shutil.disk_usage(base).free
+    if free < 2 * need:
+        n = max(8, int(n * free / (2.5 * need)))
+    root = os.path.join(base, f"hjd_f2b_{os.getpid()}")
+    os.makedirs(root, exist_ok=True)
+    try:
+        ins, outs = [], []
+        for i in range(n):
+            p = os.path.join(root, f"{i:05d}.jpg")
+            with open(p, "wb") as fh:
+                fh.write(files[i])
+            ins.append(p)
+            outs.append(os.path.join(root, f"{i:05d}.bmp"))
+        hjd.ConvertJpgFiles(ins[:8], outs[:8], device=local_rank)               # warm-up: contexts, page cache
+        t = time.perf_counter()
+        ok = hjd.ConvertJpgFiles(ins, outs, device=local_rank)
+        t = time.perf_counter() - t
+        assert all(ok), "file -> bmp conversion failed"
+        o = port.decode(files[0], want_planes=False, want_coef=False)
+        same = open(outs[0], "rb").read() == port.bmp24_bytes(o["rgb"])
+        rec = {"images": n, "images_per_s": round(n / t, 1), "MP_per_s": round(n * W * H / 1e6 / t, 1),
+               "bmp_GB_per_s": round(n * (W * H * 3 + 54) / t / 1e9, 2), "where": base,
+               "bmp_bytes_identical_to_WriteBMP24": bool(same),
+               "how": "hjd_convert_jpg_files_multi: file readers -> chunks of 32 images decoded with HJD_FLAG_BMP_OUT "
+                      "-> writer threads; wall clock from the first fopen to the last fclose"}
+        if with_reference:
+            from concurrent.futures import ProcessPoolExecutor
+            import multiprocessing as mp
+            from oracle import refbind
+            if refbind.available("hd"):
+                cores = os.cpu_count() or 1
+                m = min(n, cores)
+                with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+                    pairs = [(ins[i], outs[i] + ".ref.bmp") for i in range(m)]
+                    list(ex.map(_ref_file_worker, pairs[:cores]))            # load the .so before timing
+                    t0 = time.perf_counter()
+                    list(ex.map(_ref_file_worker, pairs))
+                    t0 = time.perf_counter() - t0
+                rec["reference_ConvertJpgFile"] = {"images_per_s": round(m / t0, 3), "cores": cores, "images": m,
+                                                   "kind": "reference (oracle/_ref: its own parse, JpegDecodeHW and WriteBMP24)"}
+                rec["reference_bmp_identical"] = open(pairs[0][1], "rb").read() == open(outs[0], "rb").read()
+        return rec
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def timed_resident(dec, steps, barrier):
     """K resident decodes bracketed by barriers; CUDA events on the launching stream.  Returns ms for the K steps
     and the stage times of the last one."""
@@ -383,7 +452,7 @@ def run_ours(args, rank, local_rank, world):
     n_req = args.images or wl["n"]
     files, file_ids = load_images(n_req, rank, world, args.config, args.scaling, with_ids=True)
     n = len(files)
-    arena = hjd.PinnedArena(files)
+    arena = hjd.PinnedArena(files, device=local_rank)       # pinned pages from the NUMA node next to this GPU, if any
     dec = hjd.BatchDecoder(local_rank)
     dec.upload_arena(arena)
     dec.sync()
@@ -442,7 +511,7 @@ def run_ours(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         need = hjd.rgb_slab_bytes(arena)
-        out_ptr = hjd.lib().hjd_host_alloc(need)
+        out_ptr = hjd.lib().hjd_host_alloc_near(local_rank, need)
         if not out_ptr:
             raise RuntimeError("pinned output allocation failed")
         dec.set_overlap(1)
@@ -461,6 +530,21 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(io, op=dist.ReduceOp.SUM)          # whole job, like the value
         e2e = {"value": round(job_pixels / 1e6 * args.e2e_steps / float(t_e.item()), 1), "unit": "MP/s",
                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()), "steps": args.e2e_steps}
+        # the ceiling of this host link: the same bytes, the same pinned buffers, all ranks at once, NO kernels
+        barrier()
+        ms_up, ms_down = hjd.link_probe(local_rank, arena.ptr, arena.bytes, out_ptr, need, reps=max(args.e2e_steps, 2))
+        barrier()
+        t_l = torch.tensor([max(ms_up, ms_down)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
+        t_link = float(t_l.item()) / 1e3
+        e2e["link_ceiling"] = {"value": round(job_pixels / 1e6 / t_link, 1), "unit": "MP/s",
+                               "d2h_GB_per_s": round(e2e["d2h_bytes_per_step"] / t_link / 1e9, 2),
+                               "h2d_GB_per_s": round(e2e["h2d_bytes_per_step"] / t_link / 1e9, 2),
+                               "numa_node_rank0": hjd.lib().hjd_device_numa_node(local_rank),
+                               "how": "hjd_link_probe: per rank, this step's H2D and D2H bytes copied concurrently between the same "
+                                      "pinned buffers and HBM with no kernel running, all ranks at once, max over ranks"}
+        e2e["frac_of_link_ceiling"] = round(e2e["value"] / e2e["link_ceiling"]["value"], 4)
         hjd.lib().hjd_host_free(out_ptr)
 
     # sub-records after the timed regions: parity of the timed batch, then the other BASELINE.json configs
@@ -470,6 +554,9 @@ def run_ours(args, rank, local_rank, world):
         extras["parity"] = parity_block(hjd, dist, dec, files, file_ids, rank, world, args.parity_images)
         dec.close()
         arena.close()
+        if rank == 0:
+            extras["file_to_bmp"] = file_to_bmp_record(hjd, files, local_rank, rank, with_reference=(world == 1 and not args.no_cpu_baseline))
+        barrier()
         strong = sub_record(hjd, dist, barrier, local_rank, rank, world, "c2", "strong", args.extra_steps, peak0)
         # every rank of the weak headline decoded the whole 1024-image batch on one GPU: its step time is t(1)
         strong["efficiency_vs_1gpu"] = round((ms_max / args.steps) / (world * strong["ms_per_step"]), 4)

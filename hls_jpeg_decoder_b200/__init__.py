@@ -23,7 +23,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 
 import numpy as np
 
-__all__ = ["probe", "ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
+__all__ = ["probe", "MultiDecoder", "shard_range_c", "ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
            "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU", "FLAG_BMP_OUT"]
 
@@ -118,7 +118,22 @@ _SIGS = {
     "hjd_rgb_slab_bytes": (c_uint64, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int]),
     "hjd_host_alloc": (c_void_p, [c_size_t]),
     "hjd_host_free": (None, [c_void_p]),
+    "hjd_host_alloc_near": (c_void_p, [c_int, c_size_t]),
+    "hjd_device_numa_node": (c_int, [c_int]),
+    "hjd_link_probe": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_int, POINTER(c_float), POINTER(c_float)]),
     "hjd_get_idct_tables": (None, [c_void_p, c_void_p]),
+    "hjd_decode_jpg_file_data_alloc": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_void_p), POINTER(c_uint), POINTER(c_uint)]),
+    "hjd_set_default_device": (c_int, [c_int]),
+    "hjd_convert_jpg_files_multi": (c_int, [POINTER(c_char_p), POINTER(c_char_p), c_int, POINTER(c_int), c_int, c_int, c_int, POINTER(c_int)]),
+    "hjd_shard_range": (c_int, [POINTER(c_int64), c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "hjd_multi_create": (c_void_p, [POINTER(c_int), c_int, c_uint]),
+    "hjd_multi_destroy": (None, [c_void_p]),
+    "hjd_multi_num_devices": (c_int, [c_void_p]),
+    "hjd_multi_batch": (c_void_p, [c_void_p, c_int]),
+    "hjd_multi_last_error": (c_char_p, [c_void_p]),
+    "hjd_multi_out_slab_bytes": (c_uint64, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int]),
+    "hjd_multi_decode_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_void_p, c_uint64,
+                                      POINTER(c_uint64), c_void_p]),
     "hjd_probe_jpeg": (c_int, [c_void_p, c_int64, POINTER(ImageInfo)]),
     "hjd_huff_lookup_probe": (c_uint32, [c_void_p, c_void_p, c_int, c_int, c_uint32]),
 }
@@ -157,15 +172,18 @@ def ConvertJpgFile(szJpgFileInName: str, szBmpFileOutName: str) -> int:
     return int(lib().hjd_convert_jpg_file(os.fsencode(szJpgFileInName), os.fsencode(szBmpFileOutName)))
 
 
-def ConvertJpgFiles(jpg_in: list[str], bmp_out: list[str], device: int = 0, threads: int = 0) -> list[int]:
-    """ConvertJpgFile at batch scale: one batched decode, parallel file readers / BMP writers.
+def ConvertJpgFiles(jpg_in: list[str], bmp_out: list[str], device: int = 0, threads: int = 0,
+                    devices: list[int] | None = None, chunk_images: int = 0) -> list[int]:
+    """ConvertJpgFile at batch scale: a pipeline of parallel file readers, chunked GPU decodes that write
+    the BMP file layout, and parallel file writers, on one device or a list of them.
     Returns the per-file 1/0 flags."""
     n = len(jpg_in)
     assert len(bmp_out) == n
     a = (c_char_p * n)(*[os.fsencode(p) for p in jpg_in])
     b = (c_char_p * n)(*[os.fsencode(p) for p in bmp_out])
     ok = (c_int * n)()
-    lib().hjd_convert_jpg_files(a, b, n, device, threads, ok)
+    devs = list(devices) if devices else [device]
+    lib().hjd_convert_jpg_files_multi(a, b, n, (c_int * len(devs))(*devs), len(devs), threads, chunk_images, ok)
     return list(ok)
 
 
@@ -225,7 +243,7 @@ def encode_bmp24(rgb: np.ndarray) -> bytes:
 class PinnedArena:
     """Files packed back to back (16-byte aligned) in pinned host memory."""
 
-    def __init__(self, files: list[bytes]):
+    def __init__(self, files: list[bytes], device: int | None = None):
         L = lib()
         self.n = len(files)
         self.sizes = (c_int64 * self.n)(*[len(f) for f in files])
@@ -235,7 +253,7 @@ class PinnedArena:
             o += (len(f) + 15) // 16 * 16
         self.offsets = (c_int64 * self.n)(*offs)
         self.bytes = max(o, 16)
-        self.ptr = L.hjd_host_alloc(self.bytes)
+        self.ptr = L.hjd_host_alloc(self.bytes) if device is None else L.hjd_host_alloc_near(device, self.bytes)
         if not self.ptr:
             raise HjdError(f"pinned allocation of {self.bytes} bytes failed: {_err()}")
         self.view = np.ctypeslib.as_array(ctypes.cast(self.ptr, POINTER(c_uint8)), shape=(self.bytes,))
@@ -439,6 +457,66 @@ class BatchDecoder:
                                            rgb_out_ptr, rgb_capacity, offs, status.ctypes.data, chunk_images),
                "hjd_batch_decode_host")
         return np.frombuffer(offs, dtype=np.uint64).copy(), status[:arena.n]
+
+
+class MultiDecoder:
+    """Several GPUs in one process (hjd_multi_*): one batch handle and one host thread per device, the batch
+    cut into contiguous image ranges balanced by compressed bytes; no exchange between the devices."""
+
+    def __init__(self, devices: list[int] | None = None, flags: int = 0):
+        devs = list(range(lib().hjd_device_count())) if devices is None else list(devices)
+        if not devs:
+            raise HjdError("no CUDA device available (this library has no CPU fallback)")
+        self.devices = devs
+        self._h = lib().hjd_multi_create((c_int * len(devs))(*devs), len(devs), flags)
+        if not self._h:
+            raise HjdError(f"hjd_multi_create failed: {_err()}")
+
+    def close(self):
+        if self._h:
+            lib().hjd_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def out_slab_bytes(self, arena: "PinnedArena") -> int:
+        return int(lib().hjd_multi_out_slab_bytes(self._h, arena.ptr, arena.offsets, arena.sizes, arena.n))
+
+    def decode_host(self, arena: "PinnedArena", rgb_out_ptr: int, rgb_capacity: int):
+        """Host buffers in, host buffers out, all devices at once.  Returns (offsets, status)."""
+        offs = (c_uint64 * arena.n)()
+        status = np.zeros(max(arena.n, 1), dtype=np.int32)
+        rc = lib().hjd_multi_decode_host(self._h, arena.ptr, arena.offsets, arena.sizes, arena.n, rgb_out_ptr,
+                                         rgb_capacity, offs, status.ctypes.data)
+        if rc != 0:
+            raise HjdError(f"hjd_multi_decode_host failed ({rc}): {lib().hjd_multi_last_error(self._h).decode(errors='replace')}")
+        return np.frombuffer(offs, dtype=np.uint64).copy(), status[:arena.n]
+
+
+def shard_range_c(sizes: list[int], rank: int, world: int) -> tuple[int, int]:
+    """The library's own sharding rule (hjd_shard_range); same result as sharding.shard_range."""
+    n = len(sizes)
+    lo, hi = c_int(), c_int()
+    _check(lib().hjd_shard_range((c_int64 * max(n, 1))(*sizes), n, rank, world, ctypes.byref(lo), ctypes.byref(hi)), "hjd_shard_range")
+    return lo.value, hi.value
+
+
+def link_probe(device: int, host_in_ptr: int, h2d_bytes: int, host_out_ptr: int, d2h_bytes: int, reps: int = 3):
+    """(ms_h2d, ms_d2h) per repetition of concurrent pinned copies with no kernels (hjd_link_probe)."""
+    a, b = c_float(), c_float()
+    _check(lib().hjd_link_probe(device, host_in_ptr, h2d_bytes, host_out_ptr, d2h_bytes, reps, ctypes.byref(a), ctypes.byref(b)),
+           "hjd_link_probe")
+    return a.value, b.value
 
 
 def rgb_slab_bytes(arena: PinnedArena) -> int:

@@ -14,6 +14,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -68,7 +70,7 @@ struct PinBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 4096;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -143,7 +145,7 @@ struct hjd_batch {
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_blast, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
-    PinBuf h_meta;
+    PinBuf h_meta, h_out;                       // h_out: staging of the single-image calls
 };
 
 // Bytes of one image's region in the output slab: tightly packed RGB24, or (HJD_FLAG_BMP_OUT) the BMP file
@@ -201,6 +203,13 @@ extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        // The IDCT reads only the 32-byte sectors of a block that hold coefficients: let the L2 fetch exactly
+        // those from HBM instead of whole 128-byte lines (a hint; HJD_L2_FETCH=64|128 restores coarser fetches).
+        size_t gran = 32;
+        if (const char* env = getenv("HJD_L2_FETCH")) gran = (size_t)atoi(env);
+        if (gran == 32 || gran == 64 || gran == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
+    }
     if (e == cudaSuccess) e = hjd_kernels_init_device();            // function attributes are per device
     if (e == cudaSuccess) e = hjd_mcu_rgb_init_device();
     if (e == cudaSuccess) e = hjd_selfsync_init_device(&b->max_sync_ctas);
@@ -227,7 +236,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     b->d_ss.release(); b->d_sswork.release(); b->d_sssegs.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
     b->d_flag.release();
-    b->h_meta.release();
+    b->h_meta.release(); b->h_out.release();
     for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     for (int i = 0; i < HJD_MARK_SLOTS; i++) if (b->mark[i]) cudaEventDestroy(b->mark[i]);
     for (int i = 0; i < HJD_NSTREAMS; i++) { if (b->aux[i]) { cudaStreamSynchronize(b->aux[i]); cudaStreamDestroy(b->aux[i]); } if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]); }
@@ -1122,10 +1131,97 @@ extern "C" int hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const i
     return HJD_OK;
 }
 
+// NUMA node of a GPU (from sysfs via its PCI address), -1 when the platform does not say.
+static int device_numa_node(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* fp = fopen(path, "r");
+    if (!fp) return -1;
+    int node = -1;
+    if (fscanf(fp, "%d", &node) != 1) node = -1;
+    fclose(fp);
+    return node;
+}
+
+extern "C" int hjd_device_numa_node(int device) { return device_numa_node(device); }
+
+// Pinned host memory whose pages come from the NUMA node next to `device` (set_mempolicy(MPOL_PREFERRED)
+// around the allocation: cudaHostAlloc faults the pages in on the calling thread).  The D2H copy of a
+// decoded batch is the end-to-end bottleneck, and a buffer on the far socket halves it on two-socket
+// hosts.  Falls back to plain hjd_host_alloc when the platform exposes no NUMA topology.
+extern "C" void* hjd_host_alloc_near(int device, size_t bytes)
+{
+    const int node = device_numa_node(device);
+    bool bound = false;
+#ifdef SYS_set_mempolicy
+    if (node >= 0 && node < 1024) {
+        unsigned long mask[16];
+        memset(mask, 0, sizeof mask);
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof mask * 8)) == 0;
+    }
+#endif
+    void* p = hjd_host_alloc(bytes);
+#ifdef SYS_set_mempolicy
+    if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+    (void)bound;
+    return p;
+}
+
+// Raw link probe: `reps` times, concurrently on two streams and with no kernel anywhere, h2d_bytes from
+// host_in to the device and d2h_bytes from the device to host_out (both pinned).  *ms = wall time of the
+// slower direction per repetition.  This is the ceiling hjd_batch_decode_host works against.
+extern "C" int hjd_link_probe(int device, const void* host_in, size_t h2d_bytes, void* host_out, size_t d2h_bytes,
+                              int reps, float* ms_h2d, float* ms_d2h)
+{
+    if (reps <= 0) return fail(HJD_ERR_ARG, "hjd_link_probe", "bad arguments");
+    CU(cudaSetDevice(device));
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = HJD_OK;
+    auto cleanup = [&]() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& q : s) if (q) cudaStreamDestroy(q);
+        if (d_in) cudaFree(d_in);
+        if (d_out) cudaFree(d_out);
+    };
+    cudaError_t e = cudaSuccess;
+    if (h2d_bytes && host_in) e = cudaMalloc(&d_in, h2d_bytes);
+    if (e == cudaSuccess && d2h_bytes && host_out) e = cudaMalloc(&d_out, d2h_bytes);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&ev[k]);
+    if (e == cudaSuccess && d_out) e = cudaMemset(d_out, 0x5a, d2h_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) {
+        cudaEventRecord(ev[0], s[0]); cudaEventRecord(ev[2], s[1]);
+        for (int r = 0; r < reps; r++) {
+            if (d_in) cudaMemcpyAsync(d_in, host_in, h2d_bytes, cudaMemcpyHostToDevice, s[0]);
+            if (d_out) cudaMemcpyAsync(host_out, d_out, d2h_bytes, cudaMemcpyDeviceToHost, s[1]);
+        }
+        cudaEventRecord(ev[1], s[0]); cudaEventRecord(ev[3], s[1]);
+        e = cudaStreamSynchronize(s[0]);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s[1]);
+        float a = 0.f, b = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&a, ev[0], ev[1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&b, ev[2], ev[3]);
+        if (ms_h2d) *ms_h2d = a / (float)reps;
+        if (ms_d2h) *ms_d2h = b / (float)reps;
+    }
+    if (e != cudaSuccess) rc = fail(HJD_ERR_CUDA, "hjd_link_probe", cudaGetErrorString(e));
+    cleanup();
+    return rc;
+}
+
 extern "C" void* hjd_host_alloc(size_t bytes)
 {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); fail(HJD_ERR_NOMEM, "cudaHostAlloc"); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); fail(HJD_ERR_NOMEM, "cudaHostAlloc"); return nullptr; }
     return p;
 }
 extern "C" void hjd_host_free(void* p) { if (p) cudaFreeHost(p); }
@@ -1134,15 +1230,27 @@ extern "C" void hjd_host_free(void* p) { if (p) cudaFreeHost(p); }
 // reference-shaped single-image calls
 // ------------------------------------------------------------------------------------------
 struct DefaultBatch {
-    hjd_batch* b = nullptr;
-    ~DefaultBatch() { if (b) hjd_batch_destroy(b); }
+    hjd_batch* b[2] = {nullptr, nullptr};      // [0] RGB out (DecodeJpgFileData), [1] BMP out (ConvertJpgFile)
+    int device[2] = {-1, -1};
+    ~DefaultBatch() { for (int k = 0; k < 2; k++) if (b[k]) hjd_batch_destroy(b[k]); }
 };
 static thread_local DefaultBatch g_default;
+static std::atomic<int> g_default_device(0);
 
-static hjd_batch* default_batch()
+extern "C" int hjd_set_default_device(int device)
 {
-    if (!g_default.b) g_default.b = hjd_batch_create(0, 0);
-    return g_default.b;
+    if (device < 0 || device >= hjd_device_count()) return fail(HJD_ERR_ARG, "hjd_set_default_device", "bad device index");
+    g_default_device.store(device);
+    return HJD_OK;
+}
+
+// The lazily created per-thread batch behind the single-image calls, on the process-wide default device.
+static hjd_batch* default_batch(bool bmp)
+{
+    const int k = bmp ? 1 : 0, dev = g_default_device.load();
+    if (g_default.b[k] && g_default.device[k] != dev) { hjd_batch_destroy(g_default.b[k]); g_default.b[k] = nullptr; }
+    if (!g_default.b[k]) { g_default.b[k] = hjd_batch_create(dev, bmp ? HJD_FLAG_BMP_OUT : 0); g_default.device[k] = dev; }
+    return g_default.b[k];
 }
 
 extern "C" void hjd_free(void* p) { free(p); }
@@ -1205,26 +1313,44 @@ extern "C" uint32_t hjd_huff_lookup_probe(const uint8_t bits[16], const uint8_t*
     return hjd_host_huff_lookup(&tab, peek16);
 }
 
-extern "C" int hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsigned* width, unsigned* height)
+// One image through a default batch; the result (RGB24, or the BMP file) is downloaded into memory from
+// alloc(bytes).  The staging is the batch's own pinned buffer: one asynchronous copy, one host copy.
+static int decode_one(bool bmp, const uint8_t* buf, int size, void* (*alloc)(size_t), uint8_t** out_ptr, size_t* out_bytes,
+                      unsigned* width, unsigned* height, const char* who)
 {
-    if (!buf || size <= 0 || !rgb) { fail(HJD_ERR_ARG, "hjd_decode_jpg_file_data", "bad arguments"); return 0; }
-    *rgb = nullptr;
-    hjd_batch* b = default_batch();
+    if (!buf || size <= 0 || !out_ptr || !alloc) { fail(HJD_ERR_ARG, who, "bad arguments"); return 0; }
+    *out_ptr = nullptr;
+    hjd_batch* b = default_batch(bmp);
     if (!b) return 0;
     const uint8_t* bufs[1] = {buf};
     const int64_t sizes[1] = {size};
     if (hjd_batch_upload(b, bufs, sizes, 1) != HJD_OK) return 0;
-    if (b->parse_status[0] != HJD_IMG_OK) { fail(HJD_ERR_ARG, "hjd_decode_jpg_file_data", "unsupported or corrupt JPEG"); return 0; }
+    if (b->parse_status[0] != HJD_IMG_OK) { fail(HJD_ERR_ARG, who, "unsupported or corrupt JPEG"); return 0; }
     if (hjd_batch_decode(b) != HJD_OK) return 0;
     const HjdImageDesc& d = b->imgs[0];
-    const size_t bytes = (size_t)d.width * d.height * 3;
-    uint8_t* out = (uint8_t*)malloc(bytes ? bytes : 1);
-    if (!out) { fail(HJD_ERR_NOMEM, "malloc"); return 0; }
-    if (hjd_batch_download_image(b, 0, out) != HJD_OK) { free(out); return 0; }
-    *rgb = out;
+    const size_t bytes = bmp ? (size_t)hjd_batch_bmp_bytes(b, 0) : (size_t)d.width * d.height * 3;
+    if (cudaSetDevice(b->device) != cudaSuccess || b->h_out.ensure(bytes + 16) != cudaSuccess) { cudaGetLastError(); fail(HJD_ERR_NOMEM, who, "pinned staging buffer"); return 0; }
+    if (cudaMemcpyAsync(b->h_out.p, (const uint8_t*)b->d_rgb.p + d.rgb_off + (bmp ? 10 : 0), bytes, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
+        cudaStreamSynchronize(b->stream) != cudaSuccess) { fail(HJD_ERR_CUDA, who, cudaGetErrorString(cudaGetLastError())); return 0; }
+    uint8_t* out = (uint8_t*)alloc(bytes ? bytes : 1);
+    if (!out) { fail(HJD_ERR_NOMEM, who, "allocation failed"); return 0; }
+    memcpy(out, b->h_out.p, bytes);
+    *out_ptr = out;
+    if (out_bytes) *out_bytes = bytes;
     if (width) *width = d.width;
     if (height) *height = d.height;
     return 1;
+}
+
+extern "C" int hjd_decode_jpg_file_data_alloc(const uint8_t* buf, int size, void* (*alloc)(size_t), uint8_t** rgb,
+                                              unsigned* width, unsigned* height)
+{
+    return decode_one(false, buf, size, alloc, rgb, nullptr, width, height, "hjd_decode_jpg_file_data");
+}
+
+extern "C" int hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsigned* width, unsigned* height)
+{
+    return decode_one(false, buf, size, malloc, rgb, nullptr, width, height, "hjd_decode_jpg_file_data");
 }
 
 extern "C" size_t hjd_encode_bmp24(unsigned width, unsigned height, const uint8_t* rgb, uint8_t* out)
@@ -1270,7 +1396,8 @@ extern "C" int hjd_write_bmp24(const char* path, unsigned width, unsigned height
 
 extern "C" int hjd_convert_jpg_file(const char* jpg_in, const char* bmp_out)
 {
-    // ConvertJpgFile, openjpg.cpp:593-684: returns 1 on success, 0 on failure.
+    // ConvertJpgFile, openjpg.cpp:593-684: returns 1 on success, 0 on failure.  The decode runs with
+    // HJD_FLAG_BMP_OUT: what comes back from the GPU is the file WriteBMP24 would write.
     if (!jpg_in || !bmp_out) { fail(HJD_ERR_ARG, "hjd_convert_jpg_file", "bad arguments"); return 0; }
     FILE* fp = fopen(jpg_in, "rb");
     if (!fp) { fail(HJD_ERR_IO, "fopen", jpg_in); return 0; }          // openjpg.cpp:603-608
@@ -1282,87 +1409,16 @@ extern "C" int hjd_convert_jpg_file(const char* jpg_in, const char* bmp_out)
     if (!buf) { fclose(fp); fail(HJD_ERR_NOMEM, "malloc"); return 0; }
     const size_t got = fread(buf, 1, (size_t)len, fp);
     fclose(fp);
-    uint8_t* rgb = nullptr;
-    unsigned w = 0, h = 0;
-    int ok = (got == (size_t)len) && hjd_decode_jpg_file_data(buf, (int)len, &rgb, &w, &h);
+    uint8_t* bmp = nullptr;
+    size_t bytes = 0;
+    int ok = (got == (size_t)len) && decode_one(true, buf, (int)len, malloc, &bmp, &bytes, nullptr, nullptr, "hjd_convert_jpg_file");
     free(buf);
     if (!ok) return 0;
-    ok = hjd_write_bmp24(bmp_out, w, h, rgb);
-    hjd_free(rgb);
+    fp = fopen(bmp_out, "wb");
+    if (!fp) { free(bmp); fail(HJD_ERR_IO, "fopen", bmp_out); return 0; }
+    ok = fwrite(bmp, 1, bytes, fp) == bytes;
+    if (fclose(fp) != 0) ok = 0;
+    free(bmp);
+    if (!ok) fail(HJD_ERR_IO, "fwrite", bmp_out);
     return ok;
-}
-
-// ------------------------------------------------------------------------------------------
-// batch-scale ConvertJpgFile: batched loader + one decode + parallel BMP writers
-// ------------------------------------------------------------------------------------------
-extern "C" int hjd_convert_jpg_files(const char* const* jpg_in, const char* const* bmp_out, int n, int device,
-                                     int threads, int* ok)
-{
-    if (!jpg_in || !bmp_out || n < 0) { fail(HJD_ERR_ARG, "hjd_convert_jpg_files", "bad arguments"); return 0; }
-    if (ok) for (int i = 0; i < n; i++) ok[i] = 0;
-    if (n == 0) return 0;
-    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
-    if (threads <= 0) threads = 1;
-    if (threads > n) threads = n;
-
-    // 1. sizes, then all files into one pinned arena (the batched counterpart of openjpg.cpp:603-619)
-    std::vector<int64_t> sizes((size_t)n, 0), offsets((size_t)n, 0);
-    int64_t total = 0;
-    for (int i = 0; i < n; i++) {
-        FILE* fp = jpg_in[i] ? fopen(jpg_in[i], "rb") : nullptr;
-        if (fp) { fseek(fp, 0, SEEK_END); long len = ftell(fp); fclose(fp); if (len > 0) sizes[i] = len; }
-        offsets[i] = total;
-        total += (int64_t)align_up((uint64_t)sizes[i], 16);
-    }
-    uint8_t* arena = (uint8_t*)hjd_host_alloc((size_t)total + 16);
-    if (!arena) return 0;
-    {
-        std::atomic<int> next(0);
-        auto reader = [&]() {
-            for (int i = next++; i < n; i = next++) {
-                if (!sizes[i]) continue;
-                FILE* fp = fopen(jpg_in[i], "rb");
-                size_t got = fp ? fread(arena + offsets[i], 1, (size_t)sizes[i], fp) : 0;
-                if (fp) fclose(fp);
-                if (got != (size_t)sizes[i]) sizes[i] = 0;
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; t++) pool.emplace_back(reader);
-        for (auto& th : pool) th.join();
-    }
-
-    // 2. one batch decode with host buffers
-    int converted = 0;
-    hjd_batch* b = hjd_batch_create(device, 0);
-    uint8_t* rgb = nullptr;
-    std::vector<uint64_t> rgb_off((size_t)n, 0);
-    std::vector<int32_t> status((size_t)n, 0);
-    if (b) {
-        const uint64_t need = hjd_rgb_slab_bytes(arena, offsets.data(), sizes.data(), n);
-        rgb = (uint8_t*)hjd_host_alloc((size_t)need + 16);
-        if (rgb && hjd_batch_decode_host(b, arena, offsets.data(), sizes.data(), n, rgb, need, rgb_off.data(),
-                                         status.data(), 0) == HJD_OK) {
-            // 3. BMP encode + write in parallel (openjpg.cpp:504-570 layout)
-            std::atomic<int> next(0), done(0);
-            auto writer = [&]() {
-                for (int i = next++; i < n; i = next++) {
-                    if (status[i] < 0 || !bmp_out[i]) continue;          // rejected by the parser
-                    const HjdImageDesc& d = b->imgs[i];
-                    if (hjd_write_bmp24(bmp_out[i], d.width, d.height, rgb + rgb_off[i])) {
-                        if (ok) ok[i] = 1;
-                        done++;
-                    }
-                }
-            };
-            std::vector<std::thread> pool;
-            for (int t = 0; t < threads; t++) pool.emplace_back(writer);
-            for (auto& th : pool) th.join();
-            converted = done.load();
-        }
-        hjd_batch_destroy(b);
-    }
-    if (rgb) hjd_host_free(rgb);
-    hjd_host_free(arena);
-    return converted;
 }

@@ -458,7 +458,9 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                         hjd_sts_zero16_sync(src);
                         ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
                     }
+#ifndef HJD_TUNE_NO_BLAST
                     if (chunk == 0) blk_last[ent.x] = (uint8_t)last;
+#endif
                 }
             }
             __syncwarp();
@@ -538,7 +540,7 @@ __host__ __device__ constexpr int hjd_km_of_class(int cls) { return cls == 0 ? 9
 
 // q: HjdQuantSet::qp (byte-packed pairs).  Dequantise one block held as 8 x uint4 (zig-zag order) into
 // bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)), stored as row pairs: bp2[(v>>1)*8+u] = (bp[8v+u], bp[8(v+1)+u]), v even.
-// Only zig-zag positions <= KM are touched (the others are zero and never read).
+// Only zig-zag positions <= KM are computed; the others are zero by the block's length and are set to zero.
 // Returns A_ac = sum over AC terms of |bp| ; *a_dc = |bp[0]|.
 template <int KM>
 __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4 q[8], float2 bp2[32], float* a_dc)
@@ -548,7 +550,10 @@ __device__ __forceinline__ float hjd_dequant_block(const uint4 c[8], const uint4
     const uint32_t* qw = (const uint32_t*)q;
     float a_ac = 0.f;
 #define HJD_DQ(P, N)                                                                           \
-    if ((P) <= KM) {                                                                           \
+    if ((P) > KM) {                                                                            \
+        if (((N) >> 3) & 1) bp2[((N) >> 4) * 8 + ((N) & 7)].y = 0.f;                            \
+        else                bp2[((N) >> 4) * 8 + ((N) & 7)].x = 0.f;                            \
+    } else {                                                                                   \
         /* coef*q straight from the packed pair (loadjpg.cpp:150; the product is exact) */      \
         const int prod = ((P) & 1) ? hjd_dp2a_hi_su(cw[(P) >> 1], qw[(P) >> 1])                \
                                    : hjd_dp2a_lo_su(cw[(P) >> 1], qw[(P) >> 1]);               \
@@ -582,20 +587,16 @@ __device__ __forceinline__ uint32_t hjd_pack_sat_u8(int a, int b, uint32_t c)
     return d;
 }
 
-// Exact re-evaluation of sample (x, y) in the reference's order.  tx/ty: rows of the cos table.  Terms of
-// frequencies beyond KM are zero: adding them would not change the sum, so they are left out.
-template <int KM>
+// Exact re-evaluation of sample (x, y) in the reference's order.  tx/ty: rows of the cos table.
 __device__ __forceinline__ float hjd_exact_sum(const float2 bp2[32], const float* tx, const float* ty)
 {
-    constexpr uint64_t LIVE = hjd_live_mask(KM);
     float sum = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
         const float cxu = tx[u];
 #pragma unroll
         for (int v = 0; v < 8; v++)
-            if ((LIVE >> (8 * v + u)) & 1)
-                sum = __fadd_rn(sum, __fmul_rn(__fmul_rn((v & 1) ? bp2[(v >> 1) * 8 + u].y : bp2[(v >> 1) * 8 + u].x, cxu), ty[v]));
+            sum = __fadd_rn(sum, __fmul_rn(__fmul_rn((v & 1) ? bp2[(v >> 1) * 8 + u].y : bp2[(v >> 1) * 8 + u].x, cxu), ty[v]));
     }
     return sum;
 }
@@ -613,63 +614,67 @@ __device__ __forceinline__ void hjd_ldg256_nc(const uint4* p, uint4& a, uint4& b
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
-// One 8x8 block that ends at zig-zag index `last` <= KM: dequantise, IDCT, +128, clamp; rows go to
+// Pass 1 of one output column x for the frequencies that variant KM keeps:
+//   r[vp] = (r[2vp][x], r[2vp+1][x]),  r[v][x] = sum_u bp[8v+u] * cos[x][u],  u over the live columns of row pair vp.
+// The dead entries of bp2 hold zeros (the dequantisation step cleared them), so leaving them out changes nothing.
+template <int KM, int X>
+__device__ __forceinline__ void hjd_pass1_column(const float2 bp2[32], float2 r[4])
+{
+    constexpr uint64_t L = hjd_live_mask(KM);
+#pragma unroll
+    for (int vp = 0; vp < 4; vp++) {
+        float2 acc = bp2[vp * 8];                  // cos[x][0] == 1
+#pragma unroll
+        for (int u = 1; u < 8; u++)
+            if (((L >> (16 * vp + u)) | (L >> (16 * vp + 8 + u))) & 1)
+                acc = __ffma2_rn(bp2[vp * 8 + u], c_cos2[X * 8 + u], acc);
+        r[vp] = acc;
+    }
+}
+
+// One 8x8 block that ends at zig-zag index `last`: dequantise, IDCT, +128, clamp; rows go to
 // dst[y*pitch + 0..7] (planes in HBM for the unfused kernel, a shared-memory tile for the fused one).
 // s_cos: the cos table in shared memory (the exact re-evaluation indexes it dynamically).
-template <int KM>
-__device__ __forceinline__ void hjd_idct_block_km(const uint4* __restrict__ cp, const uint4* __restrict__ qp,
-                                                  const float* s_cos, uint8_t* dst, uint32_t pitch, uint32_t last)
+// cls (WARP-UNIFORM: the class of the longest block among the lanes that are here together) selects how
+// much of the dequantisation and of pass 1 is executed: 0/1 -> KM 20, 2 -> KM 35, 3 -> everything.
+// The variants are arms of small switches inside ONE body -- pass 2, the epilogue and the exact path are
+// shared -- because the whole kernel has to stay around the 32 KB of the instruction cache: four complete
+// copies of this routine (one per class) executed 17 % fewer instructions and ran 45 % SLOWER, with
+// "no instruction" as the top stall reason (ncu, profiles/r2_*).
+__device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, const uint4* __restrict__ qp,
+                                               const float* s_cos, uint8_t* dst, uint32_t pitch, uint32_t last, int cls)
 {
-    constexpr uint64_t LIVE = hjd_live_mask(KM);
-    constexpr int NSEC = (KM >> 4) + 1;             // 32-byte sectors this variant can need
     // 256-bit loads (sm_100 LDG.256): one per 32-byte sector, and only the sectors the entropy kernel wrote
-    // (the rest of the 128-byte slot holds whatever an earlier batch left there)
-    // A sector beyond the block's end is read from a zero sector instead (an address select, not a
-    // predicated load: the loads stay unconditional and the registers are written exactly once).
+    // (the rest of the 128-byte slot holds whatever an earlier batch left there): a sector beyond the
+    // block's end is read from a zero sector instead (an address select, not a predicated load).
     uint4 c[8], q[8];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        if (i < NSEC) {
-            const uint4* src = (uint32_t)i <= (last >> 4) ? cp + 2 * i : g_zero_sector;
-            hjd_ldg256(src, c[2 * i], c[2 * i + 1]);
-            hjd_ldg256_nc(qp + 2 * i, q[2 * i], q[2 * i + 1]);
-        }
+        const uint4* src = (uint32_t)i <= (last >> 4) ? cp + 2 * i : g_zero_sector;
+        hjd_ldg256(src, c[2 * i], c[2 * i + 1]);
+        hjd_ldg256_nc(qp + 2 * i, q[2 * i], q[2 * i + 1]);
     }
 
     float2 bp2[32];
-    float a_dc;
-    const float a_ac = hjd_dequant_block<KM>(c, q, bp2, &a_dc);
+    float a_dc, a_ac;
+#ifndef HJD_IDCT_VARIANTS
+#define HJD_IDCT_VARIANTS 3
+#endif
+    if (HJD_IDCT_VARIANTS == 1) cls = 3;
+    if (HJD_IDCT_VARIANTS == 2 && cls == 2) cls = 3;
+    if (cls <= 1) {
+        a_ac = hjd_dequant_block<20>(c, q, bp2, &a_dc);
+    } else if (cls == 2) {
+        a_ac = hjd_dequant_block<35>(c, q, bp2, &a_dc);
+    } else {
+        a_ac = hjd_dequant_block<63>(c, q, bp2, &a_dc);
+    }
     // re-evaluation window on the 0.25*sum scale: 24 * 2^-24 * A; DC-only blocks are exact (no window)
     const float win = (a_ac == 0.f) ? -1.f : (a_ac + a_dc) * 1.430511474609375e-06f;
 
-    // Packed FP32x2 FMAs (Blackwell FFMA2) halve the issue slots of this issue-bound kernel.
-    // pass 1 (horizontal frequency u -> position x), two coefficient rows per instruction:
-    //   r2[vp*8+x] = (r[2vp][x], r[2vp+1][x]),  r[v][x] = sum_u bp[8v+u] * cos[x][u]
-    // A pair (row pair vp, frequency u) is live if either of its rows can hold that frequency; a half that
-    // is dead is a zero that was never written: bp2 is cleared where only one half is live.
-    float2 r2[32];
-#pragma unroll
-    for (int vp = 0; vp < 4; vp++) {
-        constexpr uint64_t L = LIVE;
-        const bool vp_live = ((L >> (16 * vp)) & 0xFFFFull) != 0;
-        if (!vp_live) continue;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {               // the half of a live pair that is beyond KM is zero
-            const bool lo = (L >> (16 * vp + u)) & 1, hi = (L >> (16 * vp + 8 + u)) & 1;
-            if (lo && !hi) bp2[vp * 8 + u].y = 0.f;
-            if (hi && !lo) bp2[vp * 8 + u].x = 0.f;
-        }
-#pragma unroll
-        for (int x = 0; x < 8; x++) {
-            float2 acc = bp2[vp * 8];              // cos[x][0] == 1; column 0 of a live row pair is live (zig-zag order)
-#pragma unroll
-            for (int u = 1; u < 8; u++)
-                if (((L >> (16 * vp + u)) | (L >> (16 * vp + 8 + u))) & 1)
-                    acc = __ffma2_rn(bp2[vp * 8 + u], c_cos2[x * 8 + u], acc);
-            r2[vp * 8 + x] = acc;
-        }
-    }
     const float2* cosp = (const float2*)c_cosq;    // cosp[y*4+vp] = 0.25 * (cos[y][2vp], cos[y][2vp+1])
+    // Packed FP32x2 FMAs (Blackwell FFMA2) halve the issue slots of this issue-bound kernel.  Column by column:
+    // pass 1 (horizontal frequency u -> position x) for two coefficient rows per instruction, then
     // pass 2 (vertical frequency v -> position y), pack rows, collect near-integer samples:
     // |h - rint(h)| <= win  <=  an integer (truncation boundary) lies within the error window of h;
     // everywhere else trunc(h) is provably the reference's value.
@@ -680,35 +685,45 @@ __device__ __forceinline__ void hjd_idct_block_km(const uint4* __restrict__ cp, 
 #pragma unroll
     for (int y = 0; y < 8; y++) { row_lo[y] = 0; row_hi[y] = 0; }
     uint32_t near_lo = 0, near_hi = 0;             // bit (8y + x)
-#pragma unroll
-    for (int xq = 0; xq < 4; xq++) {
-        const int xp = xq ^ 1;                     // pairs (2,3) (0,1) (6,7) (4,5): high half-word first
-#pragma unroll
-        for (int y = 0; y < 8; y++) {
-            int iv[2];
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int x = 2 * xp + e;
-                // pass 2: even and odd vertical frequencies accumulate in the two halves; the table
-                // carries the 0.25 (0.25 * fl(s) == fl(0.25 * s): scaling by a power of two commutes with rounding)
-                float2 a2 = __fmul2_rn(r2[x], cosp[y * 4]);          // 0.25 * (r[0][x] * 1, r[1][x] * cos[y][1])
-#pragma unroll
-                for (int vp = 1; vp < 4; vp++)
-                    if (((LIVE >> (16 * vp)) & 0xFFFFull) != 0) a2 = __ffma2_rn(r2[vp * 8 + x], cosp[y * 4 + vp], a2);
-                const float h = a2.x + a2.y;
-                // rint(h) as (h + 1.5*2^23) - 1.5*2^23 (|h| < 2^22 whenever the window is in use): two FADDs
-                // instead of an FRND, which runs on the conversion unit that this kernel loads as much as
-                // the FMA pipe (ncu: pipe_xu 56 %); 4.23 -> 4.08 ms
-                const float hr = __fadd_rn(__fadd_rn(h, 12582912.0f), -12582912.0f);
-                const bool nearint = fabsf(__fadd_rn(h, -hr)) <= win;
-                iv[e] = __float2int_rz(h);         // (int)(0.25*sum), loadjpg.cpp:123; the + 128 of :137 follows the packing
-                if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + x); }
-                else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + x); }
-            }
-            if (xp < 2) row_lo[y] = hjd_pack_sat_s8(iv[1], iv[0], row_lo[y]);
-            else        row_hi[y] = hjd_pack_sat_s8(iv[1], iv[0], row_hi[y]);
-        }
+#define HJD_COLUMN(X)                                                                                          \
+    {                                                                                                          \
+        float2 r[4];                                                                                           \
+        if (cls <= 1) hjd_pass1_column<20, X>(bp2, r);                                                         \
+        else if (cls == 2) hjd_pass1_column<35, X>(bp2, r);                                                    \
+        else hjd_pass1_column<63, X>(bp2, r);                                                                  \
+        _Pragma("unroll")                                                                                      \
+        for (int y = 0; y < 8; y++) {                                                                          \
+            /* pass 2: even and odd vertical frequencies accumulate in the two halves; the table carries the */ \
+            /* 0.25 (0.25 * fl(s) == fl(0.25 * s): scaling by a power of two commutes with rounding)         */ \
+            float2 a2 = __fmul2_rn(r[0], cosp[y * 4]);                                                         \
+            _Pragma("unroll")                                                                                  \
+            for (int vp = 1; vp < 4; vp++) a2 = __ffma2_rn(r[vp], cosp[y * 4 + vp], a2);                       \
+            const float h = a2.x + a2.y;                                                                       \
+            /* rint(h) as (h + 1.5*2^23) - 1.5*2^23 (|h| < 2^22 whenever the window is in use): two FADDs     */ \
+            /* instead of an FRND on the conversion unit (ncu: pipe_xu as loaded as the FMA pipe)            */ \
+            const float hr = __fadd_rn(__fadd_rn(h, 12582912.0f), -12582912.0f);                               \
+            const bool nearint = fabsf(__fadd_rn(h, -hr)) <= win;                                              \
+            iv[y][(X) & 1] = __float2int_rz(h);    /* (int)(0.25*sum), loadjpg.cpp:123 */                      \
+            if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + (X)); }                                        \
+            else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + (X)); }                                  \
+        }                                                                                                      \
     }
+#define HJD_PACK(XP)                                                                                           \
+    _Pragma("unroll")                                                                                          \
+    for (int y = 0; y < 8; y++) {                                                                              \
+        if ((XP) < 2) row_lo[y] = hjd_pack_sat_s8(iv[y][1], iv[y][0], row_lo[y]);                              \
+        else          row_hi[y] = hjd_pack_sat_s8(iv[y][1], iv[y][0], row_hi[y]);                              \
+    }
+    {
+        int iv[8][2];
+        // pairs (2,3) (0,1) (6,7) (4,5): high half-word first
+        HJD_COLUMN(2) HJD_COLUMN(3) HJD_PACK(1)
+        HJD_COLUMN(0) HJD_COLUMN(1) HJD_PACK(0)
+        HJD_COLUMN(6) HJD_COLUMN(7) HJD_PACK(3)
+        HJD_COLUMN(4) HJD_COLUMN(5) HJD_PACK(2)
+    }
+#undef HJD_COLUMN
+#undef HJD_PACK
     if (a_ac + a_dc >= 1.0e5f) { near_lo = 0xFFFFFFFFu; near_hi = 0xFFFFFFFFu; }
 
 #pragma unroll
@@ -721,21 +736,15 @@ __device__ __forceinline__ void hjd_idct_block_km(const uint4* __restrict__ cp, 
         if (near_lo) { pos = __ffs(near_lo) - 1; near_lo &= near_lo - 1; }
         else         { pos = 32 + __ffs(near_hi) - 1; near_hi &= near_hi - 1; }
         const int y = pos >> 3, x = pos & 7;
-        const float sum = hjd_exact_sum<KM>(bp2, s_cos + x * 8, s_cos + y * 8);
+        const float sum = hjd_exact_sum(bp2, s_cos + x * 8, s_cos + y * 8);
         dst[(size_t)y * pitch + x] = (uint8_t)hjd_finish_sample(sum);
     }
 }
 
-// The variant for the longest block among the lanes that are here together (warp-uniform choice: the
-// instruction stream is what binds).  `last`: this lane's own block end.
-__device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, const uint4* __restrict__ qp,
-                                               const float* s_cos, uint8_t* dst, uint32_t pitch, uint32_t last)
+// Warp-uniform class of the blocks that the lanes here hold (their last zig-zag indices).
+__device__ __forceinline__ int hjd_warp_class(uint32_t last)
 {
-    const uint32_t wmax = __reduce_max_sync(__activemask(), last);
-    if (wmax <= 9u)       hjd_idct_block_km<9>(cp, qp, s_cos, dst, pitch, last);
-    else if (wmax <= 20u) hjd_idct_block_km<20>(cp, qp, s_cos, dst, pitch, last);
-    else if (wmax <= 35u) hjd_idct_block_km<35>(cp, qp, s_cos, dst, pitch, last);
-    else                  hjd_idct_block_km<63>(cp, qp, s_cos, dst, pitch, last);
+    return hjd_class_of_last((int)__reduce_max_sync(__activemask(), last));
 }
 
 __global__ void __launch_bounds__(HJD_IDCT_THREADS, 4)
@@ -762,8 +771,9 @@ hjd_k_idct_planes(const int16_t* __restrict__ coef, const uint8_t* __restrict__ 
         comp = (bi == ny) ? 1 : 2; pitch = d->c_pitch; poff = comp == 1 ? d->cb_off : d->cr_off;
         bx = mx; by = my;
     }
+    const uint32_t last = blk_last[d->block_base + b];
     hjd_idct_block((const uint4*)(coef + (d->block_base + b) * 64), (const uint4*)(qsets[d->quant_set].qp[comp]),
-                   s_cos, planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8, pitch, blk_last[d->block_base + b]);
+                   s_cos, planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8, pitch, last, hjd_warp_class(last));
 }
 
 cudaError_t hjd_launch_idct_planes(const int16_t* coef, const uint8_t* blk_last, const HjdImageDesc* imgs,
@@ -1081,8 +1091,10 @@ __device__ __forceinline__ void hjd_mcu_phase_b(const HjdImageDesc* __restrict__
                         if ((uint32_t)i < npix * 3) dst[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
                 }
             }
-            if (BMP && last_col)
-                for (uint32_t q = 0; q < row_pad; q++) dst[npix * 3 + q] = 0;          // openjpg.cpp:563-567
+            if constexpr (BMP) {
+                if (last_col)
+                    for (uint32_t q = 0; q < row_pad; q++) dst[npix * 3 + q] = 0;      // openjpg.cpp:563-567
+            }
         }
     }
 }
@@ -1207,7 +1219,7 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const uint8_t* __restrict__ blk_
         const bool chroma = bi >= inf.ny;
         const uint32_t tile = chroma ? 4u + (bi - inf.ny) : bi;
         hjd_idct_block(inf.cp + bi * 8, (const uint4*)inf.qs->qp[chroma ? 1u + (bi - inf.ny) : 0u], s_cos,
-                       (uint8_t*)&s_tile[tile * 8 * T + mt], kPitch, last);
+                       (uint8_t*)&s_tile[tile * 8 * T + mt], kPitch, last, hjd_warp_class(last));
     }
     __syncthreads();
 

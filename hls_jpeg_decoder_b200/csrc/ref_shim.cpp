@@ -27,22 +27,14 @@ HJD_EXPORT int ConvertJpgFile(char* szJpgFileInName, char* szBmpFileOutName)
     return hjd_convert_jpg_file(szJpgFileInName, szBmpFileOutName);
 }
 
+static void* shim_new(size_t bytes) { return new unsigned char[bytes]; }     // "Don't forget to delete[] rgbpix"
+
 HJD_EXPORT int DecodeJpgFileData(const unsigned char* buf, int sizeBuf, unsigned char** rgbpix,
                                  unsigned int* width, unsigned int* height)
 {
-    unsigned char* tmp = nullptr;
-    unsigned w = 0, h = 0;
     if (!rgbpix) return 0;
-    *rgbpix = nullptr;
-    if (!hjd_decode_jpg_file_data(buf, sizeBuf, &tmp, &w, &h)) return 0;
-    const size_t bytes = (size_t)w * h * 3;
-    unsigned char* out = new unsigned char[bytes ? bytes : 1];   // "Don't forget to delete[] rgbpix"
-    memcpy(out, tmp, bytes);
-    hjd_free(tmp);
-    *rgbpix = out;
-    if (width) *width = w;
-    if (height) *height = h;
-    return 1;
+    // the library copies the result straight into memory from new[]: no intermediate buffer
+    return hjd_decode_jpg_file_data_alloc(buf, sizeBuf, shim_new, rgbpix, width, height);
 }
 
 HJD_EXPORT void WriteBMP24(const char* szBmpFileName, unsigned int Width, unsigned int Height, unsigned char* RGB)

@@ -108,6 +108,12 @@ int  hjd_convert_jpg_file(const char* jpg_in, const char* bmp_out);
 /* loadjpg.h:186 DecodeJpgFileData: *rgb is allocated by the library (release with hjd_free). */
 int  hjd_decode_jpg_file_data(const uint8_t* buf, int size, uint8_t** rgb, unsigned* width, unsigned* height);
 void hjd_free(void* p);
+/* Same, with the result allocated by the caller's allocator (the C++ shim passes operator new[], so that the
+ * reference's "delete[] rgbpix" contract holds without a second copy). */
+int  hjd_decode_jpg_file_data_alloc(const uint8_t* buf, int size, void* (*alloc)(size_t), uint8_t** rgb,
+                                    unsigned* width, unsigned* height);
+/* Device used by the reference-shaped single-image calls (a lazily created per-thread batch); default 0. */
+int  hjd_set_default_device(int device);
 /* loadjpg.h:183 JpegGetImageSize, from the file bytes (header parse only, no GPU). */
 int  hjd_get_image_size(const uint8_t* buf, int size, unsigned* width, unsigned* height);
 /* Header parse only (no GPU): the per-image status a batch would report for this file (HJD_IMG_OK or a
@@ -122,11 +128,15 @@ int  hjd_write_bmp24(const char* path, unsigned width, unsigned height, const ui
 /* Same bytes as hjd_write_bmp24 into memory; returns the BMP size (call with out = NULL to size it). */
 size_t hjd_encode_bmp24(unsigned width, unsigned height, const uint8_t* rgb, uint8_t* out);
 
-/* ConvertJpgFile at batch scale: read n .jpg files, decode them as one batch (chunked H2D / kernels /
- * D2H overlap), write n 24-bit .bmp files with `threads` host threads (0 = all cores).
- * ok[i] = 1 / 0 per file (may be NULL).  Returns the number of files converted. */
+/* ConvertJpgFile at batch scale, as a pipeline (openjpg.cpp:593-684 per file): `threads` readers fill a pinned
+ * arena; per device up to three workers decode one chunk of `chunk_images` images at a time with
+ * HJD_FLAG_BMP_OUT (the GPU writes the BMP file layout); `threads` writers fwrite every file as soon as its
+ * chunk has landed in pinned memory, while later chunks are being copied and decoded (0 = all cores / 32
+ * images).  ok[i] = 1 / 0 per file (may be NULL).  Returns the number of files converted. */
 int  hjd_convert_jpg_files(const char* const* jpg_in, const char* const* bmp_out, int n, int device,
                            int threads, int* ok);
+int  hjd_convert_jpg_files_multi(const char* const* jpg_in, const char* const* bmp_out, int n,
+                                 const int* devices, int n_devices, int threads, int chunk_images, int* ok);
 
 /* ---- batch API: the JpegDecodeHW replacement, N independent images per call -------------- */
 hjd_batch* hjd_batch_create(int device, unsigned flags);
@@ -205,9 +215,33 @@ int  hjd_batch_decode_host(hjd_batch* b, const uint8_t* arena, const int64_t* of
 uint64_t hjd_rgb_slab_bytes(const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n);
 uint64_t hjd_out_slab_bytes(const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n, unsigned flags);
 
-/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA binding. */
+/* ---- several GPUs in one process -------------------------------------------
+ * Images are independent and there is no exchange step: a batch is cut into one contiguous image range per
+ * device, balanced by compressed bytes (hjd_shard_range), and every device decodes its range with its own
+ * hjd_batch, driven by its own host thread.  rgb_out receives the shards back to back: image i is at
+ * rgb_offsets_out[i], exactly the bytes a single-device decode produces for it. */
+typedef struct hjd_multi hjd_multi;
+int        hjd_shard_range(const int64_t* sizes, int n, int rank, int world, int* lo, int* hi);
+hjd_multi* hjd_multi_create(const int* devices /* NULL: 0..n-1 */, int n_devices, unsigned flags);
+void       hjd_multi_destroy(hjd_multi* m);
+int        hjd_multi_num_devices(const hjd_multi* m);
+hjd_batch* hjd_multi_batch(hjd_multi* m, int k);      /* the k-th device's batch handle (resident use, timings) */
+const char* hjd_multi_last_error(const hjd_multi* m);
+uint64_t   hjd_multi_out_slab_bytes(const hjd_multi* m, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n);
+int        hjd_multi_decode_host(hjd_multi* m, const uint8_t* arena, const int64_t* offsets, const int64_t* sizes, int n,
+                                 uint8_t* rgb_out, uint64_t rgb_capacity, uint64_t* rgb_offsets_out, int32_t* status_out);
+
+/* Pinned host memory helpers (cudaHostAlloc, portable: pinned for every device of the process / cudaFreeHost) for callers without a CUDA binding. */
 void* hjd_host_alloc(size_t bytes);
 void  hjd_host_free(void* p);
+/* Same, with the pages taken from the NUMA node next to `device` where the platform exposes one
+ * (hjd_device_numa_node: -1 otherwise): the D2H copy of the decoded batch is the end-to-end bottleneck. */
+void* hjd_host_alloc_near(int device, size_t bytes);
+int   hjd_device_numa_node(int device);
+/* Raw host-link probe, no kernels: reps x (h2d_bytes up || d2h_bytes down, pinned buffers, two streams);
+ * milliseconds per repetition and direction.  The ceiling hjd_batch_decode_host works against. */
+int   hjd_link_probe(int device, const void* host_in, size_t h2d_bytes, void* host_out, size_t d2h_bytes,
+                     int reps, float* ms_h2d, float* ms_d2h);
 
 /* Testing aid: build the kernels' two-level lookup table from BITS / HUFFVAL (as in a DHT segment) and look
  * up the next 16 bits of a stream: returns len | size << 5 | zig-zag advance << 9 (0xFE01: no such code;

@@ -1,6 +1,8 @@
 """GPU tests added in round 2 (pytest -m gpu, through the C ABI): inputs beyond the reference
 (SURVEY.md 8(f) rank 4), the advisor's crafted-table case, per-device kernel attributes, the honoured
 chunk_images argument."""
+import os
+
 import numpy as np
 import pytest
 
@@ -222,3 +224,69 @@ def test_sparse_coefficient_slab_and_block_ends(hjd, port):
             got = last[inf.block_base:inf.block_base + inf.n_blocks]
             # a stored zero value (size > 0 never encodes 0) cannot occur, so the recorded end is the last non-zero
             assert np.array_equal(got, want), names[i]
+
+
+def test_multi_device_handle_matches_single_device(hjd, port):
+    """hjd_multi_*: the batch cut into contiguous ranges balanced by compressed bytes, one handle + one host
+    thread per device.  With one visible GPU two handles share it (the sharding, offsets and threading are
+    the same); with more, every device takes part.  Every image must be exactly the single-handle result --
+    including a six-table image that lands on the second handle."""
+    n_dev = hjd.lib().hjd_device_count()
+    six, src = six_table_image(port)
+    base = list(cases.small_cases().values())
+    files = base[:9] + [six] + base[9:16] + [six]
+    arena = hjd.PinnedArena(files)
+    need = hjd.rgb_slab_bytes(arena)
+    ref = np.zeros(need, dtype=np.uint8)
+    with hjd.BatchDecoder(0) as d:
+        ref_offs, st = d.decode_host(arena, ref.ctypes.data, need)
+    assert (st == 0).all()
+    for devices in ([0, 0], [0, 0, 0], list(range(n_dev)) if n_dev > 1 else [0]):
+        with hjd.MultiDecoder(devices) as m:
+            cap = m.out_slab_bytes(arena)
+            assert cap >= need
+            out = np.zeros(cap, dtype=np.uint8)
+            for rep in range(2):
+                offs, st = m.decode_host(arena, out.ctypes.data, cap)
+                assert (st == 0).all(), (devices, st)
+                for i, f in enumerate(files):
+                    inf = hjd.probe(f)[1]
+                    nb = inf.width * inf.height * 3
+                    a = out[int(offs[i]):int(offs[i]) + nb]
+                    b = ref[int(ref_offs[i]):int(ref_offs[i]) + nb]
+                    assert np.array_equal(a, b), (devices, i)
+    o = port.decode(src)
+    i = 9
+    assert np.array_equal(ref[int(ref_offs[i]):int(ref_offs[i]) + o["rgb"].size].reshape(o["rgb"].shape), o["rgb"])
+    arena.close()
+
+
+def test_pipelined_file_to_bmp_conversion(hjd, port, tmp_path):
+    """hjd_convert_jpg_files_multi: readers -> chunked GPU decodes in BMP layout -> writers.  Small chunks force
+    several chunks per worker and several workers; bad inputs do not stop the rest; bytes are WriteBMP24's."""
+    names = list(cases.small_cases().keys())
+    ins, outs = [], []
+    for k, n in enumerate(names):
+        p = tmp_path / f"{k:02d}_{n}.jpg"
+        p.write_bytes(cases.small_cases()[n])
+        ins.append(str(p))
+        outs.append(str(tmp_path / f"{k:02d}_{n}.bmp"))
+    bad = tmp_path / "bad.jpg"
+    bad.write_bytes(b"this is not a jpeg")
+    ins[5:5] = [str(bad), str(tmp_path / "missing.jpg")]
+    outs[5:5] = [str(tmp_path / "bad.bmp"), str(tmp_path / "missing.bmp")]
+    n_dev = hjd.lib().hjd_device_count()
+    for devices, chunk in (([0], 2), ([0], 0), (list(range(n_dev)), 3)):
+        for o in outs:
+            if os.path.exists(o):
+                os.remove(o)
+        ok = hjd.ConvertJpgFiles(ins, outs, threads=4, devices=devices, chunk_images=chunk)
+        assert ok == [1] * 5 + [0, 0] + [1] * (len(names) - 5), (devices, chunk, ok)
+        k = 0
+        for i, (src, dst) in enumerate(zip(ins, outs)):
+            if i in (5, 6):
+                assert not os.path.exists(dst)
+                continue
+            want = port.bmp24_bytes(port.decode(cases.small_cases()[names[k]])["rgb"])
+            assert open(dst, "rb").read() == want, (devices, chunk, names[k])
+            k += 1

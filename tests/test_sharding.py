@@ -59,3 +59,15 @@ def test_two_rank_gloo_sharded_decode(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_library_shard_rule_equals_python_rule():
+    """hjd_shard_range (what hjd_multi_decode_host cuts a batch with) == sharding.shard_range (what bench.py's
+    ranks use): same ranges for every rank, including empty batches and more ranks than images."""
+    import hls_jpeg_decoder_b200 as hjd
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 5, 33, 1024):
+        sizes = rng.integers(1, 900000, size=n).tolist()
+        for world in (1, 2, 3, 4, 8, 16):
+            for r in range(world):
+                assert hjd.shard_range_c(sizes, r, world) == shard_range(sizes, r, world), (n, world, r)
