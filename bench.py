@@ -184,13 +184,15 @@ def _ref_worker(jpg: bytes) -> float:
 
 
 def _ref_file_worker(paths) -> float:
-    """The reference's ConvertJpgFile sequence for one file (openjpg.cpp:593-684): read, parse + JpegDecodeHW,
-    WriteBMP24 -- its own code for every step (oracle/_ref), heap buffers instead of the 105 KB stack buffer."""
+    """The reference's ConvertJpgFile sequence for one file (openjpg.cpp:593-684): read, parse + decode, WriteBMP24
+    -- the reference's own code for every step (oracle/_ref), with heap buffers instead of the 105 KB stack
+    buffer and restarts counted in MCUs by the harness (mode 1: the reference's own restart handling is
+    broken), exactly as in the cpu_baseline."""
     from oracle import refbind
     src, dst = paths
     t = time.perf_counter()
     jpg = open(src, "rb").read()
-    r = refbind.decode(jpg, mode=0, variant="hd", want_planes=False)
+    r = refbind.decode(jpg, mode=1, variant="hd", want_planes=False)
     assert r["rc"] == 0
     refbind.write_bmp24(dst, r["rgb"])
     return time.perf_counter() - t
@@ -261,6 +263,36 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 # sub-records measured AFTER the timed headline (never inside it)
 # ---------------------------------------------------------------------------------------------
+def single_image_record(hjd, local_rank):
+    """Config 1 through the reference-named single-image calls (DecodeJpgFileData loadjpg.h:186, ConvertJpgFile
+    openjpg.cpp:593): wall-clock latency per call after the first.  The image is a synthetic stand-in of
+    data/Lenna.jpg's shape (512x512 4:2:0, no restart markers: kernel 1b), since the reference's own file is
+    not on the GPU box; tests/test_gpu_parity.py::test_lenna_config1 checks the real one where it exists."""
+    import statistics
+    from tools.gen_jpegs import encode_jpeg, synth_rgb
+    jpg = encode_jpeg(synth_rgb(512, 512, 1), 92, "4:2:0", 0)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    src, dst = os.path.join(base, f"hjd_c1_{os.getpid()}.jpg"), os.path.join(base, f"hjd_c1_{os.getpid()}.bmp")
+    with open(src, "wb") as fh:
+        fh.write(jpg)
+    try:
+        hjd.lib().hjd_set_default_device(local_rank)
+        for _ in range(5):
+            hjd.DecodeJpgFileData(jpg)
+            assert hjd.ConvertJpgFile(src, dst) == 1
+        td, tc = [], []
+        for _ in range(40):
+            t = time.perf_counter(); hjd.DecodeJpgFileData(jpg); td.append(time.perf_counter() - t)
+            t = time.perf_counter(); hjd.ConvertJpgFile(src, dst); tc.append(time.perf_counter() - t)
+        return {"workload": f"one synthetic 512x512 4:2:0 baseline JPEG, {len(jpg)} bytes, no restart markers (the shape of configs[0]'s data/Lenna.jpg)",
+                "DecodeJpgFileData_ms": round(1e3 * statistics.median(td), 3),
+                "ConvertJpgFile_ms": round(1e3 * statistics.median(tc), 3), "calls": 40}
+    finally:
+        for p in (src, dst):
+            if os.path.exists(p):
+                os.remove(p)
+
+
 def file_to_bmp_record(hjd, files, local_rank, rank, n_images=256, with_reference=False):
     """.jpg files on disk -> .bmp files on disk through hjd_convert_jpg_files_multi
     (readers -> chunked GPU decodes in BMP layout -> writers), on a tmpfs so that the number is the
@@ -310,7 +342,7 @@ def file_to_bmp_record(hjd, files, local_rank, rank, n_images=256, with_referenc
                     list(ex.map(_ref_file_worker, pairs))
                     t0 = time.perf_counter() - t0
                 rec["reference_ConvertJpgFile"] = {"images_per_s": round(m / t0, 3), "cores": cores, "images": m,
-                                                   "kind": "reference (oracle/_ref: its own parse, JpegDecodeHW and WriteBMP24)"}
+                                                   "kind": "reference (oracle/_ref: its own parser, block decode and WriteBMP24; restarts counted by the harness)"}
                 rec["reference_bmp_identical"] = open(pairs[0][1], "rb").read() == open(outs[0], "rb").read()
         return rec
     finally:
@@ -555,6 +587,7 @@ def run_ours(args, rank, local_rank, world):
         dec.close()
         arena.close()
         if rank == 0:
+            extras["c1"] = single_image_record(hjd, local_rank)
             extras["file_to_bmp"] = file_to_bmp_record(hjd, files, local_rank, rank, with_reference=(world == 1 and not args.no_cpu_baseline))
         barrier()
         strong = sub_record(hjd, dist, barrier, local_rank, rank, world, "c2", "strong", args.extra_steps, peak0)

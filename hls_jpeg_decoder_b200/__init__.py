@@ -107,11 +107,8 @@ _SIGS = {
     "hjd_batch_download_coef": (c_int, [c_void_p, c_void_p]),
     "hjd_batch_download_planes": (c_int, [c_void_p, c_void_p]),
     "hjd_batch_download_image_coef": (c_int, [c_void_p, c_int, c_void_p]),
-    "hjd_batch_download_block_last": (c_int, [c_void_p, c_void_p]),
     "hjd_batch_bmp_bytes": (c_uint64, [c_void_p, c_int]),
     "hjd_batch_download_bmp": (c_int, [c_void_p, c_int, c_void_p]),
-    "hjd_batch_densify_coef": (c_int, [c_void_p]),
-    "hjd_batch_device_block_last": (c_void_p, [c_void_p]),
     "hjd_out_slab_bytes": (c_uint64, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_uint]),
     "hjd_batch_decode_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_void_p,
                                       c_uint64, POINTER(c_uint64), c_void_p, c_int]),
@@ -413,13 +410,6 @@ class BatchDecoder:
         inf = self.info(i)
         c = self.coefficients() if all_coef is None else all_coef
         return c[inf.block_base:inf.block_base + inf.n_blocks]
-
-    def block_last(self) -> np.ndarray:
-        """Per block, the zig-zag index of its last stored coefficient (what the sparse IDCT goes by)."""
-        n = self.coef_bytes // 128
-        out = np.zeros(max(n, 1), dtype=np.uint8)
-        _check(lib().hjd_batch_download_block_last(self._h, out.ctypes.data), "hjd_batch_download_block_last")
-        return out[:n]
 
     def image_coefficients_direct(self, i: int) -> np.ndarray:
         """Blocks of image i only (int16 [n_blocks, 64]), without downloading the whole slab."""

@@ -143,7 +143,7 @@ struct hjd_batch {
     bool uploaded = false, decoded = false;
     int launches = 0;
 
-    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_blast, d_planes, d_rgb, d_status;
+    DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
     PinBuf h_meta, h_out;                       // h_out: staging of the single-image calls
 };
@@ -203,15 +203,7 @@ extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < HJD_NSTREAMS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) {
-        // The IDCT reads only the 32-byte sectors of a block that hold coefficients: let the L2 fetch exactly
-        // those from HBM instead of whole 128-byte lines (a hint; HJD_L2_FETCH=64|128 restores coarser fetches).
-        size_t gran = 32;
-        if (const char* env = getenv("HJD_L2_FETCH")) gran = (size_t)atoi(env);
-        if (gran == 32 || gran == 64 || gran == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
-    }
     if (e == cudaSuccess) e = hjd_kernels_init_device();            // function attributes are per device
-    if (e == cudaSuccess) e = hjd_mcu_rgb_init_device();
     if (e == cudaSuccess) e = hjd_selfsync_init_device(&b->max_sync_ctas);
     if (e == cudaSuccess) {
         float cos_tab[64], c0, c00;
@@ -232,7 +224,7 @@ extern "C" void hjd_batch_destroy(hjd_batch* b)
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_arena.release(); b->d_imgs.release(); b->d_tsets.release(); b->d_qsets.release(); b->d_work.release(); b->d_segs.release(); b->d_mcucta.release(); b->d_slices.release(); b->d_slicecnt.release();
-    b->d_istart.release(); b->d_coef.release(); b->d_blast.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
+    b->d_istart.release(); b->d_coef.release(); b->d_planes.release(); b->d_rgb.release(); b->d_status.release();
     b->d_ss.release(); b->d_sswork.release(); b->d_sssegs.release(); b->d_destuff.release(); b->d_dlen.release(); b->d_counts.release();
     b->d_scantmp.release(); b->d_ssE0.release(); b->d_ssX.release(); b->d_ssnb.release();
     b->d_flag.release();
@@ -557,7 +549,6 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_mcucta.ensure(sizeof(uint32_t) * ((size_t)n + 2)));
     CU(b->d_istart.ensure(sizeof(uint32_t) * ((size_t)b->total_intervals + 2)));
     CU(b->d_coef.ensure(b->total_blocks * 128 + 256));
-    CU(b->d_blast.ensure(b->total_blocks + 256));                  // last zig-zag index of every block
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
     if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
@@ -785,8 +776,8 @@ static int run_selfsync(hjd_batch* b, cudaStream_t st)
                           b->max_sync_ctas, st));
     CU(hjd_scan_u32(cnt, 4 * N + 1, (uint32_t*)b->d_scantmp.p, st));              // cnt[] becomes its exclusive prefix
     CU(hjd_launch_ss_write(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
-                           (uint8_t*)b->d_blast.p, (int32_t*)b->d_status.p, st));
-    CU(hjd_launch_ss_fill_tail(imgs, ss, n_ss, cnt, (int16_t*)b->d_coef.p, (uint8_t*)b->d_blast.p, st));
+                           (int32_t*)b->d_status.p, st));
+    CU(hjd_launch_ss_fill_tail(imgs, ss, n_ss, cnt, (int16_t*)b->d_coef.p, st));
     b->launches += 4 + (4 * N + 1 > 2048 ? 3 : 1);
     b->ss_ran = true;
     return HJD_OK;
@@ -814,15 +805,14 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
         CU(hjd_launch_entropy_restart(arena, imgs, (const HjdTableSet*)b->d_tsets.p, (const uint32_t*)b->d_istart.p,
                                       (const HjdEntropyWork*)b->d_work.p + c.work0, (const HjdEntropySeg*)b->d_segs.p,
                                       (int)(c.work1 - c.work0),
-                                      b->max_tabs, (int16_t*)b->d_coef.p, (uint8_t*)b->d_blast.p, status, st));
+                                      b->max_tabs, (int16_t*)b->d_coef.p, status, st));
         b->launches += 1;
     }
     if (ev) CU(cudaEventRecord(ev[2], st));
     if (!(b->flags & HJD_FLAG_KEEP_PLANES)) {
         // default: kernels 2+3 fused per MCU, planes never reach HBM
         if (c.blocks) {
-            CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, (const uint8_t*)b->d_blast.p, imgs + c.img0,
-                                  (const HjdQuantSet*)b->d_qsets.p,
+            CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                   (uint8_t*)b->d_rgb.p, (const uint32_t*)b->d_mcucta.p + c.img0, n,
                                   b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, (b->flags & HJD_FLAG_BMP_OUT) != 0, st));
             b->launches += 1;
@@ -830,7 +820,7 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
         if (ev) CU(cudaEventRecord(ev[3], st));
     } else {
         if (c.blocks) {
-            CU(hjd_launch_idct_planes((const int16_t*)b->d_coef.p, (const uint8_t*)b->d_blast.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
+            CU(hjd_launch_idct_planes((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                       (uint8_t*)b->d_planes.p, n, c.max_blocks, st));
             b->launches += (n + 65534) / 65535;
         }
@@ -1011,7 +1001,6 @@ extern "C" uint64_t hjd_batch_scan_bytes(const hjd_batch* b)  { return b ? b->sc
 extern "C" uint64_t hjd_batch_pixels(const hjd_batch* b)      { return b ? b->pixels : 0; }
 extern "C" void* hjd_batch_device_rgb(hjd_batch* b)    { return b ? b->d_rgb.p : nullptr; }
 extern "C" void* hjd_batch_device_coef(hjd_batch* b)   { return b ? b->d_coef.p : nullptr; }
-extern "C" void* hjd_batch_device_block_last(hjd_batch* b) { return b ? b->d_blast.p : nullptr; }
 extern "C" void* hjd_batch_device_planes(hjd_batch* b) { return b ? b->d_planes.p : nullptr; }
 
 static int download(hjd_batch* b, void* dst, const void* src, uint64_t bytes, const char* who)
@@ -1051,39 +1040,13 @@ extern "C" int hjd_batch_download_bmp(hjd_batch* b, int i, uint8_t* dst)
     return download(b, dst, (const uint8_t*)b->d_rgb.p + d.rgb_off + 10, hjd_batch_bmp_bytes(b, i), "hjd_batch_download_bmp");
 }
 
-// The entropy kernels write a block only up to its last coefficient; readers of the slab as dense
-// int16 [block][64] get the sectors behind it zeroed first (in place, idempotent).
-static int densify(hjd_batch* b, uint64_t first_block, uint64_t n_blocks, const char* who)
-{
-    if (!b->decoded) return fail(HJD_ERR_STATE, who, "no decode yet");
-    CU(cudaSetDevice(b->device));
-    CU(hjd_launch_coef_densify((int16_t*)b->d_coef.p, (const uint8_t*)b->d_blast.p, first_block, n_blocks, b->stream));
-    return HJD_OK;
-}
-
-extern "C" int hjd_batch_download_block_last(hjd_batch* b, uint8_t* dst)
-{ return download(b, dst, b ? b->d_blast.p : nullptr, b ? b->total_blocks : 0, "hjd_batch_download_block_last"); }
-
-extern "C" int hjd_batch_densify_coef(hjd_batch* b)
-{
-    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_densify_coef", "null batch");
-    return densify(b, 0, b->total_blocks, "hjd_batch_densify_coef");
-}
-
 extern "C" int hjd_batch_download_coef(hjd_batch* b, int16_t* dst)
-{
-    if (!b) return fail(HJD_ERR_ARG, "hjd_batch_download_coef", "null batch");
-    int rc = densify(b, 0, b->total_blocks, "hjd_batch_download_coef");
-    if (rc) return rc;
-    return download(b, dst, b->d_coef.p, b->total_blocks * 128, "hjd_batch_download_coef");
-}
+{ return download(b, dst, b ? b->d_coef.p : nullptr, b ? b->total_blocks * 128 : 0, "hjd_batch_download_coef"); }
 
 extern "C" int hjd_batch_download_image_coef(hjd_batch* b, int i, int16_t* dst)
 {
     if (!b || i < 0 || i >= (int)b->imgs.size()) return fail(HJD_ERR_ARG, "hjd_batch_download_image_coef", "bad arguments");
     const HjdImageDesc& d = b->imgs[i];
-    int rc = densify(b, d.block_base, d.n_blocks, "hjd_batch_download_image_coef");
-    if (rc) return rc;
     return download(b, dst, (const uint8_t*)b->d_coef.p + d.block_base * 128, d.n_blocks * 128, "hjd_batch_download_image_coef");
 }
 

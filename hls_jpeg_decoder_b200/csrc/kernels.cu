@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(HJD_ENT_THREADS, HJD_ENT_MINBLOCKS)
 hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
                       const HjdTableSet* __restrict__ tsets, const uint32_t* __restrict__ interval_start,
                       const HjdEntropyWork* __restrict__ work, const HjdEntropySeg* __restrict__ segs,
-                      int16_t* __restrict__ coef, uint8_t* __restrict__ blk_last,
+                      int16_t* __restrict__ coef,
                       int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
@@ -333,20 +333,22 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     __syncthreads();
 
     // ---- per-lane interval setup -----------------------------------------------------------
+    const uint32_t sel = (uint32_t)tid;     // (ordering a CTA's intervals by compressed length so that a warp's lanes finish
+                                            //  together was measured: no gain, 2.97 vs 2.94 ms -- DESIGN.md 4.6)
     BitReader br;
     br.base = arena; br.pos = br.end = 0; br.hi = br.lo = 0; br.nbits = 0; br.padbits = 0;
     br.wptr = (const uint32_t*)arena; br.w0 = br.w1 = br.w2 = 0;
     uint32_t blocks_left = 0, gblk = 0;
     int img = 0, bpm = 1, ny = 1;
-    if ((uint32_t)tid < wk.n_intervals) {
-        // the segment this thread falls into (tid0 is ascending): binary search
+    if (sel < wk.n_intervals) {
+        // the segment this interval falls into (tid0 is ascending): binary search
         uint32_t lo = 0, hi = wk.n_segs - 1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) >> 1;
-            if (segs[wk.first_seg + mid].tid0 <= (uint32_t)tid) lo = mid; else hi = mid - 1;
+            if (segs[wk.first_seg + mid].tid0 <= sel) lo = mid; else hi = mid - 1;
         }
         const HjdEntropySeg sg = segs[wk.first_seg + lo];
-        const uint32_t g = sg.first_interval + ((uint32_t)tid - sg.tid0);
+        const uint32_t g = sg.first_interval + (sel - sg.tid0);
         img = (int)sg.image;
         const HjdImageDesc* d = imgs + img;
         const uint32_t j = g - d->interval_base;
@@ -373,7 +375,6 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
     const uint32_t warp_list = sh_list + (uint32_t)(tid & ~31) * 8u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     int k = 0, bi = 0;                 // zig-zag index inside the block, block index inside the MCU
-    uint32_t klast = 0;                // zig-zag index of the last coefficient stored in the current block
     int flags = 0;
     bool dead = false;                 // undecodable code or data exhausted: zero-fill the rest
     br_prefetch(br);
@@ -410,7 +411,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                     br.nbits -= (int)used;
                     const uint32_t kpos = (uint32_t)k + kadv - 1u;                         // loadjpg.cpp:778, 806
                     if (size) {                          // a value follows: DC difference or AC coefficient (slot is pre-zeroed)
-                        if (kpos <= 63u) { hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)val); klast = kpos; }
+                        if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)val);
                         else flags |= HJD_ST_COEF_RANGE;                                   // loadjpg.cpp:780-783
                     }
                     k += (int)kadv;                      // EOB: +64, ZRL: +16 (loadjpg.cpp:771-775)
@@ -420,14 +421,12 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
             }
         }
         // ---- block hand-over ---------------------------------------------------------------
-        uint32_t flush_blk = 0, flush_last = 0;
+        uint32_t flush_blk = 0;
         if (done_block) {
             if (!dead) {                                  // DCT[0] = data + prevDC in int16 (loadjpg.cpp:664-665)
                 p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
                 hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
             }
-            flush_last = klast;
-            klast = 0;
             flush_blk = gblk++;
             blocks_left--;
             k = 0;
@@ -439,28 +438,20 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
             if (blocks_left == 0 && br.nbits < br.padbits) flags |= HJD_ST_OVERRUN;
         }
         // ---- cooperative flush of the finished blocks, four per step --------------------------
-        // Only the 32-byte sectors up to the last stored coefficient leave the SM (a block ends at zig-zag
-        // index ~20 on average: 59 instead of 128 bytes); blk_last[] tells the IDCT how far to read.
         const uint32_t m = __ballot_sync(0xffffffffu, done_block);
         if (m) {
-            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane | flush_last << 8);
+            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane);
             __syncwarp();
             const int n_done = __popc(m);
             const uint32_t chunk = (uint32_t)lane & 7u;
             for (int base = 0; base < n_done; base += 4) {                                  // warp-uniform trip count
                 const int idx = base + (lane >> 3);
                 if (idx < n_done) {
-                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);      // {block, owner lane | last index << 8}
-                    const uint32_t owner = ent.y & 255u, last = ent.y >> 8;
-                    if ((chunk >> 1) <= (last >> 4)) {                                      // slot chunks beyond are zero already
-                        const uint32_t src = warp_slots + owner * 128u + ((chunk ^ (owner & 7u)) << 4);
-                        const uint4 w = hjd_lds_v4_sync(src);
-                        hjd_sts_zero16_sync(src);
-                        ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
-                    }
-#ifndef HJD_TUNE_NO_BLAST
-                    if (chunk == 0) blk_last[ent.x] = (uint8_t)last;
-#endif
+                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);      // {block, owner lane}
+                    const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
+                    const uint4 w = hjd_lds_v4_sync(src);
+                    hjd_sts_zero16_sync(src);
+                    ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
                 }
             }
             __syncwarp();
@@ -481,13 +472,13 @@ cudaError_t hjd_kernels_init_device(void)
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
                                        const uint32_t* interval_start, const HjdEntropyWork* work,
                                        const HjdEntropySeg* segs, int n_work,
-                                       int max_tabs, int16_t* coef, uint8_t* blk_last, int32_t* status, cudaStream_t st)
+                                       int max_tabs, int16_t* coef, int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
     if (max_tabs < 1) max_tabs = 1;
     if (max_tabs > HJD_MAX_TABLES) max_tabs = HJD_MAX_TABLES;
     const size_t smem = HJD_ENT_THREADS * (128 + 8) + (size_t)max_tabs * sizeof(HjdHuffTable);
-    hjd_k_entropy_restart<<<n_work, HJD_ENT_THREADS, smem, st>>>(arena, imgs, tsets, interval_start, work, segs, coef, blk_last, status);
+    hjd_k_entropy_restart<<<n_work, HJD_ENT_THREADS, smem, st>>>(arena, imgs, tsets, interval_start, work, segs, coef, status);
     return cudaGetLastError();
 }
 
@@ -519,13 +510,12 @@ __device__ __forceinline__ int hjd_finish_sample(float sum)
 __device__ __forceinline__ int hjd_dp2a_lo_su(uint32_t a, uint32_t b) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
 __device__ __forceinline__ int hjd_dp2a_hi_su(uint32_t a, uint32_t b) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
 
-// Sparse blocks.  A block's coefficients end, in zig-zag order, at the index the entropy kernel recorded in
-// blk_last[] (20 on average for the q85 workload), and everything behind it is zero.  Skipping a zero
-// term is exact -- x + 0*c == x, and fl() of an unchanged sum is unchanged -- so an IDCT variant that
-// leaves out the frequencies beyond index KM computes, instruction for instruction, the same sums as the
-// full one on any block that ends at or before KM: the error window, the exact re-evaluation and with
-// them bit-exactness carry over.  Variants end on whole anti-diagonals of the zig-zag scan:
-//   KM =  9: u + v <= 3 (10 coefficients)   KM = 20: u + v <= 5 (21)   KM = 35: u + v <= 7 (36)   KM = 63: all
+// Short blocks.  Most blocks end, in zig-zag order, long before index 63 (at 20 on average for the q85
+// workload) and everything behind the end is zero.  Skipping a zero term is exact -- x + 0*c == x, and
+// fl() of an unchanged sum is unchanged -- so an IDCT variant that leaves out the frequencies beyond index
+// KM computes, instruction for instruction, the same sums as the full one on any block that ends at or
+// before KM: the error window, the exact re-evaluation and with them bit-exactness carry over.
+// A variant ends on a whole anti-diagonal of the zig-zag scan: KM = 20 <=> u + v <= 5 (21 coefficients).
 // hjd_live_mask(KM): bit n set <=> natural position n (8 * row + column) can be non-zero.
 __host__ __device__ constexpr uint64_t hjd_live_mask(int km)
 {
@@ -535,8 +525,6 @@ __host__ __device__ constexpr uint64_t hjd_live_mask(int km)
 #undef HJD_LM
     return m;
 }
-__host__ __device__ constexpr int hjd_class_of_last(int last) { return last <= 9 ? 0 : last <= 20 ? 1 : last <= 35 ? 2 : 3; }
-__host__ __device__ constexpr int hjd_km_of_class(int cls) { return cls == 0 ? 9 : cls == 1 ? 20 : cls == 2 ? 35 : 63; }
 
 // q: HjdQuantSet::qp (byte-packed pairs).  Dequantise one block held as 8 x uint4 (zig-zag order) into
 // bp[natural] = fl(C(u)C(v) * (float)(short)(coef*q)), stored as row pairs: bp2[(v>>1)*8+u] = (bp[8v+u], bp[8(v+1)+u]), v even.
@@ -601,8 +589,6 @@ __device__ __forceinline__ float hjd_exact_sum(const float2 bp2[32], const float
     return sum;
 }
 
-__device__ uint4 g_zero_sector[2];      // 32 zero bytes (zero-initialised device memory)
-
 __device__ __forceinline__ void hjd_ldg256(const uint4* p, uint4& a, uint4& b)
 {
     asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -632,40 +618,41 @@ __device__ __forceinline__ void hjd_pass1_column(const float2 bp2[32], float2 r[
     }
 }
 
-// One 8x8 block that ends at zig-zag index `last`: dequantise, IDCT, +128, clamp; rows go to
-// dst[y*pitch + 0..7] (planes in HBM for the unfused kernel, a shared-memory tile for the fused one).
-// s_cos: the cos table in shared memory (the exact re-evaluation indexes it dynamically).
-// cls (WARP-UNIFORM: the class of the longest block among the lanes that are here together) selects how
-// much of the dequantisation and of pass 1 is executed: 0/1 -> KM 20, 2 -> KM 35, 3 -> everything.
-// The variants are arms of small switches inside ONE body -- pass 2, the epilogue and the exact path are
-// shared -- because the whole kernel has to stay around the 32 KB of the instruction cache: four complete
-// copies of this routine (one per class) executed 17 % fewer instructions and ran 45 % SLOWER, with
-// "no instruction" as the top stall reason (ncu, profiles/r2_*).
+// One 8x8 block: dequantise, IDCT, +128, clamp; rows go to dst[y*pitch + 0..7] (planes in HBM for the
+// unfused kernel, a shared-memory tile for the fused one).  s_cos: the cos table in shared memory (the
+// exact re-evaluation indexes it dynamically).
+// Short blocks: when NONE of the lanes that are here together holds a coefficient beyond zig-zag index 20
+// (u + v <= 5: the usual case for the chroma blocks of a warp, 79 % on the q85 workload; a warp's 32 luma
+// blocks practically never qualify), the dequantisation and pass 1 leave those frequencies out.  The two
+// variants are arms of small warp-uniform switches inside ONE body -- pass 2, the epilogue and the exact path
+// are shared -- because the kernel has to stay around the 32 KB of the instruction cache (see DESIGN 4.6:
+// complete copies of this routine per length class executed 17 % fewer instructions and ran 45 % slower).
 __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, const uint4* __restrict__ qp,
-                                               const float* s_cos, uint8_t* dst, uint32_t pitch, uint32_t last, int cls)
+                                               const float* s_cos, uint8_t* dst, uint32_t pitch)
 {
-    // 256-bit loads (sm_100 LDG.256): one per 32-byte sector, and only the sectors the entropy kernel wrote
-    // (the rest of the 128-byte slot holds whatever an earlier batch left there): a sector beyond the
-    // block's end is read from a zero sector instead (an address select, not a predicated load).
+    // 256-bit loads (sm_100 LDG.256): a lane owns a whole 128-byte line, and every instruction of the
+    // warp touches 32 different lines, so wider loads halve the L1 wavefronts of this kernel
     uint4 c[8], q[8];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint4* src = (uint32_t)i <= (last >> 4) ? cp + 2 * i : g_zero_sector;
-        hjd_ldg256(src, c[2 * i], c[2 * i + 1]);
-        hjd_ldg256_nc(qp + 2 * i, q[2 * i], q[2 * i + 1]);
+    for (int i = 0; i < 4; i++) { hjd_ldg256(cp + 2 * i, c[2 * i], c[2 * i + 1]); hjd_ldg256_nc(qp + 2 * i, q[2 * i], q[2 * i + 1]); }
+    int cls;
+    {
+        // any coefficient at zig-zag index 21..63?  (the odd half of word 10, words 11..31)
+        const uint32_t* cw = (const uint32_t*)c;
+        uint32_t tail = cw[10] >> 16;
+#pragma unroll
+        for (int k = 11; k < 32; k++) tail |= cw[k];
+        cls = __any_sync(__activemask(), tail != 0u) ? 3 : 1;
     }
 
     float2 bp2[32];
     float a_dc, a_ac;
 #ifndef HJD_IDCT_VARIANTS
-#define HJD_IDCT_VARIANTS 3
+#define HJD_IDCT_VARIANTS 2
 #endif
     if (HJD_IDCT_VARIANTS == 1) cls = 3;
-    if (HJD_IDCT_VARIANTS == 2 && cls == 2) cls = 3;
     if (cls <= 1) {
         a_ac = hjd_dequant_block<20>(c, q, bp2, &a_dc);
-    } else if (cls == 2) {
-        a_ac = hjd_dequant_block<35>(c, q, bp2, &a_dc);
     } else {
         a_ac = hjd_dequant_block<63>(c, q, bp2, &a_dc);
     }
@@ -689,7 +676,6 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
     {                                                                                                          \
         float2 r[4];                                                                                           \
         if (cls <= 1) hjd_pass1_column<20, X>(bp2, r);                                                         \
-        else if (cls == 2) hjd_pass1_column<35, X>(bp2, r);                                                    \
         else hjd_pass1_column<63, X>(bp2, r);                                                                  \
         _Pragma("unroll")                                                                                      \
         for (int y = 0; y < 8; y++) {                                                                          \
@@ -741,15 +727,8 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
     }
 }
 
-// Warp-uniform class of the blocks that the lanes here hold (their last zig-zag indices).
-__device__ __forceinline__ int hjd_warp_class(uint32_t last)
-{
-    return hjd_class_of_last((int)__reduce_max_sync(__activemask(), last));
-}
-
 __global__ void __launch_bounds__(HJD_IDCT_THREADS, 4)
-hjd_k_idct_planes(const int16_t* __restrict__ coef, const uint8_t* __restrict__ blk_last,
-                  const HjdImageDesc* __restrict__ imgs,
+hjd_k_idct_planes(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
                   const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ planes, int img_base)
 {
     __shared__ float s_cos[64];
@@ -771,20 +750,18 @@ hjd_k_idct_planes(const int16_t* __restrict__ coef, const uint8_t* __restrict__ 
         comp = (bi == ny) ? 1 : 2; pitch = d->c_pitch; poff = comp == 1 ? d->cb_off : d->cr_off;
         bx = mx; by = my;
     }
-    const uint32_t last = blk_last[d->block_base + b];
     hjd_idct_block((const uint4*)(coef + (d->block_base + b) * 64), (const uint4*)(qsets[d->quant_set].qp[comp]),
-                   s_cos, planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8, pitch, last, hjd_warp_class(last));
+                   s_cos, planes + poff + (uint64_t)by * 8 * pitch + (uint64_t)bx * 8, pitch);
 }
 
-cudaError_t hjd_launch_idct_planes(const int16_t* coef, const uint8_t* blk_last, const HjdImageDesc* imgs,
-                                   const HjdQuantSet* qsets,
+cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                    uint8_t* planes, int n_images, uint32_t max_blocks, cudaStream_t st)
 {
     if (n_images <= 0 || max_blocks == 0) return cudaSuccess;
     const unsigned gx = (max_blocks + HJD_IDCT_THREADS - 1) / HJD_IDCT_THREADS;
     for (int base = 0; base < n_images; base += 65535) {
         const int n = min(65535, n_images - base);
-        hjd_k_idct_planes<<<dim3(gx, n), HJD_IDCT_THREADS, 0, st>>>(coef, blk_last, imgs, qsets, planes, base);
+        hjd_k_idct_planes<<<dim3(gx, n), HJD_IDCT_THREADS, 0, st>>>(coef, imgs, qsets, planes, base);
     }
     return cudaGetLastError();
 }
@@ -979,75 +956,102 @@ cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// kernels 2+3 fused per MCU (the default path): 128 MCUs per CTA, coefficients -> RGB, planes never in HBM
+// kernels 2+3 fused per MCU (the default path): one thread decodes a whole MCU to RGB
 // ------------------------------------------------------------------------------------------
-// The reference couples DecodeMCU and YCrCB_to_RGB24_Block8x8 per MCU (loadjpg.cpp:1179-1180); so does this
-// kernel, per CTA of 128 MCUs, in two phases around ONE barrier:
-//   A. IDCT of the CTA's blocks (up to 6 x 128) into shared-memory tiles, IN ORDER OF BLOCK LENGTH: the
-//      blocks are counting-sorted (warp ballots, no atomics) by the class of their last zig-zag index, so
-//      that the 32 blocks a warp transforms together need the same sparse IDCT variant -- unsorted, the
-//      longest of 32 neighbouring luma blocks is almost always a long one (measured on the q85 workload:
-//      0.6 % of the warps could have used anything but the two longest variants, against 48 % of the
-//      blocks).  A thread transforms as many blocks as its MCU has, but not its own.
-//   B. upsampling + colour conversion of the thread's own MCU from the tiles, whole MCU-wide pixel rows
-//      (16 pixels = three 128-bit stores per thread and row, adjacent lanes contiguous).
-// Tiles are interleaved by thread (row r of tile s of thread t at [((s*8 + r) * T + t) * 8 B]): conflict-free
-// 8-byte row reads in phase B; phase A writes them in (block slot, thread) order inside a class, which
-// keeps consecutive lanes on consecutive threads' tiles.  The exact re-evaluation patches bytes in the tile.
-// BMP: the epilogue writes the reference's BMP file layout instead of top-down RGB (see below).
+// The reference couples DecodeMCU and YCrCB_to_RGB24_Block8x8 per MCU (loadjpg.cpp:1179-1180); so
+// does this kernel, with no barrier at all: a thread runs the IDCT of its MCU's Cb and Cr blocks into
+// thread-private shared-memory tiles, then, Y block by Y block, the IDCT into a third private tile
+// followed at once by upsampling + colour conversion of those 8x8 pixels and 24-byte row stores.
+// Planes never reach HBM.  Tiles are interleaved by thread (row r of thread t at [(r*T + t) * 8 B])
+// so row stores and loads are bank-conflict free; the exact re-evaluation patches bytes in the tile
+// before the colour step reads them.
 #ifndef HJD_MCU_MINBLOCKS
 #define HJD_MCU_MINBLOCKS 4
 #endif
-#define HJD_MCU_TILE_BYTES  (6 * 8 * HJD_MCU_THREADS * 8)          // six block tiles per MCU
-#define HJD_MCU_SMEM_BYTES  (HJD_MCU_TILE_BYTES + 256 + 6 * HJD_MCU_THREADS * 2 + HJD_MCU_THREADS * 32 + 6 * 4 * 4 * 4 + 64)
 #define HJD_BMP_PIXEL_OFF   64      // pixel array at +64 of an image's slab region, so the 54-byte header starts at +10
 #define HJD_BMP_FILE_OFF    10
-
-struct HjdMcuInfo {                 // what phase A needs to know about the MCU of another thread,
-    const uint4* cp;                // its first block's coefficients
-    const HjdQuantSet* qs;
-    uint32_t ny;                    // luma blocks per MCU (0: no MCU here)
-    uint32_t m;                     // and what its own thread picks up again in phase B: MCU index,
-    uint32_t img;                   // image index (kept here, not in registers, across the IDCTs)
-    uint32_t pad;
-};
-
-// Phase B of hjd_k_mcu_rgb: upsampling + colour conversion of one MCU from the CTA's tiles to HBM.
-template <bool BMP>
-__device__ __forceinline__ void hjd_mcu_phase_b(const HjdImageDesc* __restrict__ d, uint32_t m, const uint2* s_tile,
-                                                uint32_t t, uint8_t* __restrict__ rgb)
+template <bool FLAT, bool BMP>     // FLAT: exact 1-D grid with an image look-up; BMP: the reference's BMP file layout (see below)
+__global__ void __launch_bounds__(HJD_MCU_THREADS, HJD_MCU_MINBLOCKS)
+hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
+              const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb,
+              const uint32_t* __restrict__ mcu_prefix, int n_images, int img_base)
 {
-    constexpr uint32_t T = HJD_MCU_THREADS;
-    const uint32_t hf = d->hf, vf = d->vf;
+    __shared__ float s_cos[64];
+    __shared__ uint2 s_tile[4][8 * HJD_MCU_THREADS];             // Y (left), Y (right), Cb, Cr: 8 rows x T threads x 8 bytes
+    const uint32_t t = threadIdx.x;
+    if (t < 64) s_cos[t] = c_cos[t];
+    __syncthreads();
+
+    // Two grid shapes (two instantiations: the kernel sits at the 128-register cap, and a run-time switch
+    // cost 2 %).  Images of similar size: blockIdx.y = image, blockIdx.x = its CTA (no look-up).
+    // Mixed or tiny sizes (FLAT): a 1-D grid over ALL MCUs of the batch, the image of each thread found by
+    // binary search in mcu_prefix[i] = MCUs of the images before i.  The 2-D grid is sized for the largest
+    // image and launched 2 M empty CTAs for one 4096x4096 image among 4096 thumbnails (2.2 ms instead of
+    // 0.6), and gives a 16x16 image a CTA with one active thread; the search costs similar-sized batches
+    // 4 % (a chain of dependent loads in front of every CTA), an empty CTA next to nothing.
+    const HjdImageDesc* d;
+    uint32_t m;
+    if (FLAT) {
+        const uint32_t key = blockIdx.x * HJD_MCU_THREADS + t + mcu_prefix[0];
+        if (key >= mcu_prefix[n_images]) return;
+        int lo = 0, hi = n_images - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (mcu_prefix[mid] <= key) lo = mid; else hi = mid - 1;
+        }
+        d = imgs + lo;
+        m = key - mcu_prefix[lo];
+    } else {
+        d = imgs + (blockIdx.y + img_base);
+        m = blockIdx.x * HJD_MCU_THREADS + t;
+    }
+    if (m >= d->n_mcus || d->blocks_per_mcu == 0) return;
+    const uint32_t hf = d->hf, vf = d->vf, bpm = d->blocks_per_mcu;
     const bool gray = d->ncomp == 1;
+    const uint32_t ny = gray ? 1u : hf * vf;
     const uint32_t my = m / d->mcus_x, mx = m - my * d->mcus_x;
-    const int vs = (int)vf - 1;
+    const int hs = (int)hf - 1, vs = (int)vf - 1;
+    const HjdQuantSet* qs = qsets + d->quant_set;
+    const uint4* cp = (const uint4*)(coef + (d->block_base + (uint64_t)m * bpm) * 64);
+    constexpr uint32_t kPitch = HJD_MCU_THREADS * 8;
+    uint8_t* tY0 = (uint8_t*)&s_tile[0][t];
+    uint8_t* tY1 = (uint8_t*)&s_tile[1][t];
+    uint8_t* tCb = (uint8_t*)&s_tile[2][t];
+    uint8_t* tCr = (uint8_t*)&s_tile[3][t];
+
     const uint32_t W = d->width, H = d->height;
-    const uint32_t px = mx * hf * 8;                              // left edge of the MCU
-    const uint32_t npix = px < W ? min(8u * hf, W - px) : 0u;     // loadjpg.cpp:907
-    if (npix == 0) return;
     // RGB: top-down, stride 3W (loadjpg.cpp:921-925).  BMP: the file WriteBMP24 would write (openjpg.cpp:504-570),
     // laid out in the image's slab region from +HJD_BMP_FILE_OFF: 54-byte header, then rows bottom-up, B G R,
-    // each padded with zeros to a multiple of four bytes.
-    const uint64_t row_pitch = BMP ? (uint64_t)((W * 3 + 3) & ~3u) : (uint64_t)W * 3;
-    uint8_t* img_out = rgb + d->rgb_off + (BMP ? HJD_BMP_PIXEL_OFF : 0);
-    const uint32_t row_pad = BMP ? (uint32_t)(row_pitch - (uint64_t)W * 3) : 0u;
-    const bool last_col = px + npix == W;
+    // each padded with zeros to a multiple of four bytes; the pixel array starts 64-byte aligned.
+    const uint64_t img_pitch = BMP ? (uint64_t)((W * 3 + 3) & ~3u) : (uint64_t)W * 3;
+    uint8_t* img_rgb = rgb + d->rgb_off + (BMP ? HJD_BMP_PIXEL_OFF : 0);
+    const uint32_t px = mx * hf * 8;                              // left edge of the MCU
+    const uint32_t npix = px < W ? min(8u * hf, W - px) : 0u;     // loadjpg.cpp:907
     if (BMP && m == 0) {                                          // the header, by the thread of the first MCU
         uint8_t* hp = rgb + d->rgb_off + HJD_BMP_FILE_OFF;
-        const uint32_t file_size = (uint32_t)(row_pitch * H) + 54u;                   // openjpg.cpp:541
+        const uint32_t file_size = (uint32_t)(img_pitch * H) + 54u;                    // openjpg.cpp:541
         const uint32_t words[13] = {file_size, 0u, 54u, 40u, W, H, 1u | 24u << 16, 0u, 0u, 0u, 0u, 0u, 0u};
         hp[0] = 'B'; hp[1] = 'M';
 #pragma unroll
         for (int k = 0; k < 13; k++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) hp[2 + 4 * k + q] = (uint8_t)(words[k] >> (8 * q));
+            for (int qq = 0; qq < 4; qq++) hp[2 + 4 * k + qq] = (uint8_t)(words[k] >> (8 * qq));
     }
-    const uint2* tY = s_tile + t;
-    const uint2* tCb = s_tile + 4 * 8 * T + t;
-    const uint2* tCr = s_tile + 5 * 8 * T + t;
+    // one loop, one inlined IDCT: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order;
+    // after the last Y block of a block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB
+    const uint32_t n_pre = gray ? 0u : 2u;
 #pragma unroll 1
-    for (uint32_t by = 0; by < vf; by++) {
+    for (uint32_t it = 0; it < n_pre + ny; it++) {
+        const bool chroma = it < n_pre;
+        const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
+        if (it + 1 < n_pre + ny) {                                // next block's 128-byte line -> L1 while this one computes
+            const uint32_t nbi = (it + 1 < n_pre) ? ny + it + 1 : it + 1 - n_pre;
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(cp + nbi * 8));
+        }
+        const uint32_t bx = chroma ? 0u : bi % hf, by = chroma ? 0u : bi / hf;
+        hjd_idct_block(cp + bi * 8, (const uint4*)qs->qp[chroma ? 1 + it : 0], s_cos,
+                       chroma ? (it ? tCr : tCb) : (bx ? tY1 : tY0), kPitch);
+        if (chroma || bx + 1 < hf || npix == 0) continue;
         const uint32_t py0 = (my * vf + by) * 8;
 #pragma unroll 1
         for (uint32_t r = 0; r < 8; r++) {
@@ -1056,13 +1060,13 @@ __device__ __forceinline__ void hjd_mcu_phase_b(const HjdImageDesc* __restrict__
             uint32_t cbw[2] = {0x80808080u, 0x80808080u}, crw[2] = {0x80808080u, 0x80808080u};
             if (!gray) {
                 const uint32_t crow = (by * 8 + r) >> vs;         // nearest neighbour, loadjpg.cpp:911-912
-                const uint2 b8 = tCb[crow * T], r8 = tCr[crow * T];
+                const uint2 b8 = *(const uint2*)(tCb + crow * kPitch), r8 = *(const uint2*)(tCr + crow * kPitch);
                 cbw[0] = b8.x; cbw[1] = b8.y; crw[0] = r8.x; crw[1] = r8.y;
             }
-            uint8_t* dst = img_out + (uint64_t)(BMP ? H - 1 - py : py) * row_pitch + (uint64_t)px * 3;
-            const uint2 ya = tY[((by * hf) * 8 + r) * T];
-            if (hf == 2) {                                        // 16 pixels: 48 bytes, three 128-bit stores
-                const uint2 yb = tY[((by * hf + 1) * 8 + r) * T];
+            uint8_t* dst = img_rgb + (uint64_t)(BMP ? H - 1 - py : py) * img_pitch + (uint64_t)px * 3;      // loadjpg.cpp:921-925 / openjpg.cpp:555
+            const uint2 ya = *(const uint2*)(tY0 + r * kPitch);
+            if (hs) {                                             // 16 pixels: 48 bytes, three 128-bit stores
+                const uint2 yb = *(const uint2*)(tY1 + r * kPitch);
                 const uint32_t yw[4] = {ya.x, ya.y, yb.x, yb.y};
                 uint32_t out[12];
                 hjd_color_n<1, 16, BMP>(yw, cbw, crw, out);
@@ -1092,154 +1096,14 @@ __device__ __forceinline__ void hjd_mcu_phase_b(const HjdImageDesc* __restrict__
                 }
             }
             if constexpr (BMP) {
-                if (last_col)
-                    for (uint32_t q = 0; q < row_pad; q++) dst[npix * 3 + q] = 0;      // openjpg.cpp:563-567
+                if (px + npix == W)                               // row padding, openjpg.cpp:563-567
+                    for (uint32_t qq = W * 3; qq < (uint32_t)img_pitch; qq++) dst[qq - px * 3] = 0;
             }
         }
     }
 }
 
-template <bool FLAT, bool BMP>     // FLAT: exact 1-D grid with an image look-up (see below)
-__global__ void __launch_bounds__(HJD_MCU_THREADS, HJD_MCU_MINBLOCKS)
-hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const uint8_t* __restrict__ blk_last,
-              const HjdImageDesc* __restrict__ imgs,
-              const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb,
-              const uint32_t* __restrict__ mcu_prefix, int n_images, int img_base)
-{
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    constexpr uint32_t T = HJD_MCU_THREADS;
-    uint2* s_tile = (uint2*)s_dyn;                                   // [tile 6][row 8][thread T]
-    float* s_cos = (float*)(s_dyn + HJD_MCU_TILE_BYTES);
-    uint16_t* s_order = (uint16_t*)(s_cos + 64);                     // sorted blocks: thread | slot << 7 | last << 10
-    HjdMcuInfo* s_info = (HjdMcuInfo*)(s_order + 6 * T);
-    uint32_t* s_cnt = (uint32_t*)(s_info + T);                       // [slot 6][warp 4][class 4]: counts, then offsets
-    uint32_t* s_cbase = s_cnt + 6 * 4 * 4;                           // class bases [4] + total
-    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t < 64) s_cos[t] = c_cos[t];
-
-    // Two grid shapes (two instantiations: a run-time switch cost 2 %).  Images of similar size:
-    // blockIdx.y = image, blockIdx.x = its CTA (no look-up).  Mixed or tiny sizes (FLAT): a 1-D grid over
-    // ALL MCUs of the batch, the image of each thread found by binary search in mcu_prefix[i] = MCUs of the
-    // images before i.  The 2-D grid is sized for the largest image and launched 2 M empty CTAs for one
-    // 4096x4096 image among 4096 thumbnails (2.2 ms instead of 0.6), and gives a 16x16 image a CTA with one
-    // active thread; the search costs similar-sized batches 4 % (a chain of dependent loads in front of
-    // every CTA), an empty CTA next to nothing.
-    const HjdImageDesc* d = nullptr;
-    uint32_t m = 0;
-    bool valid = true;
-    if (FLAT) {
-        const uint32_t key = blockIdx.x * T + t + mcu_prefix[0];
-        if (key >= mcu_prefix[n_images]) valid = false;
-        else {
-            int lo = 0, hi = n_images - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (mcu_prefix[mid] <= key) lo = mid; else hi = mid - 1;
-            }
-            d = imgs + lo;
-            m = key - mcu_prefix[lo];
-        }
-    } else {
-        d = imgs + (blockIdx.y + img_base);
-        m = blockIdx.x * T + t;
-    }
-    if (valid && (m >= d->n_mcus || d->blocks_per_mcu == 0)) valid = false;
-    if (!FLAT && !__syncthreads_or(valid)) return;                   // whole CTA beyond the image
-    uint32_t hf = 1, vf = 1, bpm = 0, ny = 0;
-    bool gray = true;
-    uint64_t blk0 = 0;
-    if (valid) {
-        hf = d->hf; vf = d->vf; bpm = d->blocks_per_mcu;
-        gray = d->ncomp == 1;
-        ny = gray ? 1u : hf * vf;
-        blk0 = d->block_base + (uint64_t)m * bpm;
-    }
-    {
-        HjdMcuInfo inf;
-        inf.cp = (const uint4*)(coef + blk0 * 64);
-        inf.qs = valid ? qsets + d->quant_set : qsets;
-        inf.ny = valid ? ny : 0u;
-        inf.m = m;
-        inf.img = valid ? (uint32_t)(d - imgs) : 0u;
-        inf.pad = 0;
-        s_info[t] = inf;
-    }
-
-    // ---- phase A.1: counting sort of the CTA's blocks by length class ------------------------------
-    // order inside a class: (block slot, thread).  rank6 holds this thread's rank per slot (5 bits each).
-    uint32_t lasts = 0, lasts_hi = 0, rank6 = 0;                     // last indices of slots 0..3 / 4..5, one byte each
-    const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-    for (int bi = 0; bi < 6; bi++) {
-        const bool have = valid && (uint32_t)bi < bpm;
-        const uint32_t last = have ? (uint32_t)blk_last[blk0 + bi] : 0u;
-        if (bi < 4) lasts |= last << (8 * bi); else lasts_hi |= last << (8 * (bi - 4));
-        const int cls = hjd_class_of_last((int)last);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, have && cls == c);
-            if (have && cls == c) rank6 |= (uint32_t)__popc(bal & lt_mask) << (5 * bi);
-            if (lane == 0) s_cnt[(bi * 4 + warp) * 4 + c] = (uint32_t)__popc(bal);
-        }
-    }
-    __syncthreads();
-    if (t < 4) {                                                     // one thread per class: offsets of the (slot, warp) cells
-        uint32_t run = 0;
-        for (int cell = 0; cell < 24; cell++) {
-            const uint32_t n = s_cnt[cell * 4 + t];
-            s_cnt[cell * 4 + t] = run;
-            run += n;
-        }
-        s_cbase[t] = run;                                            // class totals for now
-    }
-    __syncthreads();
-    uint32_t n_entries;
-    {
-        const uint32_t n0 = s_cbase[0], n1 = s_cbase[1], n2 = s_cbase[2], n3 = s_cbase[3];
-        n_entries = n0 + n1 + n2 + n3;
-        const uint32_t cb[4] = {0u, n0, n0 + n1, n0 + n1 + n2};
-#pragma unroll
-        for (int bi = 0; bi < 6; bi++) {
-            if (valid && (uint32_t)bi < bpm) {
-                const uint32_t last = ((bi < 4 ? lasts >> (8 * bi) : lasts_hi >> (8 * (bi - 4))) & 255u);
-                const int cls = hjd_class_of_last((int)last);
-                const uint32_t pos = cb[cls] + s_cnt[(bi * 4 + warp) * 4 + cls] + ((rank6 >> (5 * bi)) & 31u);
-                s_order[pos] = (uint16_t)(t | (uint32_t)bi << 7 | last << 10);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase A.2: IDCT in sorted order, 32 blocks of (nearly always) one class per warp step --------
-    constexpr uint32_t kPitch = T * 8;
-    for (uint32_t j = t; j < n_entries; j += T) {
-        const uint32_t ent = s_order[j];
-        const uint32_t mt = ent & 127u, bi = (ent >> 7) & 7u, last = ent >> 10;
-        const HjdMcuInfo inf = s_info[mt];
-        const bool chroma = bi >= inf.ny;
-        const uint32_t tile = chroma ? 4u + (bi - inf.ny) : bi;
-        hjd_idct_block(inf.cp + bi * 8, (const uint4*)inf.qs->qp[chroma ? 1u + (bi - inf.ny) : 0u], s_cos,
-                       (uint8_t*)&s_tile[tile * 8 * T + mt], kPitch, last, hjd_warp_class(last));
-    }
-    __syncthreads();
-
-    // ---- phase B: upsample + colour of this thread's MCU, MCU-wide rows ---------------------------------
-    const HjdMcuInfo me = s_info[t];
-    if (me.ny == 0) return;
-    hjd_mcu_phase_b<BMP>(imgs + me.img, me.m, s_tile, t, rgb);
-}
-
-cudaError_t hjd_mcu_rgb_init_device(void)
-{
-    cudaError_t e = cudaFuncSetAttribute(hjd_k_mcu_rgb<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HJD_MCU_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HJD_MCU_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HJD_MCU_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HJD_MCU_SMEM_BYTES);
-    return e;
-}
-
-cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const uint8_t* blk_last, const HjdImageDesc* imgs,
-                               const HjdQuantSet* qsets,
+cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
                                uint32_t max_mcus, bool bmp, cudaStream_t st)
 {
@@ -1250,37 +1114,13 @@ cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const uint8_t* blk_last, con
     if ((uint64_t)gx * HJD_MCU_THREADS * (uint64_t)n_images <= (uint64_t)n_mcus * 4) {
         for (int base = 0; base < n_images; base += 65535) {
             const int n = min(65535, n_images - base);
-            if (bmp) hjd_k_mcu_rgb<false, true><<<dim3(gx, n), HJD_MCU_THREADS, HJD_MCU_SMEM_BYTES, st>>>(coef, blk_last, imgs, qsets, rgb, nullptr, n_images, base);
-            else hjd_k_mcu_rgb<false, false><<<dim3(gx, n), HJD_MCU_THREADS, HJD_MCU_SMEM_BYTES, st>>>(coef, blk_last, imgs, qsets, rgb, nullptr, n_images, base);
+            if (bmp) hjd_k_mcu_rgb<false, true><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+            else hjd_k_mcu_rgb<false, false><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
         }
     } else {
         const unsigned g = (unsigned)(((uint64_t)n_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS);
-        if (bmp) hjd_k_mcu_rgb<true, true><<<g, HJD_MCU_THREADS, HJD_MCU_SMEM_BYTES, st>>>(coef, blk_last, imgs, qsets, rgb, mcu_prefix, n_images, 0);
-        else hjd_k_mcu_rgb<true, false><<<g, HJD_MCU_THREADS, HJD_MCU_SMEM_BYTES, st>>>(coef, blk_last, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+        if (bmp) hjd_k_mcu_rgb<true, true><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+        else hjd_k_mcu_rgb<true, false><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
     }
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
-// coefficient slab -> dense (parity / debug downloads only)
-// ------------------------------------------------------------------------------------------
-// The entropy kernels write only the 32-byte sectors of a block up to its last coefficient; the rest
-// of a 128-byte slot holds stale bytes that the IDCT never reads.  Anyone who reads the slab as
-// int16 [block][64] (hjd_batch_download_coef, hjd_batch_densify_coef) gets the dead sectors zeroed first.
-__global__ void __launch_bounds__(256)
-hjd_k_coef_densify(int16_t* __restrict__ coef, const uint8_t* __restrict__ blk_last, uint64_t first_block, uint64_t n_blocks)
-{
-    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;      // one 16-byte chunk per thread
-    const uint64_t b = i >> 3;
-    const uint32_t chunk = (uint32_t)i & 7u;
-    if (b >= n_blocks) return;
-    if ((chunk >> 1) > ((uint32_t)blk_last[first_block + b] >> 4))
-        ((uint4*)coef)[(first_block + b) * 8 + chunk] = make_uint4(0, 0, 0, 0);
-}
-
-cudaError_t hjd_launch_coef_densify(int16_t* coef, const uint8_t* blk_last, uint64_t first_block, uint64_t n_blocks, cudaStream_t st)
-{
-    if (n_blocks == 0) return cudaSuccess;
-    hjd_k_coef_densify<<<(unsigned)((n_blocks * 8 + 255) / 256), 256, 0, st>>>(coef, blk_last, first_block, n_blocks);
     return cudaGetLastError();
 }

@@ -26,32 +26,25 @@ cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* img
                                    int32_t* status, int first_image, int n_images, const HjdScanSlice* slices,
                                    int n_slices, uint32_t* slice_cnt, cudaStream_t st);
 
-// Kernel 1a: restart-interval-parallel Huffman decode -> int16 coefficients (zig-zag order).  Only the 32-byte
-// sectors of a block up to its last coefficient are written; blk_last[block] = that zig-zag index.
+// Kernel 1a: restart-interval-parallel Huffman decode -> int16 coefficients (zig-zag order).
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
                                        const uint32_t* interval_start, const HjdEntropyWork* work,
                                        const HjdEntropySeg* segs, int n_work,
-                                       int max_tabs, int16_t* coef, uint8_t* blk_last, int32_t* status, cudaStream_t st);
+                                       int max_tabs, int16_t* coef, int32_t* status, cudaStream_t st);
 
 // Kernel 2: dequantise + de-zig-zag + IDCT -> u8 planes (bit-exact with the reference's direct form).
-cudaError_t hjd_launch_idct_planes(const int16_t* coef, const uint8_t* blk_last, const HjdImageDesc* imgs,
-                                   const HjdQuantSet* qsets,
+cudaError_t hjd_launch_idct_planes(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                    uint8_t* planes, int n_images, uint32_t max_blocks, cudaStream_t st);
 
 // Kernel 3: chroma upsample + YCbCr->RGB + clamp -> packed RGB24.
 cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, uint8_t* rgb, int n_images,
                              uint32_t max_width, uint32_t max_height, cudaStream_t st);
 
-// Kernels 2+3 fused per MCU (default path): coefficients -> RGB, no plane traffic, blocks transformed in
-// order of their length.  mcu_prefix[i] = MCUs of images 0..i-1 (any common offset; n_images + 1 entries);
+// Kernels 2+3 fused per MCU (default path): one thread = one MCU, coefficients -> RGB, no plane traffic, no barriers.
+// mcu_prefix[i] = MCUs of images 0..i-1 (any common offset; n_images + 1 entries);
 // n_mcus = mcu_prefix[n_images] - mcu_prefix[0]; max_mcus = MCUs of the largest image.  Batches of
 // similar-sized images get an (image, CTA) grid, mixed or tiny sizes a flat grid over all MCUs (see the kernel).
 // bmp: write the reference's BMP file layout (header at rgb_off + 10, bottom-up B G R rows from rgb_off + 64).
-cudaError_t hjd_mcu_rgb_init_device(void);
-cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const uint8_t* blk_last, const HjdImageDesc* imgs,
-                               const HjdQuantSet* qsets,
+cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
                                uint32_t max_mcus, bool bmp, cudaStream_t st);
-
-// Zero the sectors of blocks [first_block, first_block + n_blocks) that the entropy kernels did not write.
-cudaError_t hjd_launch_coef_densify(int16_t* coef, const uint8_t* blk_last, uint64_t first_block, uint64_t n_blocks, cudaStream_t st);

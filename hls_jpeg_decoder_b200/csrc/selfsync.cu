@@ -692,7 +692,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                const HjdSsSeg* __restrict__ segs,
                const uint8_t* __restrict__ dst, const uint32_t* __restrict__ dlen, uint32_t n_subs_total,
                const uint64_t* __restrict__ x_arr, const uint32_t* __restrict__ prefix,
-               int16_t* __restrict__ coef, uint8_t* __restrict__ blk_last, int32_t* __restrict__ status)
+               int16_t* __restrict__ coef, int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
     constexpr uint32_t kTabBytes = (uint32_t)sizeof(HjdHuffTable);
@@ -737,7 +737,6 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
     SsBits br;
     br.hi = br.lo = br.wa = br.wb = br.wc = 0; br.nbits = 64; br.wp = (const uint32_t*)D;
     int flags = 0;
-    uint32_t klast = 0;               // zig-zag index of the last coefficient stored in the current block
     int steps = 0;                    // rounds spent on the current owned block
     int rem_min = 0;                  // rem below this: the bit position has left the zeroed slack
     uint32_t own_end = 0;             // image-local index one past the last block this thread owns
@@ -787,7 +786,7 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                     rem -= (int)sy.used;
                     const uint32_t kpos = (uint32_t)k + sy.kadv - 1u;
                     if (owned && sy.size) {
-                        if (kpos <= 63u) { hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)sy.val); klast = kpos; }
+                        if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)sy.val);
                         else flags |= HJD_ST_COEF_RANGE;
                     }
                     k += (int)sy.kadv;
@@ -812,19 +811,15 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
         // ---- bounds (see SS_WRITE_MAX_STEPS) ---------------------------------------------------
         if (!finished && !done_block && owned && (++steps > SS_WRITE_MAX_STEPS || rem < rem_min)) {
             flags |= steps > SS_WRITE_MAX_STEPS ? HJD_ST_BAD_CODE : HJD_ST_OVERRUN;
-            for (uint32_t bz = blk; bz < own_end; bz++) {            // zero blocks: first sector + "ends at index 0"
-                for (int q = 0; q < 2; q++) ((uint4*)coef)[(size_t)(blk_base + bz) * 8u + q] = make_uint4(0, 0, 0, 0);
-                blk_last[blk_base + bz] = 0;
-            }
+            for (uint32_t bz = blk; bz < own_end; bz++)
+                for (int q = 0; q < 8; q++) ((uint4*)coef)[(size_t)(blk_base + bz) * 8u + q] = make_uint4(0, 0, 0, 0);
             blk = own_end;
             finished = true;
         }
         // ---- block hand-over ---------------------------------------------------------------
-        uint32_t flush_blk = 0, flush_last = 0;
+        uint32_t flush_blk = 0;
         if (done_block) {
             steps = 0;
-            flush_last = klast;
-            klast = 0;
             p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
             hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
             flush_blk = blk_base + blk;
@@ -840,22 +835,18 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
         // ---- cooperative flush, four blocks per step (as in kernel 1a) ----------------------
         const uint32_t m = __ballot_sync(0xffffffffu, done_block);
         if (m) {
-            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane | flush_last << 8);
+            if (done_block) hjd_sts_v2_sync(warp_list + (uint32_t)__popc(m & lt_mask) * 8u, flush_blk, (uint32_t)lane);
             __syncwarp();
             const int n_done = __popc(m);
             const uint32_t chunk = (uint32_t)lane & 7u;
             for (int base = 0; base < n_done; base += 4) {
                 const int idx = base + (lane >> 3);
                 if (idx < n_done) {
-                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);     // {block, owner lane | last index << 8}
-                    const uint32_t owner = ent.y & 255u, last = ent.y >> 8;
-                    if ((chunk >> 1) <= (last >> 4)) {                                     // only the sectors that hold coefficients
-                        const uint32_t src = warp_slots + owner * 128u + ((chunk ^ (owner & 7u)) << 4);
-                        const uint4 w = hjd_lds_v4_sync(src);
-                        hjd_sts_zero16_sync(src);
-                        ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
-                    }
-                    if (chunk == 0) blk_last[ent.x] = (uint8_t)last;
+                    const uint2 ent = hjd_lds_v2_sync(warp_list + (uint32_t)idx * 8u);
+                    const uint32_t src = warp_slots + ent.y * 128u + ((chunk ^ (ent.y & 7u)) << 4);
+                    const uint4 w = hjd_lds_v4_sync(src);
+                    hjd_sts_zero16_sync(src);
+                    ((uint4*)coef)[(size_t)(ent.x * 8u + chunk)] = w;
                 }
             }
             __syncwarp();
@@ -889,12 +880,12 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
                                 const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
                                 const uint32_t* dlen,
                                 uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
-                                uint8_t* blk_last, int32_t* status, cudaStream_t st)
+                                int32_t* status, cudaStream_t st)
 {
     if (n_work <= 0) return cudaSuccess;
     const size_t smem = HJD_SS_THREADS * (128 + 8) + 6 * sizeof(HjdHuffTable);
     hjd_k_ss_write<<<n_work, HJD_SS_THREADS, smem, st>>>(imgs, tsets, ss, work, segs, dst, dlen, n_subs_total, x, prefix,
-                                                        coef, blk_last, status);
+                                                        coef, status);
     return cudaGetLastError();
 }
 
@@ -906,7 +897,7 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
 // keep the output a function of the input alone.  Nothing to do for a complete scan.
 __global__ void __launch_bounds__(256)
 hjd_k_ss_fill_tail(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __restrict__ ss, int n_ss,
-                   const uint32_t* __restrict__ prefix, int16_t* __restrict__ coef, uint8_t* __restrict__ blk_last)
+                   const uint32_t* __restrict__ prefix, int16_t* __restrict__ coef)
 {
     // one warp per image: nothing but two loads for a complete scan
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -916,19 +907,15 @@ hjd_k_ss_fill_tail(const HjdImageDesc* __restrict__ imgs, const HjdSsImage* __re
     const uint64_t started = prefix[s.sub_base + s.n_subs] - prefix[s.sub_base];
     const uint64_t n_blocks = d->n_blocks;
     if (started >= n_blocks) return;
-    // a zero block = a zero first sector and "ends at index 0"
-    for (uint64_t bz = started + lane; bz < n_blocks; bz += 32) {
-        uint4* out = (uint4*)coef + (d->block_base + bz) * 8;
-        out[0] = make_uint4(0, 0, 0, 0);
-        out[1] = make_uint4(0, 0, 0, 0);
-        blk_last[d->block_base + bz] = 0;
-    }
+    uint4* out = (uint4*)coef + (d->block_base + started) * 8;
+    const uint64_t n16 = (n_blocks - started) * 8;
+    for (uint64_t i = lane; i < n16; i += 32) out[i] = make_uint4(0, 0, 0, 0);
 }
 
 cudaError_t hjd_launch_ss_fill_tail(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, const uint32_t* prefix,
-                                    int16_t* coef, uint8_t* blk_last, cudaStream_t st)
+                                    int16_t* coef, cudaStream_t st)
 {
     if (n_ss <= 0) return cudaSuccess;
-    hjd_k_ss_fill_tail<<<(n_ss + 7) / 8, 256, 0, st>>>(imgs, ss, n_ss, prefix, coef, blk_last);
+    hjd_k_ss_fill_tail<<<(n_ss + 7) / 8, 256, 0, st>>>(imgs, ss, n_ss, prefix, coef);
     return cudaGetLastError();
 }

@@ -42,8 +42,8 @@ cudaError_t hjd_launch_ss_write(const HjdImageDesc* imgs, const HjdTableSet* tse
                                 const HjdSsWork* work, const HjdSsSeg* segs, int n_work, const uint8_t* dst,
                                 const uint32_t* dlen,
                                 uint32_t n_subs_total, const uint64_t* x, const uint32_t* prefix, int16_t* coef,
-                                uint8_t* blk_last, int32_t* status, cudaStream_t st);
+                                int32_t* status, cudaStream_t st);
 
 // Zero the blocks of truncated scans that no sub-sequence started (prefix as for hjd_launch_ss_write).
 cudaError_t hjd_launch_ss_fill_tail(const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss, const uint32_t* prefix,
-                                    int16_t* coef, uint8_t* blk_last, cudaStream_t st);
+                                    int16_t* coef, cudaStream_t st);

@@ -184,14 +184,9 @@ uint64_t hjd_batch_plane_bytes(const hjd_batch* b);
 uint64_t hjd_batch_scan_bytes(const hjd_batch* b);    /* sum of entropy-coded bytes */
 uint64_t hjd_batch_pixels(const hjd_batch* b);        /* sum of width*height */
 
-/* Device pointers of the result slabs (valid until the next upload / destroy).
- * The coefficient slab is int16 [block][64] in zig-zag order, but a block is WRITTEN only up to the 32-byte
- * sector of its last non-zero coefficient, whose zig-zag index is block_last[block] (one byte per block);
- * the bytes behind it are undefined until hjd_batch_densify_coef() zeroes them (the downloads below do). */
+/* Device pointers of the result slabs (valid until the next upload / destroy). */
 void* hjd_batch_device_rgb(hjd_batch* b);
 void* hjd_batch_device_coef(hjd_batch* b);
-void* hjd_batch_device_block_last(hjd_batch* b);
-int   hjd_batch_densify_coef(hjd_batch* b);            /* asynchronous on the batch stream */
 void* hjd_batch_device_planes(hjd_batch* b);
 
 /* Device -> host copies (synchronous with respect to the batch stream). */
@@ -200,7 +195,6 @@ int  hjd_batch_download_image(hjd_batch* b, int i, uint8_t* dst /* w*h*3 */);
 int  hjd_batch_download_coef(hjd_batch* b, int16_t* dst /* hjd_batch_coef_bytes */);
 uint64_t hjd_batch_bmp_bytes(const hjd_batch* b, int i);            /* HJD_FLAG_BMP_OUT: size of image i's BMP file (0: none) */
 int  hjd_batch_download_bmp(hjd_batch* b, int i, uint8_t* dst /* hjd_batch_bmp_bytes(i) */);
-int  hjd_batch_download_block_last(hjd_batch* b, uint8_t* dst /* one byte per block: last zig-zag index */);
 int  hjd_batch_download_image_coef(hjd_batch* b, int i, int16_t* dst /* n_blocks*64 */);   /* one image of the slab */
 int  hjd_batch_download_planes(hjd_batch* b, uint8_t* dst /* hjd_batch_plane_bytes */);
 
