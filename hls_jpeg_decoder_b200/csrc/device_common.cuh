@@ -12,7 +12,7 @@ __host__ __device__ __forceinline__ uint32_t hjd_sym_fields(uint32_t len, uint32
     const uint32_t size = sym & 15u, run = sym >> 4;
     if (!is_ac) return HJD_SYM_FIELDS(len, size, 1);                          // DC: loadjpg.cpp:616-667
     if (size) return HJD_SYM_FIELDS(len, size, run + 1);                      // loadjpg.cpp:778-806
-    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0));      // EOB / ZRL / ignored, 771-775
+    return HJD_SYM_FIELDS(len, 0, run == 0 ? 63 : (run == 15 ? 16 : 0));      // EOB / ZRL / ignored, 771-775
 }
 
 __device__ __forceinline__ uint32_t hjd_lds_u16(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }

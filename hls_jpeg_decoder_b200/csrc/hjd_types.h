@@ -17,7 +17,8 @@
 // so the kernels do no per-symbol case analysis:
 //   lut[peek >> (16 - LUT_BITS)] = len | size << 5 | kadv << 9      (16 bits; 0: code longer than LUT_BITS)
 //     len   code length (1..16); size = number of value bits that follow (0..15)
-//     kadv  advance of the zig-zag index: DC 1; AC run+1; EOB 64; ZRL 16; other size-0 symbols 0 (ignored)
+//     kadv  advance of the zig-zag index: DC 1; AC run+1; EOB 63 (k >= 1 in an AC position, so the block ends);
+//           ZRL 16; other size-0 symbols 0 (ignored)
 //   A coefficient is written at (k + kadv - 1) iff size != 0: a DC symbol with size 0 adds nothing to
 //   the predictor, and the output block is zero-filled beforehand.
 //   longer codes (second level): a first-level entry with len == 0 points at a sub-table:
@@ -26,8 +27,9 @@
 //     One more shared-memory load instead of a search over the lengths: with ~12 symbols per block some
 //     lane of a warp holds a long code on every other step.
 //   no such code (either level): HJD_BAD_ENTRY = one bit consumed, no value, zig-zag advance 127 -- the
-//     block ends there; an advance above 64 is how the kernels recognise it (kernel 1a stops the interval,
-//     kernel 1b flags the image and carries on, identically in all of its passes).
+//     block ends there, and it ends with k >= 127, which no decodable block can (63 + 63 at most): that is
+//     how the kernels recognise it, once per block instead of once per symbol (kernel 1a stops the
+//     interval, kernel 1b flags the image and carries on, identically in all of its passes).
 #define HJD_SYM_FIELDS(len, size, kadv) ((uint32_t)(len) | (uint32_t)(size) << 5 | (uint32_t)(kadv) << 9)
 #define HJD_BAD_ENTRY   HJD_SYM_FIELDS(1, 0, 127)
 #define HJD_LUT2_SIZE   512                   // canonical codes: at most 256 (one entry per long code) + 126 (sub-tables that straddle a change of length)

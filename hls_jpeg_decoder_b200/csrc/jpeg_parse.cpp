@@ -186,7 +186,7 @@ static uint32_t sym_fields(uint32_t len, uint32_t sym, bool is_ac)
     const uint32_t size = sym & 15u, run = sym >> 4;
     if (!is_ac) return HJD_SYM_FIELDS(len, size, 1);
     if (size) return HJD_SYM_FIELDS(len, size, run + 1);
-    return HJD_SYM_FIELDS(len, 0, run == 0 ? 64 : (run == 15 ? 16 : 0));
+    return HJD_SYM_FIELDS(len, 0, run == 0 ? 63 : (run == 15 ? 16 : 0));
 }
 
 bool hjd_build_huff_table(const HjdRawHuff& raw, bool is_ac, HjdHuffTable* t)

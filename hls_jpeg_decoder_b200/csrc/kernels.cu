@@ -414,8 +414,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
                         if (kpos <= 63u) hjd_sts_u16_sync(my_slot + ((kpos << 1) ^ swz), (uint32_t)val);
                         else flags |= HJD_ST_COEF_RANGE;                                   // loadjpg.cpp:780-783
                     }
-                    k += (int)kadv;                      // EOB: +64, ZRL: +16 (loadjpg.cpp:771-775)
-                    if (kadv > 64u) { dead = true; flags |= HJD_ST_BAD_CODE; }             // no such code: the interval ends here
+                    k += (int)kadv;                      // EOB: +63, ZRL: +16 (loadjpg.cpp:771-775)
                     done_block = k >= 64;
                 }
             }
@@ -423,6 +422,7 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
         // ---- block hand-over ---------------------------------------------------------------
         uint32_t flush_blk = 0;
         if (done_block) {
+            if (k >= 127) { dead = true; flags |= HJD_ST_BAD_CODE; }      // HJD_BAD_ENTRY: no such code, the interval ends here
             if (!dead) {                                  // DCT[0] = data + prevDC in int16 (loadjpg.cpp:664-665)
                 p0 = (int)(short)(p0 + (int)(short)hjd_lds_u16_sync(my_slot + swz));
                 hjd_sts_u16_sync(my_slot + swz, (uint32_t)p0);
@@ -672,44 +672,38 @@ __device__ __forceinline__ void hjd_idct_block(const uint4* __restrict__ cp, con
 #pragma unroll
     for (int y = 0; y < 8; y++) { row_lo[y] = 0; row_hi[y] = 0; }
     uint32_t near_lo = 0, near_hi = 0;             // bit (8y + x)
-#define HJD_COLUMN(X)                                                                                          \
+#define HJD_COLUMN_PAIR(X)                                                                                     \
     {                                                                                                          \
-        float2 r[4];                                                                                           \
-        if (cls <= 1) hjd_pass1_column<20, X>(bp2, r);                                                         \
-        else hjd_pass1_column<63, X>(bp2, r);                                                                  \
+        float2 ra[4], rb[4];                                                                                   \
+        if (cls <= 1) { hjd_pass1_column<20, X>(bp2, ra); hjd_pass1_column<20, (X) + 1>(bp2, rb); }            \
+        else          { hjd_pass1_column<63, X>(bp2, ra); hjd_pass1_column<63, (X) + 1>(bp2, rb); }            \
         _Pragma("unroll")                                                                                      \
         for (int y = 0; y < 8; y++) {                                                                          \
             /* pass 2: even and odd vertical frequencies accumulate in the two halves; the table carries the */ \
             /* 0.25 (0.25 * fl(s) == fl(0.25 * s): scaling by a power of two commutes with rounding)         */ \
-            float2 a2 = __fmul2_rn(r[0], cosp[y * 4]);                                                         \
+            float2 a2 = __fmul2_rn(ra[0], cosp[y * 4]), b2 = __fmul2_rn(rb[0], cosp[y * 4]);                   \
             _Pragma("unroll")                                                                                  \
-            for (int vp = 1; vp < 4; vp++) a2 = __ffma2_rn(r[vp], cosp[y * 4 + vp], a2);                       \
-            const float h = a2.x + a2.y;                                                                       \
-            /* rint(h) as (h + 1.5*2^23) - 1.5*2^23 (|h| < 2^22 whenever the window is in use): two FADDs     */ \
-            /* instead of an FRND on the conversion unit (ncu: pipe_xu as loaded as the FMA pipe)            */ \
-            const float hr = __fadd_rn(__fadd_rn(h, 12582912.0f), -12582912.0f);                               \
-            const bool nearint = fabsf(__fadd_rn(h, -hr)) <= win;                                              \
-            iv[y][(X) & 1] = __float2int_rz(h);    /* (int)(0.25*sum), loadjpg.cpp:123 */                      \
-            if (y < 4) { if (nearint) near_lo |= 1u << (8 * y + (X)); }                                        \
-            else       { if (nearint) near_hi |= 1u << (8 * (y - 4) + (X)); }                                  \
+            for (int vp = 1; vp < 4; vp++) {                                                                   \
+                a2 = __ffma2_rn(ra[vp], cosp[y * 4 + vp], a2);                                                 \
+                b2 = __ffma2_rn(rb[vp], cosp[y * 4 + vp], b2);                                                 \
+            }                                                                                                  \
+            const float2 h2 = make_float2(a2.x + a2.y, b2.x + b2.y);                                           \
+            /* rint(h) as (h + 1.5*2^23) - 1.5*2^23 (|h| < 2^22 whenever the window is in use), for the two  */ \
+            /* columns at once with packed adds: no FRND on the conversion unit, half the issue slots        */ \
+            const float2 hr2 = __fadd2_rn(__fadd2_rn(h2, make_float2(12582912.0f, 12582912.0f)),               \
+                                          make_float2(-12582912.0f, -12582912.0f));                            \
+            const float2 d2 = __fadd2_rn(h2, make_float2(-hr2.x, -hr2.y));                                     \
+            const bool near_a = fabsf(d2.x) <= win, near_b = fabsf(d2.y) <= win;                               \
+            const int ia = __float2int_rz(h2.x), ib = __float2int_rz(h2.y);   /* (int)(0.25*sum), loadjpg.cpp:123 */ \
+            if (y < 4) { if (near_a) near_lo |= 1u << (8 * y + (X)); if (near_b) near_lo |= 1u << (8 * y + (X) + 1); }             \
+            else       { if (near_a) near_hi |= 1u << (8 * (y - 4) + (X)); if (near_b) near_hi |= 1u << (8 * (y - 4) + (X) + 1); } \
+            if ((X) < 4) row_lo[y] = hjd_pack_sat_s8(ib, ia, row_lo[y]);                                       \
+            else         row_hi[y] = hjd_pack_sat_s8(ib, ia, row_hi[y]);                                       \
         }                                                                                                      \
     }
-#define HJD_PACK(XP)                                                                                           \
-    _Pragma("unroll")                                                                                          \
-    for (int y = 0; y < 8; y++) {                                                                              \
-        if ((XP) < 2) row_lo[y] = hjd_pack_sat_s8(iv[y][1], iv[y][0], row_lo[y]);                              \
-        else          row_hi[y] = hjd_pack_sat_s8(iv[y][1], iv[y][0], row_hi[y]);                              \
-    }
-    {
-        int iv[8][2];
-        // pairs (2,3) (0,1) (6,7) (4,5): high half-word first
-        HJD_COLUMN(2) HJD_COLUMN(3) HJD_PACK(1)
-        HJD_COLUMN(0) HJD_COLUMN(1) HJD_PACK(0)
-        HJD_COLUMN(6) HJD_COLUMN(7) HJD_PACK(3)
-        HJD_COLUMN(4) HJD_COLUMN(5) HJD_PACK(2)
-    }
-#undef HJD_COLUMN
-#undef HJD_PACK
+    // pairs (2,3) (0,1) (6,7) (4,5): high half-word first
+    HJD_COLUMN_PAIR(2) HJD_COLUMN_PAIR(0) HJD_COLUMN_PAIR(6) HJD_COLUMN_PAIR(4)
+#undef HJD_COLUMN_PAIR
     if (a_ac + a_dc >= 1.0e5f) { near_lo = 0xFFFFFFFFu; near_hi = 0xFFFFFFFFu; }
 
 #pragma unroll

@@ -348,7 +348,7 @@ struct SsBits {
 // One Huffman symbol from the window (hi:lo): the fields of hjd_sym_fields plus the extended value.
 // An undecodable code consumes one bit and ends the block (HJD_BAD_ENTRY) so that every path makes progress;
 // the synchronisation rounds and the write pass must agree on this rule, which is why they share this code.
-struct SsSym { uint32_t used, size, kadv; int val; bool bad; };
+struct SsSym { uint32_t used, size, kadv; int val; };
 
 __device__ __forceinline__ SsSym ss_symbol(uint32_t t, uint32_t hi, uint32_t lo, bool is_ac)
 {
@@ -357,7 +357,6 @@ __device__ __forceinline__ SsSym ss_symbol(uint32_t t, uint32_t hi, uint32_t lo,
     const uint32_t len = e & 31u;
     s.size = (e >> 5) & 15u;
     s.kadv = (e >> 9) & 127u;
-    s.bad = s.kadv > 64u;
     const uint32_t after = __funnelshift_l(lo, hi, len);
     const uint32_t v = hjd_shr(after, 32u - s.size);
     const int neg = ~((int)after >> 31);
@@ -525,7 +524,7 @@ cudaError_t hjd_launch_ss_spec(const HjdImageDesc* imgs, const HjdTableSet* tset
 // not raise it.  (The first version launched one kernel per round and had the host read a flag after
 // each: a stream synchronisation per round, in the middle of the hot path.)
 // ctl[0] barrier arrivals, ctl[1] last round (1-based) with work, ctl[2] rounds executed (bit 31: the
-// round limit was hit, which the induction argument above rules out), all zero at launch.
+// round limit was hit, which the induction argument above rules out), ctl[3] work-item counter; all zero at launch.
 __device__ __forceinline__ uint64_t ss_ld64(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
 __device__ __forceinline__ void ss_st64(uint64_t* p, uint64_t v) { __stcg((unsigned long long*)p, (unsigned long long)v); }
 
@@ -549,8 +548,19 @@ hjd_k_ss_sync(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restri
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t loaded_set = 0xFFFFFFFFu;                               // table set in s_tab (CTA-uniform)
 
+    __shared__ int s_wi;
     for (uint32_t round = 1;; round++) {
-        for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        // Work items are handed out through one counter (ctl[3]) that is never reset: in every round each CTA
+        // draws items until its draw is past the end, so a round advances the counter by n_work + gridDim.x
+        // exactly.  (Static striding left the CTAs that happened to own the ranges with many wrong entry
+        // states working long after the others: the first round is where nearly all the time goes.)
+        const uint32_t round_base = (round - 1u) * ((uint32_t)n_work + gridDim.x);
+        for (;;) {
+            __syncthreads();                                         // s_wi, s_tab and the windows are free
+            if (threadIdx.x == 0) s_wi = (int)(atomicAdd(&ctl[3], 1u) - round_base);
+            __syncthreads();
+            const int wi = s_wi;
+            if (wi >= n_work) break;
             const HjdSsWork wk = work[wi];
             const bool has_range = (uint32_t)warp < wk.n_segs;       // this warp's range (possibly of another image than its neighbours')
             const HjdSsSeg sg = segs[wk.first_seg + (has_range ? warp : 0)];
@@ -628,7 +638,6 @@ hjd_k_ss_sync(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restri
                 }
             }
             for (int j = kov + lane; j < n_act; j += 32) { ss_st64(e_arr + g0 + j, sE[j]); ss_st64(x_arr + g0 + j, sX[j]); }
-            __syncthreads();                                         // s_tab / windows are reused by the next item
         }
         // ---- grid-wide barrier, then: did anybody have work in this round? ---------------------
         __syncthreads();
@@ -779,9 +788,6 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                     br.ensure();
                     const bool is_ac = k != 0;
                     const SsSym sy = ss_symbol(t0 + (is_ac ? kTabBytes : 0u), br.hi, br.lo, is_ac);
-                    // only inside an owned (real) block: what a thread skips may be the padding after the
-                    // last block, decoded as if a block followed, and every real block has an owner who sees all of it
-                    if (sy.bad && owned) flags |= HJD_ST_BAD_CODE;
                     br.skip(sy.used);
                     rem -= (int)sy.used;
                     const uint32_t kpos = (uint32_t)k + sy.kadv - 1u;
@@ -791,6 +797,10 @@ hjd_k_ss_write(const HjdImageDesc* __restrict__ imgs, const HjdTableSet* __restr
                     }
                     k += (int)sy.kadv;
                     if (k >= 64) {
+                        // k >= 127: HJD_BAD_ENTRY, no such code.  Flagged only inside an owned (real) block: what a
+                        // thread skips may be the padding after the last block, decoded as if a block followed,
+                        // and every real block has an owner who sees all of it
+                        if (k >= 127 && owned) flags |= HJD_ST_BAD_CODE;
                         if (owned) done_block = true;             // hand-over below
                         else {                                    // the foreign block is over: the next one is mine
                             owned = true;

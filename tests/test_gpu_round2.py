@@ -288,3 +288,39 @@ def test_pipelined_file_to_bmp_conversion(hjd, port, tmp_path):
             want = port.bmp24_bytes(port.decode(cases.small_cases()[names[k]])["rgb"])
             assert open(dst, "rb").read() == want, (devices, chunk, names[k])
             k += 1
+
+
+def test_against_the_reference_itself(hjd, refbind, tmp_path):
+    """VERDICT r1 (weak 2): the GPU path against the REFERENCE's own code (oracle/_ref, compiled from
+    /root/reference/src by oracle/build_ref.sh), not its restatement: unmodified JpegParseHeader + JpegDecodeHW
+    (mode 0) for restart-free colour files, the reference's block-level code with MCU-counted restarts and
+    grayscale by extension (mode 1) otherwise -- coefficients, planes, RGB and the BMP file, bit for bit."""
+    from tools.gen_jpegs import encode_jpeg, make_c2, synth_rgb
+    base = cases.small_cases()
+    files = {n: base[n] for n in ("444_64x48_q85", "422_64x48_q85", "420_37x53_q75", "420_100x70_ri2", "444_opt_ri5",
+                                  "440_61x35_ri3", "gray_33x9_ri4", "420_noise_q100", "420_gradient_q50", "444_1x1")}
+    files["420_512x384_q90"] = encode_jpeg(synth_rgb(512, 384, 77), 90, "4:2:0")
+    files["c2_1080p_ri8"] = make_c2(5)
+    files["c2_1080p_twin"] = make_c2(5, restart=False)
+    names = list(files)
+    with hjd.BatchDecoder(0, hjd.FLAG_KEEP_PLANES) as d1, hjd.BatchDecoder(0) as d2, hjd.BatchDecoder(0, hjd.FLAG_BMP_OUT) as d3:
+        for d in (d1, d2, d3):
+            d.upload([files[n] for n in names])
+            d.decode()
+            assert (d.status() == 0).all(), d.status()
+        coef, slab = d1.coefficients(), d1.plane_slab()
+        for i, n in enumerate(names):
+            r = refbind.decode(files[n], mode=1)
+            assert r["rc"] == 0, n
+            assert np.array_equal(d1.image_coefficients(i, coef), r["coef"]), n
+            for a, b in zip(d1.planes(i, slab), r["planes"]):
+                if a is not None:
+                    assert np.array_equal(a, b), n
+            assert np.array_equal(d1.rgb(i), r["rgb"]) and np.array_equal(d2.rgb(i), r["rgb"]), n
+            inf = d1.info(i)
+            if inf.restart_interval == 0 and inf.ncomp == 3:          # what the unmodified reference can decode
+                r0 = refbind.decode(files[n], mode=0)
+                assert r0["rc"] == 0 and np.array_equal(d2.rgb(i), r0["rgb"]), n
+            p = str(tmp_path / "ref.bmp")
+            refbind.write_bmp24(p, r["rgb"])                           # the reference's own WriteBMP24
+            assert d3.bmp(i) == open(p, "rb").read(), n

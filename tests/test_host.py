@@ -127,7 +127,7 @@ def _fields(length, sym, is_ac):
         return length | size << 5 | 1 << 9
     if size:
         return length | size << 5 | (run + 1) << 9
-    return length | (64 if run == 0 else 16 if run == 15 else 0) << 9
+    return length | (63 if run == 0 else 16 if run == 15 else 0) << 9
 
 
 def test_two_level_huffman_tables_match_the_canonical_code_walk(hjd):
