@@ -94,6 +94,13 @@ struct Chunk {
     uint64_t rgb_lo = 0, rgb_hi = 0;
     uint32_t max_blocks = 0, max_w = 0, max_h = 0, max_mcus = 0;
     uint64_t blocks = 0;
+    // kernel 1b (restart-free images of this chunk): ranges in the batch-wide index spaces, each with a gap of
+    // one entry behind it so that the chunks' prefix sums (which append a sentinel) can run side by side
+    uint32_t ss0 = 0, ss1 = 0;                // entries of b->ss
+    uint32_t sub0 = 0, n_subs = 0;            // sub-sequences
+    uint32_t ck0 = 0, n_ck = 0;               // 16-byte de-stuffing chunks
+    uint32_t sw0 = 0, sw1 = 0, sf0 = 0, sf1 = 0;   // work items: speculative / write kernels, synchronisation kernel
+    uint32_t ss_range = 0;                    // sub-sequences per warp in the synchronisation kernel
 };
 
 #define HJD_NSTREAMS 3
@@ -126,10 +133,9 @@ struct hjd_batch {
     std::vector<HjdSsImage> ss;                 // images on the self-synchronising path (kernel 1b)
     std::vector<HjdSsWork> sswork;       // one entry per CTA: speculative / write kernels, then synchronisation rounds
     std::vector<HjdSsSeg> sssegs;        // their segments
-    size_t n_sswork_main = 0;            // entries of the first list
-    uint32_t ss_range = 0;               // sub-sequences per warp in the synchronisation rounds
     uint32_t ss_range_req = 0;           // 0 = automatic
-    uint32_t ss_subs = 0, ss_chunks = 0;
+    uint32_t ss_subs = 0, ss_chunks = 0;          // batch-wide totals, including one gap per chunk
+    uint32_t ss_tmp_stride = 0;                  // words of prefix-sum scratch per chunk
     uint64_t ss_dst_bytes = 0;
     bool ss_ran = false;                        // the last decode ran kernel 1b (its round count is in d_flag)
     int max_sync_ctas = 1;                      // grid limit of the cooperative synchronisation kernel on this device
@@ -405,18 +411,13 @@ static int upload_common(hjd_batch* b, bool chunked)
             HjdSsImage si;
             memset(&si, 0, sizeof si);
             si.img = (uint32_t)i;
-            si.sub_base = b->ss_subs;
             si.n_subs = (uint32_t)((ps.scan_len + HJD_SS_SUB_BYTES - 1) / HJD_SS_SUB_BYTES);
             si.lead = (uint32_t)(d.scan_off & 15);
-            si.chunk_base = b->ss_chunks;
             si.n_chunks = (uint32_t)((ps.scan_len + si.lead + 15) / 16);
             si.dst_off = b->ss_dst_bytes;
             d.n_intervals = 0;
-            d.sub_base = si.sub_base;
             d.n_subs = si.n_subs;
-            b->ss.push_back(si);
-            b->ss_subs += si.n_subs;
-            b->ss_chunks += si.n_chunks;
+            b->ss.push_back(si);                 // sub_base / chunk_base: after the chunk plan (below)
             b->ss_dst_bytes += align_up(ps.scan_len + HJD_SS_SLACK + 16, 256);   // + 16: the slack is zeroed from the next 16-byte boundary
         }
         d.table_set = tset; d.quant_set = qset;
@@ -552,65 +553,91 @@ static int upload_common(hjd_batch* b, bool chunked)
     CU(b->d_rgb.ensure(b->rgb_bytes + 256));
     CU(b->d_status.ensure(sizeof(int32_t) * (size_t)(n + 1)));
     if (b->flags & HJD_FLAG_KEEP_PLANES) CU(b->d_planes.ensure(b->plane_bytes + 256));
-    // Work lists of kernel 1b.  Images are grouped by table set (batch order kept inside a group) and their
-    // sub-sequences packed into CTAs as segments, so small restart-free images share CTAs.
-    // Synchronisation rounds: one range per warp; longer ranges make the re-decode lists denser, shorter
-    // ones give more independent warps: pick by the amount of work.  That list is staged behind the first.
+    // Kernel 1b, chunk by chunk (so that restart-free images pipeline like the rest: nothing in it needs the
+    // host any more).  Index spaces are batch-wide with one spare entry after every chunk.  Inside a chunk the
+    // images are grouped by table set (batch order kept inside a group) and their sub-sequences packed into
+    // CTAs as segments, so small restart-free images share CTAs.  Synchronisation kernel: one range per warp;
+    // longer ranges make the re-decode lists denser, shorter ones give more independent warps: by the amount
+    // of work in the chunk.
     {
-        std::vector<uint32_t> order(b->ss.size());
-        for (size_t k = 0; k < order.size(); k++) order[k] = (uint32_t)k;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-            return b->imgs[b->ss[x].img].table_set < b->imgs[b->ss[y].img].table_set;
-        });
-        HjdSsWork w{0, 0, 0, 0};
-        auto flush = [&]() {
-            if (w.n_subs) b->sswork.push_back(w);
-            w = HjdSsWork{(uint32_t)b->sssegs.size(), 0, 0, 0};
-        };
-        flush();
-        for (uint32_t k : order) {
-            const uint32_t ts = b->imgs[b->ss[k].img].table_set;
-            if (w.n_subs && w.table_set != ts) flush();
-            uint32_t left = b->ss[k].n_subs, f = 0;
-            while (left) {
-                if (w.n_subs == HJD_SS_THREADS) flush();
-                w.table_set = ts;
-                const uint32_t take = left < (HJD_SS_THREADS - w.n_subs) ? left : (HJD_SS_THREADS - w.n_subs);
-                b->sssegs.push_back(HjdSsSeg{k, f, w.n_subs, take});
-                w.n_segs++; w.n_subs += take; f += take; left -= take;
+        size_t k0 = 0;
+        uint32_t max_scan = 0;
+        for (Chunk& c : b->chunks) {
+            c.ss0 = (uint32_t)k0;
+            c.sub0 = b->ss_subs;
+            c.ck0 = b->ss_chunks;
+            while (k0 < b->ss.size() && (int)b->ss[k0].img < c.img1) {
+                HjdSsImage& si = b->ss[k0++];
+                si.sub_base = b->ss_subs;
+                si.chunk_base = b->ss_chunks;
+                b->imgs[si.img].sub_base = si.sub_base;
+                b->ss_subs += si.n_subs;
+                b->ss_chunks += si.n_chunks;
             }
-        }
-        flush();
-        b->n_sswork_main = b->sswork.size();
-        b->ss_range = b->ss_range_req ? b->ss_range_req : b->ss_subs >= 400000 ? 256 : b->ss_subs >= 150000 ? 128 : 64;
-        for (uint32_t k : order) {
-            const uint32_t ts = b->imgs[b->ss[k].img].table_set;
-            for (uint32_t f = 0; f < b->ss[k].n_subs; f += b->ss_range) {
-                if (w.n_segs == HJD_SS_FIX_WARPS || (w.n_segs && w.table_set != ts)) flush();
-                w.table_set = ts;
-                const uint32_t take = b->ss[k].n_subs - f < b->ss_range ? b->ss[k].n_subs - f : b->ss_range;
-                b->sssegs.push_back(HjdSsSeg{k, f, 0, take});
-                w.n_segs++; w.n_subs += take;
+            c.ss1 = (uint32_t)k0;
+            c.n_subs = b->ss_subs - c.sub0;
+            c.n_ck = b->ss_chunks - c.ck0;
+            b->ss_subs += 1;                     // the gaps
+            b->ss_chunks += 1;
+            if (c.n_ck + 1 > max_scan) max_scan = c.n_ck + 1;
+            if (4 * c.n_subs + 2 > max_scan) max_scan = 4 * c.n_subs + 2;
+
+            std::vector<uint32_t> order;
+            for (uint32_t k = c.ss0; k < c.ss1; k++) order.push_back(k);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+                return b->imgs[b->ss[x].img].table_set < b->imgs[b->ss[y].img].table_set;
+            });
+            HjdSsWork w{0, 0, 0, 0};
+            auto flush = [&]() {
+                if (w.n_subs) b->sswork.push_back(w);
+                w = HjdSsWork{(uint32_t)b->sssegs.size(), 0, 0, 0};
+            };
+            flush();
+            c.sw0 = (uint32_t)b->sswork.size();
+            for (uint32_t k : order) {
+                const uint32_t ts = b->imgs[b->ss[k].img].table_set;
+                if (w.n_subs && w.table_set != ts) flush();
+                uint32_t left = b->ss[k].n_subs, f = 0;
+                while (left) {
+                    if (w.n_subs == HJD_SS_THREADS) flush();
+                    w.table_set = ts;
+                    const uint32_t take = left < (HJD_SS_THREADS - w.n_subs) ? left : (HJD_SS_THREADS - w.n_subs);
+                    b->sssegs.push_back(HjdSsSeg{k, f, w.n_subs, take});
+                    w.n_segs++; w.n_subs += take; f += take; left -= take;
+                }
             }
+            flush();
+            c.sw1 = c.sf0 = (uint32_t)b->sswork.size();
+            c.ss_range = b->ss_range_req ? b->ss_range_req : c.n_subs >= 400000 ? 256 : c.n_subs >= 150000 ? 128 : 64;
+            if (!b->ss_range_req && HJD_SS_FIX_MAXR >= 512 && c.n_subs >= 1000000) c.ss_range = 512;
+            for (uint32_t k : order) {
+                const uint32_t ts = b->imgs[b->ss[k].img].table_set;
+                for (uint32_t f = 0; f < b->ss[k].n_subs; f += c.ss_range) {
+                    if (w.n_segs == HJD_SS_FIX_WARPS || (w.n_segs && w.table_set != ts)) flush();
+                    w.table_set = ts;
+                    const uint32_t take = b->ss[k].n_subs - f < c.ss_range ? b->ss[k].n_subs - f : c.ss_range;
+                    b->sssegs.push_back(HjdSsSeg{k, f, 0, take});
+                    w.n_segs++; w.n_subs += take;
+                }
+            }
+            flush();
+            c.sf1 = (uint32_t)b->sswork.size();
         }
-        flush();
+        b->ss_tmp_stride = max_scan / 2048 + 8;
     }
 
     if (!b->ss.empty()) {
-        uint32_t scan_n = b->ss_chunks + 1;
-        if (b->ss_subs + 1 > scan_n) scan_n = b->ss_subs + 1;
-        if (4 * b->ss_subs + 2 > scan_n) scan_n = 4 * b->ss_subs + 2;
         CU(b->d_ss.ensure(sizeof(HjdSsImage) * b->ss.size()));
         CU(b->d_sswork.ensure(sizeof(HjdSsWork) * b->sswork.size()));
         CU(b->d_sssegs.ensure(sizeof(HjdSsSeg) * (b->sssegs.size() + 1)));
         CU(b->d_destuff.ensure(b->ss_dst_bytes + 256));
         CU(b->d_dlen.ensure(sizeof(uint32_t) * b->ss.size()));
         CU(b->d_counts.ensure(sizeof(uint32_t) * ((size_t)b->ss_chunks + 2)));
-        CU(b->d_scantmp.ensure(sizeof(uint32_t) * ((size_t)scan_n / 2048 + 4)));
+        CU(b->d_scantmp.ensure(sizeof(uint32_t) * (size_t)b->ss_tmp_stride * (b->chunks.size() + 1)));
         CU(b->d_ssE0.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssX.ensure(sizeof(uint64_t) * (size_t)b->ss_subs));
         CU(b->d_ssnb.ensure(sizeof(uint32_t) * (4 * (size_t)b->ss_subs + 4)));
-        CU(b->d_flag.ensure(sizeof(uint32_t) * 4));
+        CU(b->d_flag.ensure(sizeof(uint32_t) * 4 * (b->chunks.size() + 1)));
     }
 
     // metadata: one pinned staging block, then async copies
@@ -737,54 +764,57 @@ extern "C" int hjd_batch_set_selfsync_range(hjd_batch* b, int range)
 {
     if (!b) return fail(HJD_ERR_ARG, "hjd_batch_set_selfsync_range", "null batch");
     if (range < 0 || range > HJD_SS_FIX_MAXR || (range & 31))
-        return fail(HJD_ERR_ARG, "hjd_batch_set_selfsync_range", "range must be 0 or a multiple of 32 up to 256");
+        return fail(HJD_ERR_ARG, "hjd_batch_set_selfsync_range", "range must be 0 or a multiple of 32 up to HJD_SS_FIX_MAXR");
     b->ss_range_req = (uint32_t)range;
     return HJD_OK;
 }
 
-// Kernel 1b for all restart-free images of the batch (see selfsync.cu).  Everything is enqueued on `st`;
-// the synchronisation rounds terminate on the device, so the host never waits here.
-static int run_selfsync(hjd_batch* b, cudaStream_t st)
+// Kernel 1b for the restart-free images of one chunk (see selfsync.cu).  Everything is enqueued on `st`; the
+// synchronisation rounds terminate on the device, so the host never waits here.
+static int run_selfsync(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaStream_t st)
 {
-    if (b->ss.empty()) return HJD_OK;
+    if (c.ss1 <= c.ss0) return HJD_OK;
     const uint8_t* arena = (const uint8_t*)b->d_arena.p;
     const HjdImageDesc* imgs = (const HjdImageDesc*)b->d_imgs.p;
     const HjdTableSet* tsets = (const HjdTableSet*)b->d_tsets.p;
     const HjdSsImage* ss = (const HjdSsImage*)b->d_ss.p;
-    const HjdSsWork* work = (const HjdSsWork*)b->d_sswork.p;
-    const int n_ss = (int)b->ss.size(), n_work = (int)b->n_sswork_main;
-    const HjdSsWork* work_fix = work + b->n_sswork_main;
+    const HjdSsWork* work = (const HjdSsWork*)b->d_sswork.p + c.sw0;
+    const HjdSsWork* work_fix = (const HjdSsWork*)b->d_sswork.p + c.sf0;
+    const int n_work = (int)(c.sw1 - c.sw0), n_work_fix = (int)(c.sf1 - c.sf0);
     const HjdSsSeg* segs = (const HjdSsSeg*)b->d_sssegs.p;
-    const int n_work_fix = (int)(b->sswork.size() - b->n_sswork_main);
     uint8_t* dst = (uint8_t*)b->d_destuff.p;
     uint32_t* dlen = (uint32_t*)b->d_dlen.p;
     uint64_t* E = (uint64_t*)b->d_ssE0.p;
     uint64_t* X = (uint64_t*)b->d_ssX.p;
-    uint32_t* cnt = (uint32_t*)b->d_ssnb.p;                       // [4][ss_subs] (+1): starts, DC sums Y/Cb/Cr
-    uint32_t* ctl = (uint32_t*)b->d_flag.p;                       // barrier count, last round with work, rounds run
-    const uint32_t N = b->ss_subs;
+    uint32_t* tmp = (uint32_t*)b->d_scantmp.p + chunk_index * b->ss_tmp_stride;
+    uint32_t* ctl = (uint32_t*)b->d_flag.p + 4 * chunk_index;    // barrier count, last round with work, rounds run, item counter
+    // [4][n_subs] (+ sentinel) counters of this chunk: starts, DC sums Y / Cb / Cr.  The kernels index them with
+    // batch-wide sub-sequence numbers, hence the pointer that is shifted back by the chunk's first one.
+    const uint32_t N = c.n_subs;
+    uint32_t* cnt_region = (uint32_t*)b->d_ssnb.p + 4 * (size_t)c.sub0;
+    uint32_t* cnt = cnt_region - c.sub0;
 
     CU(cudaMemsetAsync(ctl, 0, 4 * sizeof(uint32_t), st));
-    CU(cudaMemsetAsync(cnt + 4 * (size_t)N, 0, sizeof(uint32_t), st));
-    CU(hjd_launch_destuff(arena, imgs, ss, n_ss, b->ss_chunks, (uint32_t*)b->d_counts.p, (uint32_t*)b->d_scantmp.p,
-                          dst, dlen, st));
-    b->launches += 2 + (b->ss_chunks + 1 > 2048 ? 3 : 1);
+    CU(cudaMemsetAsync(cnt_region + 4 * (size_t)N, 0, sizeof(uint32_t), st));
+    CU(hjd_launch_destuff(arena, imgs, ss + c.ss0, (int)(c.ss1 - c.ss0), c.ck0, c.n_ck, (uint32_t*)b->d_counts.p, tmp,
+                          dst, dlen + c.ss0, st));
+    b->launches += 2 + (c.n_ck + 1 > 2048 ? 3 : 1);
     CU(hjd_launch_ss_spec(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, E, X, cnt, st));
     // a chain of wrong entry states can cross one range per round at worst: ranges + a confirming round
     const uint32_t max_rounds = N / 32 + 8;
     CU(hjd_launch_ss_sync(imgs, tsets, ss, work_fix, segs, n_work_fix, dst, dlen, N, E, X, cnt, ctl, max_rounds,
                           b->max_sync_ctas, st));
-    CU(hjd_scan_u32(cnt, 4 * N + 1, (uint32_t*)b->d_scantmp.p, st));              // cnt[] becomes its exclusive prefix
+    CU(hjd_scan_u32(cnt_region, 4 * N + 1, tmp, st));                             // the counters become their exclusive prefix
     CU(hjd_launch_ss_write(imgs, tsets, ss, work, segs, n_work, dst, dlen, N, X, cnt, (int16_t*)b->d_coef.p,
                            (int32_t*)b->d_status.p, st));
-    CU(hjd_launch_ss_fill_tail(imgs, ss, n_ss, cnt, (int16_t*)b->d_coef.p, st));
+    CU(hjd_launch_ss_fill_tail(imgs, ss + c.ss0, (int)(c.ss1 - c.ss0), cnt, (int16_t*)b->d_coef.p, st));
     b->launches += 4 + (4 * N + 1 > 2048 ? 3 : 1);
     b->ss_ran = true;
     return HJD_OK;
 }
 
 // Kernels of one chunk on one stream.  ev != nullptr: record stage boundaries (serial mode only).
-static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent_t* ev)
+static int launch_chunk(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaStream_t st, cudaEvent_t* ev)
 {
     const uint8_t* arena = (const uint8_t*)b->d_arena.p;
     const HjdImageDesc* imgs = (const HjdImageDesc*)b->d_imgs.p;
@@ -796,9 +826,9 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, cudaStream_t st, cudaEvent
                                   (uint32_t*)b->d_slicecnt.p + c.slice0, st));
         b->launches += 1 + (c.slice1 > c.slice0 ? 2 : 0);
     }
-    if (ev) {
-        CU(cudaEventRecord(ev[1], st));
-        int rc = run_selfsync(b, st);          // serial mode: counted in the entropy stage
+    if (ev) CU(cudaEventRecord(ev[1], st));
+    {
+        int rc = run_selfsync(b, c, chunk_index, st);      // counted in the entropy stage
         if (rc) return rc;
     }
     if (c.work1 > c.work0) {
@@ -848,7 +878,7 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
         } else {
             const Chunk& c = b->chunks[0];
             if (h2d) { int rc = copy_files(b, c, main); if (rc) return rc; CU(cudaEventRecord(b->ev[0], main)); }
-            int rc = launch_chunk(b, c, main, b->ev);
+            int rc = launch_chunk(b, c, 0, main, b->ev);
             if (rc) return rc;
         }
         CU(cudaEventRecord(b->ev[4], main));
@@ -856,15 +886,6 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
         return HJD_OK;
     }
     for (int k = 1; k <= 3; k++) CU(cudaEventRecord(b->ev[k], main));     // no per-stage times when chunks overlap
-    if (!b->ss.empty()) {
-        // restart-free images need their bytes before the host-driven sync rounds: copy first
-        if (h2d) {
-            for (const Chunk& c : b->chunks) { int rc = copy_files(b, c, main); if (rc) return rc; }
-            h2d = false;
-        }
-        int rc = run_selfsync(b, main);
-        if (rc) return rc;
-    }
     CU(cudaEventRecord(b->ev_fork, main));
     for (int s = 0; s < HJD_NSTREAMS; s++) CU(cudaStreamWaitEvent(b->aux[s], b->ev_fork, 0));
     // From here on work is in flight on the chunk streams: whatever fails below, they are joined back into
@@ -875,7 +896,7 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
         const Chunk& c = b->chunks[k];
         cudaStream_t st = b->aux[k % HJD_NSTREAMS];
         if (h2d) rc_all = copy_files(b, c, st);
-        if (rc_all == HJD_OK) rc_all = launch_chunk(b, c, st, nullptr);
+        if (rc_all == HJD_OK) rc_all = launch_chunk(b, c, k, st, nullptr);
         if (rc_all == HJD_OK && rgb_host && c.rgb_hi > c.rgb_lo) {
             cudaError_t e = cudaMemcpyAsync(rgb_host + c.rgb_lo, (const uint8_t*)b->d_rgb.p + c.rgb_lo, c.rgb_hi - c.rgb_lo,
                                             cudaMemcpyDeviceToHost, st);
@@ -919,10 +940,13 @@ extern "C" int hjd_batch_selfsync_rounds(hjd_batch* b)
 {
     // rounds the device-side loop ran in the last decode (working rounds + the one that confirmed); syncs
     if (!b || !b->ss_ran || !b->d_flag.p) return 0;
-    uint32_t ctl[4] = {0, 0, 0, 0};
+    std::vector<uint32_t> ctl(4 * b->chunks.size() + 4, 0);
     if (cudaSetDevice(b->device) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess ||
-        cudaMemcpy(ctl, b->d_flag.p, sizeof ctl, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
-    return (int)(ctl[2] & 0x7FFFFFFFu);
+        cudaMemcpy(ctl.data(), b->d_flag.p, 4 * b->chunks.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+    uint32_t most = 0;                                             // the chunk that needed the most rounds
+    for (size_t k = 0; k < b->chunks.size(); k++)
+        if (b->chunks[k].ss1 > b->chunks[k].ss0 && (ctl[4 * k + 2] & 0x7FFFFFFFu) > most) most = ctl[4 * k + 2] & 0x7FFFFFFFu;
+    return (int)most;
 }
 
 extern "C" int hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* o)
@@ -948,9 +972,11 @@ extern "C" int hjd_batch_get_status(hjd_batch* b, int32_t* status)
     CU(cudaMemcpyAsync(status, b->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     if (b->ss_ran) {       // the device-side synchronisation loop reports here if it ever hit its round limit
-        uint32_t ctl[4] = {0, 0, 0, 0};
-        CU(cudaMemcpy(ctl, b->d_flag.p, sizeof ctl, cudaMemcpyDeviceToHost));
-        if (ctl[2] & 0x80000000u) return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
+        std::vector<uint32_t> ctl(4 * b->chunks.size() + 4, 0);
+        CU(cudaMemcpy(ctl.data(), b->d_flag.p, 4 * b->chunks.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < b->chunks.size(); k++)
+            if (b->chunks[k].ss1 > b->chunks[k].ss0 && (ctl[4 * k + 2] & 0x80000000u))
+                return fail(HJD_ERR_STATE, "self-synchronising decode", "did not converge");
     }
     for (size_t i = 0; i < n; i++) {
         if (b->parse_status[i] != 0) status[i] = b->parse_status[i];

@@ -113,7 +113,9 @@ struct HjdScanSlice {
 #ifndef HJD_SS_FIX_WARPS
 #define HJD_SS_FIX_WARPS   4     // warps per CTA of the synchronisation rounds, one range of sub-sequences each
 #endif
+#ifndef HJD_SS_FIX_MAXR
 #define HJD_SS_FIX_MAXR    256   // largest range
+#endif
 #define HJD_SS_FIX_OVERLAP 4     // sub-sequences before a range that its warp re-checks privately
 
 // One per image decoded by the self-synchronising kernels; all index spaces below are global

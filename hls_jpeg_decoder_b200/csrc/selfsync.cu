@@ -172,7 +172,7 @@ __device__ __forceinline__ uint32_t destuff_mask(const uint8_t* a0, uint32_t lc,
 // the chunks of a CTA are consecutive and images are long.
 __device__ __forceinline__ int destuff_image_of(const HjdSsImage* __restrict__ ss, int n_ss, uint32_t t, int* s_first)
 {
-    if (threadIdx.x == 0) *s_first = ss_find_chunk(ss, n_ss, blockIdx.x * blockDim.x);
+    if (threadIdx.x == 0) *s_first = ss_find_chunk(ss, n_ss, t - threadIdx.x);
     __syncthreads();
     int si = *s_first;
     while (si + 1 < n_ss && ss[si + 1].chunk_base <= t) si++;
@@ -181,11 +181,12 @@ __device__ __forceinline__ int destuff_image_of(const HjdSsImage* __restrict__ s
 
 __global__ void __launch_bounds__(256)
 hjd_k_destuff_count(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
-                    const HjdSsImage* __restrict__ ss, int n_ss, uint32_t n_chunks_total,
+                    const HjdSsImage* __restrict__ ss, int n_ss, uint32_t t0, uint32_t n_chunks_total,
                     uint32_t* __restrict__ counts)
 {
+    // chunks [t0, n_chunks_total) of the batch-wide chunk numbering belong to the ss[] images given here
     __shared__ int s_first;
-    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t t = t0 + blockIdx.x * 256 + threadIdx.x;
     const int si = destuff_image_of(ss, n_ss, t < n_chunks_total ? t : n_chunks_total - 1, &s_first);
     if (t >= n_chunks_total) { if (t == n_chunks_total) counts[t] = 0; return; }
     const HjdSsImage s = ss[si];
@@ -201,12 +202,12 @@ hjd_k_destuff_count(const uint8_t* __restrict__ arena, const HjdImageDesc* __res
 // kernel at 260 us per 91 MB.  A warp that straddles two images falls back to byte stores.
 __global__ void __launch_bounds__(256)
 hjd_k_destuff_scatter(const uint8_t* __restrict__ arena, const HjdImageDesc* __restrict__ imgs,
-                      const HjdSsImage* __restrict__ ss, int n_ss, uint32_t n_chunks_total,
+                      const HjdSsImage* __restrict__ ss, int n_ss, uint32_t t0, uint32_t n_chunks_total,
                       const uint32_t* __restrict__ prefix, uint8_t* __restrict__ dst, uint32_t* __restrict__ dlen)
 {
     __shared__ int s_first;
     __shared__ __align__(16) uint8_t s_stage[8][544];
-    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t t = t0 + blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int si = destuff_image_of(ss, n_ss, t < n_chunks_total ? t : n_chunks_total - 1, &s_first);
     const bool in = t < n_chunks_total;
@@ -262,15 +263,16 @@ hjd_k_destuff_scatter(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
 }
 
 cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss,
-                               uint32_t n_chunks_total, uint32_t* counts, uint32_t* scan_tmp,
+                               uint32_t first_chunk, uint32_t n_chunks, uint32_t* counts, uint32_t* scan_tmp,
                                uint8_t* dst, uint32_t* dlen, cudaStream_t st)
 {
-    if (n_ss <= 0 || n_chunks_total == 0) return cudaSuccess;
-    const uint32_t grid = (n_chunks_total + 1 + 255) / 256;
-    hjd_k_destuff_count<<<grid, 256, 0, st>>>(arena, imgs, ss, n_ss, n_chunks_total, counts);
-    cudaError_t e = hjd_scan_u32(counts, n_chunks_total + 1, scan_tmp, st);
+    if (n_ss <= 0 || n_chunks == 0) return cudaSuccess;
+    const uint32_t grid = (n_chunks + 1 + 255) / 256;
+    const uint32_t end = first_chunk + n_chunks;
+    hjd_k_destuff_count<<<grid, 256, 0, st>>>(arena, imgs, ss, n_ss, first_chunk, end, counts);
+    cudaError_t e = hjd_scan_u32(counts + first_chunk, n_chunks + 1, scan_tmp, st);
     if (e != cudaSuccess) return e;
-    hjd_k_destuff_scatter<<<grid, 256, 0, st>>>(arena, imgs, ss, n_ss, n_chunks_total, counts, dst, dlen);
+    hjd_k_destuff_scatter<<<grid, 256, 0, st>>>(arena, imgs, ss, n_ss, first_chunk, end, counts, dst, dlen);
     return cudaGetLastError();
 }
 

@@ -8,9 +8,11 @@
 cudaError_t hjd_scan_u32(uint32_t* data, uint32_t n, uint32_t* tmp, cudaStream_t st);
 
 // De-stuffing pre-pass (FillNBits' FF00 rule, loadjpg.cpp:475-478, applied once, in parallel):
-// counts[] (n_chunks_total + 1 words) is scratch; dst receives the compacted streams, dlen[ss] their lengths.
+// The n_ss images given own the 16-byte chunks [first_chunk, first_chunk + n_chunks) of the batch-wide numbering
+// (HjdSsImage::chunk_base); counts[] is scratch over that range + one sentinel; dst receives the compacted
+// streams, dlen[k] the length of ss[k]'s.
 cudaError_t hjd_launch_destuff(const uint8_t* arena, const HjdImageDesc* imgs, const HjdSsImage* ss, int n_ss,
-                               uint32_t n_chunks_total, uint32_t* counts, uint32_t* scan_tmp,
+                               uint32_t first_chunk, uint32_t n_chunks, uint32_t* counts, uint32_t* scan_tmp,
                                uint8_t* dst, uint32_t* dlen, cudaStream_t st);
 
 // Speculative decode of every sub-sequence (one CTA per `work` entry, HJD_SS_THREADS sub-sequences).
