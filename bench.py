@@ -293,7 +293,7 @@ def single_image_record(hjd, local_rank):
                 os.remove(p)
 
 
-def file_to_bmp_record(hjd, files, local_rank, rank, n_images=256, with_reference=False):
+def file_to_bmp_record(hjd, files, local_rank, rank, n_images=512, with_reference=False):
     """.jpg files on disk -> .bmp files on disk through hjd_convert_jpg_files_multi
     (readers -> chunked GPU decodes in BMP layout -> writers), on a tmpfs so that the number is the
     pipeline's, not a disk's.  One file is checked against the oracle's WriteBMP24 bytes."""
@@ -323,8 +323,13 @@ def file_to_bmp_record(hjd, files, local_rank, rank, n_images=256, with_referenc
         assert all(ok), "file -> bmp conversion failed"
         o = port.decode(files[0], want_planes=False, want_coef=False)
         same = open(outs[0], "rb").read() == port.bmp24_bytes(o["rgb"])
+        # the same pipeline with every output path = /dev/null: everything but the file system's write rate
+        t_null = time.perf_counter()
+        ok_null = hjd.ConvertJpgFiles(ins, ["/dev/null"] * n, device=local_rank)
+        t_null = time.perf_counter() - t_null
         rec = {"images": n, "images_per_s": round(n / t, 1), "MP_per_s": round(n * W * H / 1e6 / t, 1),
                "bmp_GB_per_s": round(n * (W * H * 3 + 54) / t / 1e9, 2), "where": base,
+               "images_per_s_to_dev_null": round(n / t_null, 1) if all(ok_null) else None,
                "bmp_bytes_identical_to_WriteBMP24": bool(same),
                "how": "hjd_convert_jpg_files_multi: file readers -> chunks of 32 images decoded with HJD_FLAG_BMP_OUT "
                       "-> writer threads; wall clock from the first fopen to the last fclose"}
@@ -606,7 +611,7 @@ def run_ours(args, rank, local_rank, world):
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
         traffic = None
         try:   # DRAM bytes per launch of that kernel from the committed ncu capture, scaled to this batch
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_final_traffic.json")))
             if args.config == "c2":
                 traffic = int(tj["dram_bytes_per_launch"][dom.replace("_ms", "")] * n / tj["images"])
         except Exception:
@@ -625,7 +630,7 @@ def run_ours(args, rank, local_rank, world):
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1),
                              "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                             "traffic_source": "profiles/r1_final_traffic.json (ncu --set full, per launch)" if traffic else None,
+                             "traffic_source": "profiles/r2_final_traffic.json (ncu --set full, per launch)" if traffic else None,
                              "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
                              "whole_step_frac": round(whole / peak, 4)},
                 "clocks": clocks, "gpu_launches": int(job_launches)}

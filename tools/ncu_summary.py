@@ -5,6 +5,7 @@
 """
 import csv
 import json
+import re
 import sys
 
 WANT = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -15,7 +16,8 @@ WANT = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
-        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct']
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct',
+        'lts__t_sector_hit_rate.pct']
 
 
 def to_bytes(x, unit):
@@ -48,9 +50,10 @@ def main():
         out.append(f"warp stall reasons per issue: {sorted(stalls, reverse=True)}")
         name = r[hdr.index('Kernel Name')]
         key = ('scan' if 'marker' in name else 'entropy' if 'entropy' in name else
-               'idct' if ('idct' in name or 'mcu_rgb' in name) else 'color')
+               'idct' if ('idct' in name or 'mcu_rgb' in name) else 'color' if 'color' in name else
+               re.sub(r'\W+', '_', name.split('(')[0].replace('hjd_k_', ''))[:24])
         ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
-        traffic[key] = int(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]))
+        traffic.setdefault(key, int(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])))
         out.append('---')
     open(prefix + "_ncu_summary.txt", "w").write("\n".join(out) + "\n")
     json.dump({"_source": f"{prefix}_ncu_summary.txt: ncu --set full --clock-control none on `{cmd}`, "

@@ -35,7 +35,11 @@ def main():
             op = m.group(1)
             hist[kern]["_total"] += 1
             for w in WATCH:
-                if op == w or op.startswith(w + "."):
+                if w in ("LDG.E.256", "LDG.E.128", "STG.E.128"):      # width anywhere among the modifiers
+                    base, width = w.split(".")[0], w.split(".")[-1]
+                    if op.startswith(base + ".") and ("." + width) in op:
+                        hist[kern][w] += 1
+                elif op == w or op.startswith(w + "."):
                     hist[kern][w] += 1
     print(f"# {os.path.relpath(so, ROOT)}: cuobjdump -sass, architectures {arch}")
     print("# exact opcode or opcode-prefix matches; 'LDG' includes LDG.E.128/256, 'FFMA' excludes FFMA2")
