@@ -54,6 +54,9 @@ struct HjdQuantSet {
     // the same tables packed for DP2A: word i = q[2i] | q[2i+1] << 24 (bytes 1, 2 zero), so that
     // dp2a_lo/hi(coefficient pair, word) = coef[2i]*q[2i] resp. coef[2i+1]*q[2i+1] with no unpacking
     uint32_t qp[3][32];
+    // the same tables as FP16 pairs (q <= 255 is exact): word i = half(q[2i]) | half(q[2i+1]) << 16, the
+    // multiplier of the tensor-core kernel's packed FP16 de-quantisation (mcu_tc.cuh)
+    uint32_t qh[3][32];
 };
 
 struct HjdImageDesc {

@@ -283,6 +283,16 @@ int hjd_build_table_set(const HjdParsed& p, HjdTableSet* out)
     return HJD_IMG_OK;
 }
 
+// FP16 bit pattern of an integer 0 <= v < 2048 (exactly representable)
+static uint32_t half_bits_of_small_int(uint32_t v)
+{
+    if (v == 0) return 0;
+    if (v > 2047) v = 2047;     // 16-bit tables are rejected by the parser; never reached
+    int e = 0;
+    while ((v >> (e + 1)) != 0) e++;
+    return ((uint32_t)(e + 15) << 10) | ((v << (10 - e)) & 0x3FFu);
+}
+
 void hjd_build_quant_set(const HjdParsed& p, HjdQuantSet* out)
 {
     memset(out, 0, sizeof *out);
@@ -292,6 +302,8 @@ void hjd_build_quant_set(const HjdParsed& p, HjdQuantSet* out)
         for (int k = 0; k < 64; k++) out->q[c][k] = p.qt[p.tq[src]][k];
         for (int k = 0; k < 32; k++)
             out->qp[c][k] = (uint32_t)p.qt[p.tq[src]][2 * k] | ((uint32_t)p.qt[p.tq[src]][2 * k + 1] << 24);
+        for (int k = 0; k < 32; k++)
+            out->qh[c][k] = half_bits_of_small_int(p.qt[p.tq[src]][2 * k]) | (half_bits_of_small_int(p.qt[p.tq[src]][2 * k + 1]) << 16);
     }
 }
 

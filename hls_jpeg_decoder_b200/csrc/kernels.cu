@@ -24,6 +24,8 @@ __constant__ float c_cosq[64];    // 0.25f * c_cos: the final scaling folded int
 __constant__ float c_cc0;         // C(0)*C(k>0) = 1/sqrtf(2)                    (loadjpg.cpp:96-102)
 __constant__ float c_cc00;        // C(0)*C(0) = fl(0.70710677^2) = 0.49999997
 
+static cudaError_t hjd_set_idct_matrix(const float cos_tab[64], float cc0, float cc00);
+
 cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00)
 {
     cudaError_t e = cudaMemcpyToSymbol(c_cos, cos_tab, 64 * sizeof(float));
@@ -38,7 +40,9 @@ cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc0
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_cc0, &cc0, sizeof(float));
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_cc00, &cc00, sizeof(float));
+    e = cudaMemcpyToSymbol(c_cc00, &cc00, sizeof(float));
+    if (e != cudaSuccess) return e;
+    return hjd_set_idct_matrix(cos_tab, cc0, cc00);
 }
 
 // zig-zag position p -> natural (row-major) index n; inverse of the reference's ZigZagArray
@@ -463,10 +467,13 @@ hjd_k_entropy_restart(const uint8_t* __restrict__ arena, const HjdImageDesc* __r
 // Function attributes are per device: hjd_batch_create calls this after cudaSetDevice, for every batch
 // (a process-wide "done once" flag would leave the second GPU of a process without the larger
 // shared-memory window, and six distinct Huffman tables need more than the default 48 KB).
+cudaError_t hjd_mcu_tc_init_device(void);
 cudaError_t hjd_kernels_init_device(void)
 {
-    return cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(HJD_ENT_THREADS * (128 + 8) + HJD_MAX_TABLES * sizeof(HjdHuffTable)));
+    cudaError_t e = cudaFuncSetAttribute(hjd_k_entropy_restart, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(HJD_ENT_THREADS * (128 + 8) + HJD_MAX_TABLES * sizeof(HjdHuffTable)));
+    if (e != cudaSuccess) return e;
+    return hjd_mcu_tc_init_device();
 }
 
 cudaError_t hjd_launch_entropy_restart(const uint8_t* arena, const HjdImageDesc* imgs, const HjdTableSet* tsets,
@@ -1097,9 +1104,38 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
     }
 }
 
+#include "mcu_tc.cuh"
+
+// The IDCT matrix of the tensor-core kernel (see mcu_tc.cuh): M[k][8y+x] = 0.25 * C(u)C(v) * cos[x][u] * cos[y][v], the
+// real-number product of the reference's float constants, split into M_hi * 2^-13 and M_lo (integers, exact in FP16)
+// and laid out as the K-major, 128-byte-swizzled shared-memory tile tcgen05.mma reads: row n (0..63: M_hi of sample
+// n = 8y+x; 64..127: M_lo), 64 FP16 per row in zig-zag order, 16-byte chunk j of row n at chunk j ^ (n & 7).
+static cudaError_t hjd_set_idct_matrix(const float cos_tab[64], float cc0, float cc00)
+{
+    static uint16_t img[HJD_TC_TILE_BYTES / 2];
+    for (int k = 0; k < 64; k++) {
+        const int nat = hjd_zz(k), u = nat & 7, v = nat >> 3;
+        const double cc = nat == 0 ? (double)cc00 : ((u == 0 || v == 0) ? (double)cc0 : 1.0);
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) {
+                const double m = 0.25 * cc * (double)cos_tab[x * 8 + u] * (double)cos_tab[y * 8 + v];
+                const double s = ldexp(m, 13);
+                const int hi = (int)nearbyint(s);
+                const int lo = (int)nearbyint(ldexp(s - hi, 11));
+                for (int half = 0; half < 2; half++) {
+                    const int row = half * 64 + 8 * y + x;
+                    const size_t off = (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)(((k >> 3) ^ (row & 7)) << 4) + (size_t)(k & 7) * 2;
+                    const __half h = __float2half(half ? (float)lo : ldexpf((float)hi, -13));
+                    img[off / 2] = *(const uint16_t*)&h;
+                }
+            }
+    }
+    return cudaMemcpyToSymbol(g_idct_mat, img, sizeof img);
+}
+
 cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
-                               uint32_t max_mcus, bool bmp, cudaStream_t st)
+                               uint32_t max_mcus, bool bmp, bool tensor_core, cudaStream_t st)
 {
     if (n_images <= 0 || n_mcus == 0 || max_mcus == 0) return cudaSuccess;
     const unsigned gx = (max_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS;
@@ -1108,13 +1144,32 @@ cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, co
     if ((uint64_t)gx * HJD_MCU_THREADS * (uint64_t)n_images <= (uint64_t)n_mcus * 4) {
         for (int base = 0; base < n_images; base += 65535) {
             const int n = min(65535, n_images - base);
-            if (bmp) hjd_k_mcu_rgb<false, true><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
-            else hjd_k_mcu_rgb<false, false><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+            if (tensor_core) {
+                if (bmp) hjd_k_mcu_rgb_tc<false, true><<<dim3(gx, n), HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+                else hjd_k_mcu_rgb_tc<false, false><<<dim3(gx, n), HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+            } else {
+                if (bmp) hjd_k_mcu_rgb<false, true><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+                else hjd_k_mcu_rgb<false, false><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+            }
         }
     } else {
         const unsigned g = (unsigned)(((uint64_t)n_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS);
-        if (bmp) hjd_k_mcu_rgb<true, true><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
-        else hjd_k_mcu_rgb<true, false><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+        if (tensor_core) {
+            if (bmp) hjd_k_mcu_rgb_tc<true, true><<<g, HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+            else hjd_k_mcu_rgb_tc<true, false><<<g, HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+        } else {
+            if (bmp) hjd_k_mcu_rgb<true, true><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+            else hjd_k_mcu_rgb<true, false><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+        }
     }
     return cudaGetLastError();
+}
+
+cudaError_t hjd_mcu_tc_init_device(void)
+{
+    cudaError_t e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    return e;
 }

@@ -30,11 +30,13 @@ def golden_files():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.jpg")))
 
 
-@pytest.fixture(scope="module", params=["planes", "fused_mcu"])
+@pytest.fixture(scope="module", params=["planes", "fused_mcu", "fused_mcu_cuda_core"])
 def dec(hjd, request):
-    """fused_mcu: the default product path (kernels 2+3 fused per MCU, planes in shared memory only);
+    """fused_mcu: the default product path (kernels 2+3 fused per MCU, IDCT fast tier on the tensor cores, planes in
+    shared memory only); fused_mcu_cuda_core: the same with the fast tier as FP32 FMA chains (HJD_FLAG_CUDA_CORE_IDCT);
     planes: HJD_FLAG_KEEP_PLANES, unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap)."""
-    d = hjd.BatchDecoder(0, {"fused_mcu": 0, "planes": hjd.FLAG_KEEP_PLANES}[request.param])
+    d = hjd.BatchDecoder(0, {"fused_mcu": 0, "fused_mcu_cuda_core": hjd.FLAG_CUDA_CORE_IDCT,
+                             "planes": hjd.FLAG_KEEP_PLANES}[request.param])
     d.keeps_planes = request.param == "planes"
     yield d
     d.close()
