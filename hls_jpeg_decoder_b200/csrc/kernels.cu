@@ -837,6 +837,12 @@ __device__ __forceinline__ float hjd_byte_f(const uint32_t* w, int idx)
 {
     return (float)((w[idx >> 2] >> (8 * (idx & 3))) & 255u);
 }
+// The same byte under the exponent of 2^23: the float 8388608 + byte, exactly, with one PRMT on the ALU pipe instead of
+// a conversion on the quarter-rate XU pipe; the caller subtracts 8388608 (+ 128 for chroma) in the packed add it does anyway.
+__device__ __forceinline__ float hjd_byte_m(const uint32_t* w, int idx)
+{
+    return __uint_as_float(__byte_perm(w[idx >> 2], 0x4B000000u, 0x7540u | (uint32_t)(idx & 3)));
+}
 
 #ifdef HJD_COLOR_SCALAR
 template <int HS, int NP>
@@ -858,11 +864,12 @@ __device__ __forceinline__ void hjd_color_n(const uint32_t* yw, const uint32_t* 
     constexpr int NC = NP >> HS, D = 1 << HS;
     static_assert(NC % 2 == 0, "chroma samples are processed in pairs");
     float2 tx[NC / 2], tyn[NC / 2], tzn[NC / 2], tw[NC / 2];
-    const float2 m128 = make_float2(-128.0f, -128.0f);
+    const float2 m128 = make_float2(-8388736.0f, -8388736.0f);      // -(2^23 + 128)
+    const float2 m0 = make_float2(-8388608.0f, -8388608.0f);
 #pragma unroll
     for (int p = 0; p < NC / 2; p++) {
-        const float2 cb = __fadd2_rn(make_float2(hjd_byte_f(cbw, 2 * p), hjd_byte_f(cbw, 2 * p + 1)), m128);   // (float)(Cb - 128), exact
-        const float2 cr = __fadd2_rn(make_float2(hjd_byte_f(crw, 2 * p), hjd_byte_f(crw, 2 * p + 1)), m128);
+        const float2 cb = __fadd2_rn(make_float2(hjd_byte_m(cbw, 2 * p), hjd_byte_m(cbw, 2 * p + 1)), m128);   // (float)(Cb - 128), exact
+        const float2 cr = __fadd2_rn(make_float2(hjd_byte_m(crw, 2 * p), hjd_byte_m(crw, 2 * p + 1)), m128);
         tx[p]  = __fmul2_rn(make_float2(1.402f, 1.402f), cr);
         tyn[p] = __fmul2_rn(make_float2(-0.34414f, -0.34414f), cb);
         tzn[p] = __fmul2_rn(make_float2(-0.71414f, -0.71414f), cr);
@@ -873,7 +880,7 @@ __device__ __forceinline__ void hjd_color_n(const uint32_t* yw, const uint32_t* 
     for (int i = 0; i < NP; i++) {
         if (((i >> HS) & 1) != 0) continue;                  // second pixel of a pair
         const int j = i + D, p = (i >> HS) >> 1;
-        const float2 y2 = make_float2(hjd_byte_f(yw, i), hjd_byte_f(yw, j));
+        const float2 y2 = __fadd2_rn(make_float2(hjd_byte_m(yw, i), hjd_byte_m(yw, j)), m0);      // (float)Y, exact
         // loadjpg.cpp:873-879 with the argument swap of the call at 918 resolved; (int) truncates
         const float2 r2 = __fadd2_rn(y2, tx[p]);
         const float2 g2 = __fadd2_rn(__fadd2_rn(y2, tyn[p]), tzn[p]);
@@ -1133,43 +1140,53 @@ static cudaError_t hjd_set_idct_matrix(const float cos_tab[64], float cc0, float
     return cudaMemcpyToSymbol(g_idct_mat, img, sizeof img);
 }
 
+static int g_tc_ctas[64];      // resident CTAs of the tensor-core kernel per device (one per SM), set by hjd_mcu_tc_init_device
+
 cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
                                uint32_t max_mcus, bool bmp, bool tensor_core, cudaStream_t st)
 {
     if (n_images <= 0 || n_mcus == 0 || max_mcus == 0) return cudaSuccess;
+    if (tensor_core) {
+        // units of 128 MCUs, walked by the groups of one resident CTA per SM.  Images of similar size: unit = (image, 128 MCUs of it),
+        // no look-up; clearly skewed or tiny-image batches: units over all MCUs of the batch, the image found by binary search
+        // (an idle thread slot is cheap, a search in front of every unit is not: the same rule as for the CUDA-core kernel below).
+        uint32_t units_x = (max_mcus + 127u) / 128u;
+        uint64_t n_units = (uint64_t)units_x * (uint64_t)n_images;
+        if (n_units * 128u > (uint64_t)n_mcus * 4 || n_units > 0xFFFFFFFFull) { units_x = 0; n_units = ((uint64_t)n_mcus + 127u) / 128u; }
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const int resident = (dev >= 0 && dev < 64 && g_tc_ctas[dev] > 0) ? g_tc_ctas[dev] : 148;
+        const unsigned g = (unsigned)min((uint64_t)resident, (n_units + HJD_TC_GROUPS - 1) / HJD_TC_GROUPS);
+        if (bmp) hjd_k_mcu_rgb_tc<true><<<g, HJD_TC_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, (uint32_t)n_units, units_x);
+        else hjd_k_mcu_rgb_tc<false><<<g, HJD_TC_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, (uint32_t)n_units, units_x);
+        return cudaGetLastError();
+    }
     const unsigned gx = (max_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS;
     // thread slots of the 2-D grid against MCUs there are: an idle slot is cheap (config 5 runs at 1.6 x:
     // 1.02 ms against 1.11 ms with the search), so only clearly skewed or tiny-image batches go flat
     if ((uint64_t)gx * HJD_MCU_THREADS * (uint64_t)n_images <= (uint64_t)n_mcus * 4) {
         for (int base = 0; base < n_images; base += 65535) {
             const int n = min(65535, n_images - base);
-            if (tensor_core) {
-                if (bmp) hjd_k_mcu_rgb_tc<false, true><<<dim3(gx, n), HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
-                else hjd_k_mcu_rgb_tc<false, false><<<dim3(gx, n), HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
-            } else {
-                if (bmp) hjd_k_mcu_rgb<false, true><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
-                else hjd_k_mcu_rgb<false, false><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
-            }
+            if (bmp) hjd_k_mcu_rgb<false, true><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
+            else hjd_k_mcu_rgb<false, false><<<dim3(gx, n), HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, nullptr, n_images, base);
         }
     } else {
         const unsigned g = (unsigned)(((uint64_t)n_mcus + HJD_MCU_THREADS - 1) / HJD_MCU_THREADS);
-        if (tensor_core) {
-            if (bmp) hjd_k_mcu_rgb_tc<true, true><<<g, HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
-            else hjd_k_mcu_rgb_tc<true, false><<<g, HJD_MCU_THREADS, HJD_TC_SMEM_BYTES, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
-        } else {
-            if (bmp) hjd_k_mcu_rgb<true, true><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
-            else hjd_k_mcu_rgb<true, false><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
-        }
+        if (bmp) hjd_k_mcu_rgb<true, true><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
+        else hjd_k_mcu_rgb<true, false><<<g, HJD_MCU_THREADS, 0, st>>>(coef, imgs, qsets, rgb, mcu_prefix, n_images, 0);
     }
     return cudaGetLastError();
 }
 
 cudaError_t hjd_mcu_tc_init_device(void)
 {
-    cudaError_t e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hjd_k_mcu_rgb_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HJD_TC_SMEM_BYTES);
+    int dev = 0, sms = 0;
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) g_tc_ctas[dev] = sms;
     return e;
 }

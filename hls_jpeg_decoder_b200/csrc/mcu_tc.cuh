@@ -66,6 +66,10 @@ __device__ __forceinline__ void hjd_tmem_ld16(uint32_t taddr, uint32_t* r)
                    "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
 }
+// 16 bytes global -> shared, asynchronously, past the L1 (the shared-memory carve-out leaves it almost no capacity)
+__device__ __forceinline__ void hjd_cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void hjd_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void hjd_group_barrier(uint32_t id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
 __device__ __forceinline__ void hjd_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor: K-major, 128-byte swizzle, rows of 64 FP16 = 128 bytes, 8-row atoms of
@@ -78,8 +82,11 @@ __device__ __forceinline__ uint64_t hjd_smem_desc_sw128(uint32_t addr)
 #define HJD_IDESC_F16_M128_N128 ((1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24))
 
 #define HJD_TC_TILE_BYTES   16384u
-#define HJD_TC_LIST_CAP     128
-#define HJD_TC_SMEM_BYTES   (1024u + 2u * HJD_TC_TILE_BYTES + 4u * 8u * HJD_MCU_THREADS * 8u)     // slack for the 1024-byte alignment + V + M + four 8x8 tiles per thread
+#define HJD_TC_LIST_CAP     64
+#define HJD_TC_GROUPS       4                          // 128-thread groups per CTA: one V tile, one accumulator, one barrier each; the matrix is shared
+#define HJD_TC_THREADS      (128 * HJD_TC_GROUPS)
+// slack for the 1024-byte alignment + M + one V tile per group + four 8x8 tiles per thread
+#define HJD_TC_SMEM_BYTES   (1024u + (1u + HJD_TC_GROUPS) * HJD_TC_TILE_BYTES + 4u * 8u * HJD_TC_THREADS * 8u)
 #ifndef HJD_TC_WINDOW_UNITS
 #define HJD_TC_WINDOW_UNITS 20.0f
 #endif
@@ -114,8 +121,13 @@ __host__ __device__ constexpr int hjd_izz(int n)
     return r;
 }
 
+__device__ __forceinline__ uint32_t hjd_h2_as_u32(__half2 h) { return *(uint32_t*)&h; }
+__device__ __forceinline__ __half2 hjd_u32_as_h2(uint32_t u) { return *(__half2*)&u; }
+
 // One sample (x, y) of one block in the reference's exact order of operations (loadjpg.cpp:112-123), from the
 // coefficient slab: blk = the block's 64 int16 (zig-zag order), qp = its component's quantisation table packed for DP2A.
+// Same operations as hjd_exact_sum, two terms per packed instruction where the order allows it: the products
+// (rounded once each, like the scalar ones) pair up, the 64 additions stay a chain in the reference's order.
 __device__ __forceinline__ int hjd_exact_sample_gmem(const uint4* __restrict__ blk, const uint4* __restrict__ qp, const float* s_cos, int x, int y)
 {
     uint4 c[8], q[8];
@@ -127,339 +139,396 @@ __device__ __forceinline__ int hjd_exact_sample_gmem(const uint4* __restrict__ b
     { const float4 a = *(const float4*)(s_cos + x * 8), b = *(const float4*)(s_cos + x * 8 + 4); cx[0] = a.x; cx[1] = a.y; cx[2] = a.z; cx[3] = a.w; cx[4] = b.x; cx[5] = b.y; cx[6] = b.z; cx[7] = b.w; }
     { const float4 a = *(const float4*)(s_cos + y * 8), b = *(const float4*)(s_cos + y * 8 + 4); ty[0] = a.x; ty[1] = a.y; ty[2] = a.z; ty[3] = a.w; ty[4] = b.x; ty[5] = b.y; ty[6] = b.z; ty[7] = b.w; }
     const float cc0 = c_cc0, cc00 = c_cc00;
+    uint32_t m16;
+    asm volatile("mov.u32 %0, 0xFFFF;" : "=r"(m16));                  // in a register: (prod & 0xFFFF) ^ K is ONE LOP3
     float sum = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
 #pragma unroll
-        for (int v = 0; v < 8; v++) {
-            const int n = 8 * v + u, p = hjd_izz(8 * v + u);
-            const int prod = (p & 1) ? hjd_dp2a_hi_su(cw[p >> 1], qw[p >> 1]) : hjd_dp2a_lo_su(cw[p >> 1], qw[p >> 1]);   // loadjpg.cpp:150
-            // (float)(short)prod without the conversion unit: 1.5 * 2^23 + s is exact for |s| < 2^22
-            const float f = __fadd_rn(__int_as_float(0x4B400000 + (int)(short)prod), -12582912.0f);
-            const float b = (n == 0) ? __fmul_rn(cc00, f) : ((u == 0 || v == 0) ? __fmul_rn(cc0, f) : f);      // (C(u)*C(v)) * block[u][v]
-            sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(b, cx[u]), ty[v]));
+        for (int vp = 0; vp < 4; vp++) {
+            float2 f2;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int p = hjd_izz(8 * (2 * vp + h) + u);
+                const int prod = (p & 1) ? hjd_dp2a_hi_su(cw[p >> 1], qw[p >> 1]) : hjd_dp2a_lo_su(cw[p >> 1], qw[p >> 1]);   // loadjpg.cpp:150
+                // (float)(short)prod without the conversion unit: the low 16 bits, offset binary, under the exponent of
+                // 1.5 * 2^23: the float 12582912 + 32768 + s, exactly
+                uint32_t fb;
+                asm("lop3.b32 %0, %1, %2, 0x4B408000, 0x6A;" : "=r"(fb) : "r"(prod), "r"(m16));
+                if (h) f2.y = __uint_as_float(fb); else f2.x = __uint_as_float(fb);
+            }
+            f2 = __fadd2_rn(f2, make_float2(-12615680.0f, -12615680.0f));
+            // (C(u)*C(v)) * block[u][v]; a factor 1.0f is exact
+            if (u == 0) f2 = __fmul2_rn(f2, vp == 0 ? make_float2(cc00, cc0) : make_float2(cc0, cc0));
+            else if (vp == 0) f2 = __fmul2_rn(f2, make_float2(cc0, 1.0f));
+            const float2 t2 = __fmul2_rn(__fmul2_rn(f2, make_float2(cx[u], cx[u])), make_float2(ty[2 * vp], ty[2 * vp + 1]));
+            sum = __fadd_rn(__fadd_rn(sum, t2.x), t2.y);
         }
     }
     return hjd_finish_sample(sum);
 }
 
-__device__ __forceinline__ uint32_t hjd_h2_as_u32(__half2 h) { return *(uint32_t*)&h; }
-__device__ __forceinline__ __half2 hjd_u32_as_h2(uint32_t u) { return *(__half2*)&u; }
+// bit b of the result <=> byte b of d is non-zero
+__device__ __forceinline__ uint32_t hjd_nonzero_bytes(uint32_t d)
+{
+    const uint32_t t = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    return (((t >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
 
-template <bool FLAT, bool BMP>
-__global__ void __launch_bounds__(HJD_MCU_THREADS, 3)
+// Work is handed out in units of 128 MCUs, one per group and round: the four groups of a CTA share the matrix tile and
+// nothing else, so each walks its own units (unit = first + k * stride) at its own pace -- one resident CTA per SM for the
+// whole launch, no tail of half-idle CTAs, TMEM and the matrix set up once.
+//   units_x > 0: images of similar size; unit u = (image u / units_x, MCUs (u % units_x) * 128 ...)   (no look-up)
+//   units_x = 0: mixed or tiny sizes; unit u = MCUs u * 128 ... of the whole batch, the image of each thread found by
+//                binary search in mcu_prefix[i] = MCUs of the images before i.
+template <bool BMP>
+__global__ void __launch_bounds__(HJD_TC_THREADS, 1)
 hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__ imgs,
                  const HjdQuantSet* __restrict__ qsets, uint8_t* __restrict__ rgb,
-                 const uint32_t* __restrict__ mcu_prefix, int n_images, int img_base)
+                 const uint32_t* __restrict__ mcu_prefix, int n_images, uint32_t n_units, uint32_t units_x)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ float s_cos[64];
-    __shared__ uint64_t s_bar;
+    __shared__ uint64_t s_bar[HJD_TC_GROUPS];
     __shared__ uint32_t s_tmem;
-    __shared__ int s_nsteps;
-    __shared__ uint32_t s_cnt[HJD_MCU_THREADS / 32];
-    __shared__ uint32_t s_list[HJD_MCU_THREADS / 32][HJD_TC_LIST_CAP];
+    __shared__ int s_nsteps[HJD_TC_GROUPS];
+    __shared__ uint32_t s_cnt[HJD_TC_THREADS / 32];
+    __shared__ uint32_t s_list[HJD_TC_THREADS / 32][HJD_TC_LIST_CAP];
     // 1024-byte alignment of the swizzled tiles, by an offset so that the pointers stay in the shared address space (LDS / STS)
     uint8_t* const smem = smem_raw + ((1024u - (hjd_smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* const sV = smem;                                   // this step's coefficient tile
-    uint8_t* const sM = smem + HJD_TC_TILE_BYTES;               // the IDCT matrix
-    uint2* const s_tile = (uint2*)(smem + 2 * HJD_TC_TILE_BYTES);   // [4][8 * T]: Y (left), Y (right), Cb, Cr; row r of thread t at [(r * T + t)]
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, grp = t >> 7, tg = t & 127u;
+    uint8_t* const sM = smem;                                                   // the IDCT matrix, shared by the groups
+    uint8_t* const sV = smem + (1u + grp) * HJD_TC_TILE_BYTES;                  // this group's coefficient tile
+    uint2* const s_tile = (uint2*)(smem + (1u + HJD_TC_GROUPS) * HJD_TC_TILE_BYTES);   // [4][8 * T]: Y (left), Y (right), Cb, Cr; row r of thread t at [r * T + t]
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(hjd_smem_u32(&s_tmem)), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(hjd_smem_u32(&s_tmem)), "r"(128u * HJD_TC_GROUPS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (t == 0) { hjd_mbar_init(hjd_smem_u32(&s_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s_nsteps = 0; }
+    if (t < HJD_TC_GROUPS) { hjd_mbar_init(hjd_smem_u32(&s_bar[t]), 1); s_nsteps[t] = 0; }
+    if (t == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (t < 64) s_cos[t] = c_cos[t];
-    if (t < HJD_MCU_THREADS / 32) s_cnt[t] = 0;
+    if (t < HJD_TC_THREADS / 32) s_cnt[t] = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < HJD_TC_TILE_BYTES / 16 / HJD_MCU_THREADS; i++) ((uint4*)sM)[i * HJD_MCU_THREADS + t] = g_idct_mat[i * HJD_MCU_THREADS + t];
+    for (uint32_t i = 0; i < HJD_TC_TILE_BYTES / 16 / HJD_TC_THREADS; i++) ((uint4*)sM)[i * HJD_TC_THREADS + t] = g_idct_mat[i * HJD_TC_THREADS + t];
+    hjd_proxy_fence();                                            // the matrix tile was written through the generic proxy
+    hjd_tc_fence_before();
+    __syncthreads();                                              // barriers, TMEM address, matrix
+    hjd_tc_fence_after();
 
-    // ---- which MCU (same two grid shapes as hjd_k_mcu_rgb); nobody leaves: every thread takes part in the barriers
-    const HjdImageDesc* d = imgs;
-    uint32_t m = 0;
-    bool valid = true;
-    if (FLAT) {
-        const uint32_t key = blockIdx.x * HJD_MCU_THREADS + t + mcu_prefix[0];
-        if (key >= mcu_prefix[n_images]) valid = false;
-        else {
-            int lo = 0, hi = n_images - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (mcu_prefix[mid] <= key) lo = mid; else hi = mid - 1;
-            }
-            d = imgs + lo;
-            m = key - mcu_prefix[lo];
-        }
-    } else {
-        d = imgs + (blockIdx.y + img_base);
-        m = blockIdx.x * HJD_MCU_THREADS + t;
-    }
-    if (valid && (m >= d->n_mcus || d->blocks_per_mcu == 0)) valid = false;
-    const uint32_t hf = valid ? d->hf : 1u, vf = valid ? d->vf : 1u, bpm = valid ? d->blocks_per_mcu : 0u;
-    const bool gray = valid ? d->ncomp == 1 : true;
-    const uint32_t ny = gray ? 1u : hf * vf;
-    const uint32_t mcus_x = valid ? d->mcus_x : 1u;
-    const uint32_t my = m / mcus_x, mx = m - my * mcus_x;
-    const int hs = (int)hf - 1, vs = (int)vf - 1;
-    const HjdQuantSet* qs = qsets + (valid ? d->quant_set : 0u);
-    const uint4* cp = (const uint4*)(coef + ((valid ? d->block_base : 0ull) + (uint64_t)m * bpm) * 64);
-    constexpr uint32_t kPitch = HJD_MCU_THREADS * 8;
-    uint8_t* const tile0 = (uint8_t*)&s_tile[t];                  // tile s of this thread: tile0 + s * 8 * kPitch
-    constexpr uint32_t kTile = 8 * kPitch;
-
-    const uint32_t W = valid ? d->width : 0u, H = valid ? d->height : 0u;
-    const uint64_t img_pitch = BMP ? (uint64_t)((W * 3 + 3) & ~3u) : (uint64_t)W * 3;
-    uint8_t* img_rgb = rgb + (valid ? d->rgb_off : 0ull) + (BMP ? HJD_BMP_PIXEL_OFF : 0);
-    const uint32_t px = mx * hf * 8;                              // left edge of the MCU
-    const uint32_t npix = px < W ? min(8u * hf, W - px) : 0u;     // loadjpg.cpp:907
-    if (BMP && valid && m == 0) {                                 // the header, by the thread of the first MCU (openjpg.cpp:537-552)
-        uint8_t* hp = rgb + d->rgb_off + HJD_BMP_FILE_OFF;
-        const uint32_t file_size = (uint32_t)(img_pitch * H) + 54u;
-        const uint32_t words[13] = {file_size, 0u, 54u, 40u, W, H, 1u | 24u << 16, 0u, 0u, 0u, 0u, 0u, 0u};
-        hp[0] = 'B'; hp[1] = 'M';
-#pragma unroll
-        for (int k = 0; k < 13; k++)
-#pragma unroll
-            for (int qq = 0; qq < 4; qq++) hp[2 + 4 * k + qq] = (uint8_t)(words[k] >> (8 * qq));
-    }
-    const uint32_t n_pre = gray ? 0u : 2u;
-    const uint32_t n_mine = valid ? n_pre + ny : 0u;
-    {
-        const int wmax = __reduce_max_sync(0xffffffffu, (int)n_mine);
-        hjd_proxy_fence();                                        // the matrix tile was written through the generic proxy
-        hjd_tc_fence_before();
-        __syncthreads();                                          // s_nsteps = 0, barrier, TMEM address, matrix
-        if (lane == 0 && wmax) atomicMax(&s_nsteps, wmax);
-        __syncthreads();
-        hjd_tc_fence_after();
-    }
-    const int n_steps = s_nsteps;
     const uint32_t tmem = s_tmem;
-    const uint32_t bar = hjd_smem_u32(&s_bar);
+    const uint32_t bar = hjd_smem_u32(&s_bar[grp]);
     const uint64_t vdesc = hjd_smem_desc_sw128(hjd_smem_u32(sV)), mdesc = hjd_smem_desc_sw128(hjd_smem_u32(sM));
-    const uint32_t taddr = tmem + ((warp * 32u) << 16);
-    uint8_t* const vrow = sV + t * 128u;
+    const uint32_t tacc = tmem + 128u * grp;                      // this group's accumulator: 128 lanes x 128 columns
+    const uint32_t taddr = tacc + (((warp & 3u) * 32u) << 16);    // a warp reads the 32 lanes of its quarter
+    uint8_t* const vrow = sV + tg * 128u;
+    const uint32_t vrow_s = hjd_smem_u32(vrow);
+    constexpr uint32_t kPitch = HJD_TC_THREADS * 8;
+    constexpr uint32_t kTile = 8 * kPitch;
+    uint8_t* const tile0 = (uint8_t*)&s_tile[t];                  // tile s of this thread: tile0 + s * kTile, row r at + r * kPitch
     uint32_t phase = 0;
 
-    // one loop: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order; after the last Y block of a
-    // block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB
 #pragma unroll 1
-    for (int it = 0; it < n_steps; it++) {
-        const bool act = (uint32_t)it < n_mine;
-        const bool chroma = (uint32_t)it < n_pre;
-        const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
-        const uint32_t bx = chroma ? 0u : bi & (hf - 1u), by = chroma ? 0u : bi >> hs;      // sampling factors are 1 or 2
-        const uint32_t slot = chroma ? 2u + it : (bx ? 1u : 0u);
-        const uint32_t comp = chroma ? 1u + it : 0u;
+    for (uint32_t unit = blockIdx.x * HJD_TC_GROUPS + grp; unit < n_units; unit += gridDim.x * HJD_TC_GROUPS) {
+        // ---- which MCU; nobody leaves: every thread of the group takes part in its barriers
+        const HjdImageDesc* d = imgs;
+        uint32_t m = 0;
+        bool valid = true;
+        if (units_x == 0) {
+            const uint32_t key = unit * 128u + tg + mcu_prefix[0];
+            if (key >= mcu_prefix[n_images]) valid = false;
+            else {
+                int lo = 0, hi = n_images - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (mcu_prefix[mid] <= key) lo = mid; else hi = mid - 1;
+                }
+                d = imgs + lo;
+                m = key - mcu_prefix[lo];
+            }
+        } else {
+            const uint32_t img = unit / units_x;
+            d = imgs + img;
+            m = (unit - img * units_x) * 128u + tg;
+        }
+        if (valid && (m >= d->n_mcus || d->blocks_per_mcu == 0)) valid = false;
+        const uint32_t hf = valid ? d->hf : 1u, vf = valid ? d->vf : 1u, bpm = valid ? d->blocks_per_mcu : 0u;
+        const bool gray = valid ? d->ncomp == 1 : true;
+        const uint32_t ny = gray ? 1u : hf * vf;
+        const uint32_t mcus_x = valid ? d->mcus_x : 1u;
+        const uint32_t my = m / mcus_x, mx = m - my * mcus_x;
+        const int hs = (int)hf - 1, vs = (int)vf - 1;
+        const HjdQuantSet* qs = qsets + (valid ? d->quant_set : 0u);
+        const uint4* cp = (const uint4*)(coef + ((valid ? d->block_base : 0ull) + (uint64_t)m * bpm) * 64);
 
-        // ---- coefficients -> de-quantised FP16 row of the V tile; A, preconditions -------------------------
-        float win;                 // re-evaluation window on the 0.25*sum scale; < 0: no sample can be flagged
-        bool all_exact = false;    // the block is outside the fast tier's preconditions
-        bool dc_only = false;
-        float dc_bp = 0.f;         // fl(C(0)C(0) * DC), the only term of a DC-only block
+        const uint32_t W = valid ? d->width : 0u, H = valid ? d->height : 0u;
+        const uint64_t img_pitch = BMP ? (uint64_t)((W * 3 + 3) & ~3u) : (uint64_t)W * 3;
+        uint8_t* img_rgb = rgb + (valid ? d->rgb_off : 0ull) + (BMP ? HJD_BMP_PIXEL_OFF : 0);
+        const uint32_t px = mx * hf * 8;                              // left edge of the MCU
+        const uint32_t npix = px < W ? min(8u * hf, W - px) : 0u;     // loadjpg.cpp:907
+        if (BMP && valid && m == 0) {                                 // the header, by the thread of the first MCU (openjpg.cpp:537-552)
+            uint8_t* hp = rgb + d->rgb_off + HJD_BMP_FILE_OFF;
+            const uint32_t file_size = (uint32_t)(img_pitch * H) + 54u;
+            const uint32_t words[13] = {file_size, 0u, 54u, 40u, W, H, 1u | 24u << 16, 0u, 0u, 0u, 0u, 0u, 0u};
+            hp[0] = 'B'; hp[1] = 'M';
+#pragma unroll
+            for (int k = 0; k < 13; k++)
+#pragma unroll
+                for (int qq = 0; qq < 4; qq++) hp[2 + 4 * k + qq] = (uint8_t)(words[k] >> (8 * qq));
+        }
+        const uint32_t n_pre = gray ? 0u : 2u;
+        const uint32_t n_mine = valid ? n_pre + ny : 0u;
+        // The coefficients travel global -> shared memory asynchronously, straight into this thread's row of the V tile (raw
+        // int16, already at the swizzled chunk positions), one step ahead: requested as soon as the MMA that read the row has
+        // completed, converted in place at the top of the next step.  No registers and no second buffer are held meanwhile.
+        // (A lane without a block requests nothing and converts whatever its row holds, see below.)
+        if (n_mine) {
+            const uint8_t* const src = (const uint8_t*)(cp + (gray ? 0u : ny) * 8);
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++) hjd_cp_async16(vrow_s + ((i ^ (tg & 7u)) << 4), src + 16 * i);
+        }
         {
-            // Lanes without a block this step (MCU beyond the image, fewer blocks per MCU than the CTA's longest) load a
-            // block that exists and convert it like everybody else: the rows of V are independent (row t -> TMEM lane t),
-            // so what such a lane computes is never looked at; only its flags and stores are switched off.
-            uint4 c[8], q[8];
-            const uint4* const src = act ? cp + bi * 8 : (const uint4*)coef;
-            const HjdQuantSet* const qsrc = act ? qs : qsets;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                hjd_ldg256(src + 2 * i, c[2 * i], c[2 * i + 1]);
-                hjd_ldg256_nc((const uint4*)qsrc->qh[comp] + 2 * i, q[2 * i], q[2 * i + 1]);
-            }
-            const int q0 = (int)qsrc->q[comp][0];
-            if (act && (uint32_t)it + 1 < n_mine) {               // next block's 128-byte line -> L1 while this one computes
-                const uint32_t nbi = ((uint32_t)it + 1 < n_pre) ? ny + it + 1 : it + 1 - n_pre;
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(cp + nbi * 8));
-            }
-            uint32_t* cw = (uint32_t*)c;
-            const uint32_t* qw = (const uint32_t*)q;
-            // DC: un-differenced, up to +-1024 / q: through the integer path (one conversion per block)
-            const int dc_i = (int)(short)((int)(short)(cw[0] & 0xFFFFu) * q0);       // stored to short, loadjpg.cpp:150
-            // bits 15..9 of a half-word differ <=> its value is outside [-512, 511]; and p ^ 2p == 0 <=> p == 0
-            uint32_t chk = 0;
-            const uint32_t ac1_bits = cw[0] & 0xFFFF0000u;                          // position 1 shares its word with the DC
-            const uint32_t ac1_chk = (cw[0] ^ (cw[0] << 1)) & 0xFC000000u;
-            __half2 a2[2] = {__float2half2_rn(0.f), __float2half2_rn(0.f)};
-            __half2 vmax = __float2half2_rn(0.f);
-            const __half2 k1536 = __float2half2_rn(1536.f);
-            uint32_t kmask;
-            asm volatile("mov.u32 %0, 0x03FF03FF;" : "=r"(kmask));                 // in a register: (p & mask) ^ 0x66006600 is ONE LOP3
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const uint32_t p = cw[i];
-                if (i) chk |= p ^ (p + p);
-                // (c + 1536) as FP16 bit patterns: 0x6400 | ((c + 512) & 1023) for c in [-512, 511]
-                uint32_t hb;
-                asm("lop3.b32 %0, %1, %2, 0x66006600, 0x6A;" : "=r"(hb) : "r"(p), "r"(kmask));
-                const __half2 x = __hsub2(hjd_u32_as_h2(hb), k1536);
-                __half2 v = __hmul2(x, hjd_u32_as_h2(qw[i]));                      // exact while |c * q| <= 2048
-                if (i == 0) v = __halves2half2(__int2half_rn(dc_i), __high2half(v));
-                const __half2 av = __habs2(v);
-                vmax = __hmax2(vmax, av);
-                // C(u)C(v) per zig-zag position, rounded up: 1, 0.70752 (0x39A9), 0.5; the DC term is kept apart
-                a2[i & 1] = __hfma2(av, hjd_u32_as_h2(hjd_cc_pair_bits(i)), a2[i & 1]);
-                cw[i] = hjd_h2_as_u32(v);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; i++) *(uint4*)(vrow + ((i ^ (t & 7u)) << 4)) = c[i];
-            const __half2 as = __hadd2(a2[0], a2[1]);
-            const float a_ac = __low2float(as) + __high2float(as);
-            const float a_dc = 0.5f * fabsf((float)dc_i);
-            const float a_tot = (a_ac + a_dc) * 1.02f;
-            dc_only = (chk | ac1_bits) == 0u;
-            dc_bp = __fmul_rn(c_cc00, (float)dc_i);
-            const float vm = fmaxf(__low2float(vmax), __high2float(vmax));
-            all_exact = !dc_only && (((chk | ac1_chk) & 0xFC00FC00u) != 0u || !(vm < 2048.f) || !(a_tot < 4000.f));
-            win = (dc_only || !act) ? -1.f : a_tot * (HJD_TC_WINDOW_UNITS * 5.9604644775390625e-08f);
+            const int wmax = __reduce_max_sync(0xffffffffu, (int)n_mine);
+            if (tg == 0) s_nsteps[grp] = 0;
+            hjd_group_barrier(1u + grp);
+            if (lane == 0 && wmax) atomicMax(&s_nsteps[grp], wmax);
+            hjd_group_barrier(1u + grp);
         }
-        hjd_proxy_fence();                                        // generic-proxy writes of the tile -> visible to the tensor core
-        __syncthreads();                                          // everybody's row is written; everybody has read the previous D
-        if (t == 0) {
-            hjd_tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; k++) hjd_umma_f16(tmem, vdesc + 2 * k, mdesc + 2 * k, HJD_IDESC_F16_M128_N128, k > 0);
-            hjd_umma_commit(bar);
-        }
-        hjd_mbar_wait(bar, phase);
-        phase ^= 1u;
-        hjd_tc_fence_after();
+        const int n_steps = s_nsteps[grp];                            // of this group: its barrier and its MMAs are its own
 
-        // ---- D -> samples: h = D_hi + 2^-24 * D_lo, truncate, +128, clamp, pack; collect near-integer samples ----
-        uint32_t near_lo = 0, near_hi = 0;                        // bit (8y + x)
-        uint8_t* const dst = tile0 + slot * kTile;
-        const uint32_t dc_word = (uint32_t)hjd_finish_sample(dc_bp) * 0x01010101u;
-#pragma unroll
-        for (int yp = 0; yp < 4; yp++) {
-            uint32_t dh[16], dl[16];
-            hjd_tmem_ld16(taddr + 16 * yp, dh);
-            hjd_tmem_ld16(taddr + 64 + 16 * yp, dl);
-            hjd_tmem_ld_wait();
-#pragma unroll
-            for (int yy = 0; yy < 2; yy++) {
-                const int y = 2 * yp + yy;
-                int iv[8];
-#pragma unroll
-                for (int xp = 0; xp < 4; xp++) {
-                    const float2 hi2 = make_float2(__uint_as_float(dh[8 * yy + 2 * xp]), __uint_as_float(dh[8 * yy + 2 * xp + 1]));
-                    const float2 lo2 = make_float2(__uint_as_float(dl[8 * yy + 2 * xp]), __uint_as_float(dl[8 * yy + 2 * xp + 1]));
-                    const float2 h2 = __ffma2_rn(lo2, make_float2(5.9604644775390625e-08f, 5.9604644775390625e-08f), hi2);
-                    // rint(h) as (h + 1.5*2^23) - 1.5*2^23 (|h| < 2^22 whenever the window is in use)
-                    const float2 hr2 = __fadd2_rn(__fadd2_rn(h2, make_float2(12582912.0f, 12582912.0f)), make_float2(-12582912.0f, -12582912.0f));
-                    const float2 d2 = __fadd2_rn(h2, make_float2(-hr2.x, -hr2.y));
-                    const bool near_a = fabsf(d2.x) <= win, near_b = fabsf(d2.y) <= win;
-                    iv[2 * xp] = __float2int_rz(h2.x); iv[2 * xp + 1] = __float2int_rz(h2.y);         // (int)(0.25*sum), loadjpg.cpp:123
-                    if (y < 4) { if (near_a) near_lo |= 1u << (8 * y + 2 * xp); if (near_b) near_lo |= 1u << (8 * y + 2 * xp + 1); }
-                    else       { if (near_a) near_hi |= 1u << (8 * (y - 4) + 2 * xp); if (near_b) near_hi |= 1u << (8 * (y - 4) + 2 * xp + 1); }
-                }
-                // |h| <= A / 4 < 1000: neither short wrap of the reference (loadjpg.cpp:136-137) can trigger, so the sample is
-                // sat_u8(trunc(h) + 128) = sat_s8(trunc(h)) ^ 0x80
-                uint32_t r_lo = hjd_pack_sat_s8(iv[1], iv[0], hjd_pack_sat_s8(iv[3], iv[2], 0u)) ^ 0x80808080u;
-                uint32_t r_hi = hjd_pack_sat_s8(iv[5], iv[4], hjd_pack_sat_s8(iv[7], iv[6], 0u)) ^ 0x80808080u;
-                if (dc_only) { r_lo = dc_word; r_hi = dc_word; }
-                if (act) *(uint2*)(dst + (uint32_t)y * kPitch) = make_uint2(r_lo, r_hi);
-            }
-        }
-        hjd_tc_fence_before();                                    // D has been read: the next step's MMA may overwrite it after the barrier
-        if (all_exact) { near_lo = 0xFFFFFFFFu; near_hi = 0xFFFFFFFFu; }
-        if (!act) { near_lo = 0; near_hi = 0; }
-
-        // ---- exact re-evaluation, batched per warp -------------------------------------------------------------
-        const bool batch_end = act && !chroma && bx + 1 >= hf;
-        for (;;) {
-            const uint32_t n_pend = (uint32_t)__popc(near_lo) + (uint32_t)__popc(near_hi);
-            if (n_pend) {
-                const uint32_t base = atomicAdd(&s_cnt[warp], n_pend);
-                uint32_t room = base < HJD_TC_LIST_CAP ? HJD_TC_LIST_CAP - base : 0u;
-                uint32_t j = base;
-                while (room && (near_lo | near_hi)) {
-                    uint32_t pos;
-                    if (near_lo) { pos = (uint32_t)__ffs((int)near_lo) - 1u; near_lo &= near_lo - 1u; }
-                    else         { pos = 32u + (uint32_t)__ffs((int)near_hi) - 1u; near_hi &= near_hi - 1u; }
-                    s_list[warp][j++] = lane | slot << 5 | bi << 7 | pos << 11;
-                    room--;
-                }
-            }
-            __syncwarp();
-            const bool more = (near_lo | near_hi) != 0u;
-            if (!__any_sync(0xffffffffu, more || batch_end)) break;
-            const uint32_t n_list = min(s_cnt[warp], (uint32_t)HJD_TC_LIST_CAP);
-            for (uint32_t base = 0; base < n_list; base += 32) {
-                const bool have = base + lane < n_list;
-                const uint32_t e = have ? s_list[warp][base + lane] : lane;
-                const uint32_t owner = e & 31u, eslot = (e >> 5) & 3u, ebi = (e >> 7) & 15u, epos = (e >> 11) & 63u;
-                const uint64_t ocp = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)cp, (int)owner);
-                const uint64_t oqs = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)qs, (int)owner);
-                if (have) {
-                    const uint32_t ecomp = eslot < 2u ? 0u : eslot - 1u;
-                    const int val = hjd_exact_sample_gmem((const uint4*)(uintptr_t)ocp + ebi * 8,
-                                                          (const uint4*)(((const HjdQuantSet*)(uintptr_t)oqs)->qp[ecomp]), s_cos, (int)(epos & 7u), (int)(epos >> 3));
-                    ((uint8_t*)&s_tile[warp * 32u + owner])[eslot * kTile + (epos >> 3) * kPitch + (epos & 7u)] = (uint8_t)val;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) s_cnt[warp] = 0;
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, more)) break;
-        }
-
-        // ---- upsample + colour conversion of the finished block row ---------------------------------------------
-        if (!batch_end || npix == 0) continue;
-        const uint8_t* tY0 = tile0, * tY1 = tile0 + kTile, * tCb = tile0 + 2 * kTile, * tCr = tile0 + 3 * kTile;
-        const uint32_t py0 = (my * vf + by) * 8;
+        // one loop: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order; after the last Y block of a
+        // block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB
 #pragma unroll 1
-        for (uint32_t r = 0; r < 8; r++) {
-            const uint32_t py = py0 + r;
-            if (py >= H) break;                                   // loadjpg.cpp:908
-            uint32_t cbw[2] = {0x80808080u, 0x80808080u}, crw[2] = {0x80808080u, 0x80808080u};
-            if (!gray) {
-                const uint32_t crow = (by * 8 + r) >> vs;         // nearest neighbour, loadjpg.cpp:911-912
-                const uint2 b8 = *(const uint2*)(tCb + crow * kPitch), r8 = *(const uint2*)(tCr + crow * kPitch);
-                cbw[0] = b8.x; cbw[1] = b8.y; crw[0] = r8.x; crw[1] = r8.y;
-            }
-            uint8_t* o8 = img_rgb + (uint64_t)(BMP ? H - 1 - py : py) * img_pitch + (uint64_t)px * 3;      // loadjpg.cpp:921-925 / openjpg.cpp:555
-            const uint2 ya = *(const uint2*)(tY0 + r * kPitch);
-            if (hs) {                                             // 16 pixels: 48 bytes, three 128-bit stores
-                const uint2 yb = *(const uint2*)(tY1 + r * kPitch);
-                const uint32_t yw[4] = {ya.x, ya.y, yb.x, yb.y};
-                uint32_t out[12];
-                hjd_color_n<1, 16, BMP>(yw, cbw, crw, out);
-                if (npix == 16 && (((uintptr_t)o8) & 15) == 0) {
-                    uint4* o = (uint4*)o8;
-                    o[0] = make_uint4(out[0], out[1], out[2], out[3]);
-                    o[1] = make_uint4(out[4], out[5], out[6], out[7]);
-                    o[2] = make_uint4(out[8], out[9], out[10], out[11]);
-                } else {
+        for (int it = 0; it < n_steps; it++) {
+            const bool act = (uint32_t)it < n_mine;
+            const bool chroma = (uint32_t)it < n_pre;
+            const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
+            const uint32_t bx = chroma ? 0u : bi & (hf - 1u), by = chroma ? 0u : bi >> hs;      // sampling factors are 1 or 2
+            const uint32_t slot = chroma ? 2u + it : (bx ? 1u : 0u);
+            const uint32_t comp = chroma ? 1u + it : 0u;
+
+            // ---- coefficients -> de-quantised FP16 row of the V tile; A, preconditions -------------------------
+            float win;                 // re-evaluation window on the 0.25*sum scale; 0: no sample can be flagged
+            bool all_exact = false;    // the block is outside the fast tier's preconditions
+            bool dc_only = false;
+            float dc_bp = 0.f;         // fl(C(0)C(0) * DC), the only term of a DC-only block
+            {
+                // Lanes without a block this step (MCU beyond the image, fewer blocks per MCU than the group's longest) convert
+                // whatever their row holds like everybody else (any bit pattern converts to finite values): the rows of V are
+                // independent (row t -> TMEM lane t), so what such a lane computes is never looked at; only its flags and stores
+                // are switched off.  (They must not all fetch one dummy address either: 67 M requests for one L2 line cost
+                // config 5 seven milliseconds.)
+                uint4 c[8], q[8];
+                const HjdQuantSet* const qsrc = act ? qs : qsets;
 #pragma unroll
-                    for (int i = 0; i < 48; i++)
-                        if ((uint32_t)i < npix * 3) o8[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
-                }
-            } else {                                              // 8 pixels: 24 bytes
-                const uint32_t yw[2] = {ya.x, ya.y};
-                uint32_t out[6];
-                hjd_color_n<0, 8, BMP>(yw, cbw, crw, out);
-                if (npix == 8 && (((uintptr_t)o8) & 7) == 0) {
-                    uint2* o = (uint2*)o8;
-                    o[0] = make_uint2(out[0], out[1]);
-                    o[1] = make_uint2(out[2], out[3]);
-                    o[2] = make_uint2(out[4], out[5]);
-                } else {
+                for (int i = 0; i < 4; i++) hjd_ldg256_nc((const uint4*)qsrc->qh[comp] + 2 * i, q[2 * i], q[2 * i + 1]);
+                hjd_cp_async_wait();
 #pragma unroll
-                    for (int i = 0; i < 24; i++)
-                        if ((uint32_t)i < npix * 3) o8[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                for (int i = 0; i < 8; i++) c[i] = *(const uint4*)(vrow + ((i ^ (tg & 7u)) << 4));
+                uint32_t* cw = (uint32_t*)c;
+                const uint32_t* qw = (const uint32_t*)q;
+                // DC: un-differenced, up to +-1024 / q, beyond the range of the bit trick below: one conversion per block.
+                // |c0| <= 2047 converts exactly, and so does the product while it stays below 2048 (checked through vmax).
+                const int c0 = (int)(short)(cw[0] & 0xFFFFu);
+                const __half dc_h = __hmul(__int2half_rn(c0), __low2half(hjd_u32_as_h2(q[0].x)));
+                const float dc_f = __half2float(dc_h);                                // = (float)(short)(c0 * q0) whenever the block stays in the fast tier
+                // bits 15..9 of a half-word differ <=> its value is outside [-512, 511]; and p ^ 2p == 0 <=> p == 0
+                uint32_t chk = 0;
+                const uint32_t ac1_bits = cw[0] & 0xFFFF0000u;                          // position 1 shares its word with the DC
+                const uint32_t ac1_chk = (cw[0] ^ (cw[0] << 1)) & 0xFC000000u;
+                __half2 a2[2] = {__float2half2_rn(0.f), __float2half2_rn(0.f)};
+                __half2 vmax = __float2half2_rn(0.f);
+                const __half2 k1536 = __float2half2_rn(1536.f);
+                uint32_t kmask;
+                asm volatile("mov.u32 %0, 0x03FF03FF;" : "=r"(kmask));                 // in a register: (p & mask) ^ 0x66006600 is ONE LOP3
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t p = cw[i];
+                    if (i) chk |= p ^ (p + p);
+                    // (c + 1536) as FP16 bit patterns: 0x6400 | ((c + 512) & 1023) for c in [-512, 511]
+                    uint32_t hb;
+                    asm("lop3.b32 %0, %1, %2, 0x66006600, 0x6A;" : "=r"(hb) : "r"(p), "r"(kmask));
+                    const __half2 x = __hsub2(hjd_u32_as_h2(hb), k1536);
+                    __half2 v = __hmul2(x, hjd_u32_as_h2(qw[i]));                      // exact while |c * q| <= 2048
+                    if (i == 0) v = __halves2half2(dc_h, __high2half(v));
+                    const __half2 av = __habs2(v);
+                    vmax = __hmax2(vmax, av);
+                    // C(u)C(v) per zig-zag position, rounded up: 1, 0.70752 (0x39A9), 0.5; the DC term is kept apart
+                    a2[i & 1] = __hfma2(av, hjd_u32_as_h2(hjd_cc_pair_bits(i)), a2[i & 1]);
+                    cw[i] = hjd_h2_as_u32(v);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) *(uint4*)(vrow + ((i ^ (tg & 7u)) << 4)) = c[i];
+                const __half2 as = __hadd2(a2[0], a2[1]);
+                const float a_ac = __low2float(as) + __high2float(as);
+                const float a_dc = 0.5f * fabsf(dc_f);
+                const float a_tot = (a_ac + a_dc) * 1.02f;
+                dc_only = (chk | ac1_bits) == 0u;
+                dc_bp = __fmul_rn(c_cc00, dc_f);
+                const float vm = fmaxf(__low2float(vmax), __high2float(vmax));
+                const bool dc_wide = (uint32_t)(c0 + 2047) > 4094u || !(vm < 2048.f);     // the DC itself outside the exact range
+                all_exact = (!dc_only && (((chk | ac1_chk) & 0xFC00FC00u) != 0u || !(a_tot < 4000.f))) || dc_wide;
+                if (dc_wide) dc_only = false;
+                win = (dc_only || !act || all_exact) ? 0.f : a_tot * (HJD_TC_WINDOW_UNITS * 5.9604644775390625e-08f);
+            }
+            hjd_proxy_fence();                                        // generic-proxy writes of the tile -> visible to the tensor core
+            hjd_group_barrier(1u + grp);                              // everybody's row is written; everybody has read the previous D
+            if (tg == 0) {
+                hjd_tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++) hjd_umma_f16(tacc, vdesc + 2 * k, mdesc + 2 * k, HJD_IDESC_F16_M128_N128, k > 0);
+                hjd_umma_commit(bar);
+            }
+            hjd_mbar_wait(bar, phase);
+            phase ^= 1u;
+            hjd_tc_fence_after();
+            if ((uint32_t)it + 1u < n_mine) {                         // the MMA has read the tile: the next block's coefficients may land in it
+                const uint32_t nit = (uint32_t)it + 1u;
+                const uint32_t nbi = nit < n_pre ? ny + nit : nit - n_pre;
+                const uint8_t* const src = (const uint8_t*)(cp + nbi * 8);
+#pragma unroll
+                for (uint32_t i = 0; i < 8; i++) hjd_cp_async16(vrow_s + ((i ^ (tg & 7u)) << 4), src + 16 * i);
+            }
+
+            // ---- D -> samples.  h = D_hi + 2^-24 * D_lo is within `win` of the reference's 0.25 * sum, and the reference's sample is
+            // sat_u8(trunc(0.25 * sum) + 128) = sat_s8(trunc(.)) ^ 0x80 (|h| <= A / 4 < 1000: neither short wrap of loadjpg.cpp:136-137 can
+            // trigger), a monotone function: where it gives the same byte for h - win and for h + win, that byte is the reference's.
+            // Everything else -- an integer inside the window, not a saturated one, not zero -- is re-evaluated exactly.
+            uint32_t near_lo = 0, near_hi = 0;                        // bit (8y + x)
+            uint8_t* const dst = tile0 + slot * kTile;
+            const uint32_t dc_word = (uint32_t)hjd_finish_sample(dc_bp) * 0x01010101u;
+            const float2 wpos = make_float2(win, win), wneg = make_float2(-win, -win);
+#pragma unroll
+            for (int yp = 0; yp < 4; yp++) {
+                uint32_t dh[16], dl[16];
+                hjd_tmem_ld16(taddr + 16 * yp, dh);
+                hjd_tmem_ld16(taddr + 64 + 16 * yp, dl);
+                hjd_tmem_ld_wait();
+#pragma unroll
+                for (int yy = 0; yy < 2; yy++) {
+                    const int y = 2 * yp + yy;
+                    int ip[8], im[8];
+#pragma unroll
+                    for (int xp = 0; xp < 4; xp++) {
+                        const float2 hi2 = make_float2(__uint_as_float(dh[8 * yy + 2 * xp]), __uint_as_float(dh[8 * yy + 2 * xp + 1]));
+                        const float2 lo2 = make_float2(__uint_as_float(dl[8 * yy + 2 * xp]), __uint_as_float(dl[8 * yy + 2 * xp + 1]));
+                        const float2 h2 = __ffma2_rn(lo2, make_float2(5.9604644775390625e-08f, 5.9604644775390625e-08f), hi2);
+                        const float2 p2 = __fadd2_rn(h2, wpos), m2 = __fadd2_rn(h2, wneg);
+                        ip[2 * xp] = __float2int_rz(p2.x); ip[2 * xp + 1] = __float2int_rz(p2.y);         // (int)(0.25*sum), loadjpg.cpp:123
+                        im[2 * xp] = __float2int_rz(m2.x); im[2 * xp + 1] = __float2int_rz(m2.y);
+                    }
+                    const uint32_t p_lo = hjd_pack_sat_s8(ip[1], ip[0], hjd_pack_sat_s8(ip[3], ip[2], 0u));
+                    const uint32_t p_hi = hjd_pack_sat_s8(ip[5], ip[4], hjd_pack_sat_s8(ip[7], ip[6], 0u));
+                    const uint32_t m_lo = hjd_pack_sat_s8(im[1], im[0], hjd_pack_sat_s8(im[3], im[2], 0u));
+                    const uint32_t m_hi = hjd_pack_sat_s8(im[5], im[4], hjd_pack_sat_s8(im[7], im[6], 0u));
+                    const uint32_t d_lo = p_lo ^ m_lo, d_hi = p_hi ^ m_hi;
+                    if (d_lo | d_hi) {
+                        const uint32_t bits = hjd_nonzero_bytes(d_lo) | hjd_nonzero_bytes(d_hi) << 4;
+                        if (y < 4) near_lo |= bits << (8 * y); else near_hi |= bits << (8 * (y - 4));
+                    }
+                    uint32_t r_lo = p_lo ^ 0x80808080u, r_hi = p_hi ^ 0x80808080u;
+                    if (dc_only) { r_lo = dc_word; r_hi = dc_word; }
+                    if (act) *(uint2*)(dst + (uint32_t)y * kPitch) = make_uint2(r_lo, r_hi);
                 }
             }
-            if constexpr (BMP) {
-                if (px + npix == W)                               // row padding, openjpg.cpp:563-567
-                    for (uint32_t qq = W * 3; qq < (uint32_t)img_pitch; qq++) o8[qq - px * 3] = 0;
+            hjd_tc_fence_before();                                    // D has been read: the next step's MMA may overwrite it after the barrier
+            if (all_exact) { near_lo = 0xFFFFFFFFu; near_hi = 0xFFFFFFFFu; }
+            if (!act) { near_lo = 0; near_hi = 0; }
+
+            // ---- exact re-evaluation, batched per warp -------------------------------------------------------------
+            const bool batch_end = act && !chroma && bx + 1 >= hf;
+            for (;;) {
+                const uint32_t n_pend = (uint32_t)__popc(near_lo) + (uint32_t)__popc(near_hi);
+                if (n_pend) {
+                    const uint32_t base = atomicAdd(&s_cnt[warp], n_pend);
+                    uint32_t room = base < HJD_TC_LIST_CAP ? HJD_TC_LIST_CAP - base : 0u;
+                    uint32_t j = base;
+                    while (room && (near_lo | near_hi)) {
+                        uint32_t pos;
+                        if (near_lo) { pos = (uint32_t)__ffs((int)near_lo) - 1u; near_lo &= near_lo - 1u; }
+                        else         { pos = 32u + (uint32_t)__ffs((int)near_hi) - 1u; near_hi &= near_hi - 1u; }
+                        s_list[warp][j++] = lane | slot << 5 | bi << 7 | pos << 11;
+                        room--;
+                    }
+                }
+                __syncwarp();
+                const bool more = (near_lo | near_hi) != 0u;
+                if (!__any_sync(0xffffffffu, more || batch_end)) break;
+                const uint32_t n_list = min(s_cnt[warp], (uint32_t)HJD_TC_LIST_CAP);
+                for (uint32_t base = 0; base < n_list; base += 32) {
+                    const bool have = base + lane < n_list;
+                    const uint32_t e = have ? s_list[warp][base + lane] : lane;
+                    const uint32_t owner = e & 31u, eslot = (e >> 5) & 3u, ebi = (e >> 7) & 15u, epos = (e >> 11) & 63u;
+                    const uint64_t ocp = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)cp, (int)owner);
+                    const uint64_t oqs = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)qs, (int)owner);
+                    if (have) {
+                        const uint32_t ecomp = eslot < 2u ? 0u : eslot - 1u;
+                        const int val = hjd_exact_sample_gmem((const uint4*)(uintptr_t)ocp + ebi * 8,
+                                                              (const uint4*)(((const HjdQuantSet*)(uintptr_t)oqs)->qp[ecomp]), s_cos, (int)(epos & 7u), (int)(epos >> 3));
+                        ((uint8_t*)&s_tile[warp * 32u + owner])[eslot * kTile + (epos >> 3) * kPitch + (epos & 7u)] = (uint8_t)val;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) s_cnt[warp] = 0;
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, more)) break;
+            }
+
+            // ---- upsample + colour conversion of the finished block row ---------------------------------------------
+            if (batch_end && npix != 0) {
+                const uint8_t* tY0 = tile0, * tY1 = tile0 + kTile, * tCb = tile0 + 2 * kTile, * tCr = tile0 + 3 * kTile;
+                const uint32_t py0 = (my * vf + by) * 8;
+#pragma unroll 1
+                for (uint32_t r = 0; r < 8; r++) {
+                    const uint32_t py = py0 + r;
+                    if (py >= H) break;                                   // loadjpg.cpp:908
+                    uint32_t cbw[2] = {0x80808080u, 0x80808080u}, crw[2] = {0x80808080u, 0x80808080u};
+                    if (!gray) {
+                        const uint32_t crow = (by * 8 + r) >> vs;         // nearest neighbour, loadjpg.cpp:911-912
+                        const uint2 b8 = *(const uint2*)(tCb + crow * kPitch), r8 = *(const uint2*)(tCr + crow * kPitch);
+                        cbw[0] = b8.x; cbw[1] = b8.y; crw[0] = r8.x; crw[1] = r8.y;
+                    }
+                    uint8_t* o8 = img_rgb + (uint64_t)(BMP ? H - 1 - py : py) * img_pitch + (uint64_t)px * 3;      // loadjpg.cpp:921-925 / openjpg.cpp:555
+                    const uint2 ya = *(const uint2*)(tY0 + r * kPitch);
+                    if (hs) {                                             // 16 pixels: 48 bytes, three 128-bit stores
+                        const uint2 yb = *(const uint2*)(tY1 + r * kPitch);
+                        const uint32_t yw[4] = {ya.x, ya.y, yb.x, yb.y};
+                        uint32_t out[12];
+                        hjd_color_n<1, 16, BMP>(yw, cbw, crw, out);
+                        if (npix == 16 && (((uintptr_t)o8) & 15) == 0) {
+                            uint4* o = (uint4*)o8;
+                            o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                            o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+                            o[2] = make_uint4(out[8], out[9], out[10], out[11]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 48; i++)
+                                if ((uint32_t)i < npix * 3) o8[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                        }
+                    } else {                                              // 8 pixels: 24 bytes
+                        const uint32_t yw[2] = {ya.x, ya.y};
+                        uint32_t out[6];
+                        hjd_color_n<0, 8, BMP>(yw, cbw, crw, out);
+                        if (npix == 8 && (((uintptr_t)o8) & 7) == 0) {
+                            uint2* o = (uint2*)o8;
+                            o[0] = make_uint2(out[0], out[1]);
+                            o[1] = make_uint2(out[2], out[3]);
+                            o[2] = make_uint2(out[4], out[5]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 24; i++)
+                                if ((uint32_t)i < npix * 3) o8[i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                        }
+                    }
+                    if constexpr (BMP) {
+                        if (px + npix == W)                               // row padding, openjpg.cpp:563-567
+                            for (uint32_t qq = W * 3; qq < (uint32_t)img_pitch; qq++) o8[qq - px * 3] = 0;
+                    }
+                }
             }
         }
     }
     hjd_tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u * HJD_TC_GROUPS) : "memory");
 }
