@@ -83,10 +83,11 @@ __device__ __forceinline__ uint64_t hjd_smem_desc_sw128(uint32_t addr)
 
 #define HJD_TC_TILE_BYTES   16384u
 #define HJD_TC_LIST_CAP     64
-#define HJD_TC_GROUPS       4                          // 128-thread groups per CTA: one V tile, one accumulator, one barrier each; the matrix is shared
+#define HJD_TC_GROUPS       3                          // 128-thread groups per CTA: one V tile, one accumulator, one barrier each; the matrix is shared
 #define HJD_TC_THREADS      (128 * HJD_TC_GROUPS)
-// slack for the 1024-byte alignment + M + one V tile per group + four 8x8 tiles per thread
-#define HJD_TC_SMEM_BYTES   (1024u + (1u + HJD_TC_GROUPS) * HJD_TC_TILE_BYTES + 4u * 8u * HJD_TC_THREADS * 8u)
+// slack for the 1024-byte alignment + M + two V tiles per group + four 8x8 tiles per thread
+#define HJD_TC_SMEM_BYTES   (1024u + (1u + 2u * HJD_TC_GROUPS) * HJD_TC_TILE_BYTES + 4u * 8u * HJD_TC_THREADS * 8u)
+#define HJD_TC_TMEM_COLS    512u                       // allocation: a power of two >= 128 * groups
 #ifndef HJD_TC_WINDOW_UNITS
 #define HJD_TC_WINDOW_UNITS 20.0f
 #endif
@@ -192,25 +193,25 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
     __shared__ uint64_t s_bar[HJD_TC_GROUPS];
     __shared__ uint32_t s_tmem;
     __shared__ int s_nsteps[HJD_TC_GROUPS];
+    __shared__ uint32_t s_arrive[HJD_TC_GROUPS];                   // warps of the group that are ready for the next MMA
     __shared__ uint32_t s_cnt[HJD_TC_THREADS / 32];
     __shared__ uint32_t s_list[HJD_TC_THREADS / 32][HJD_TC_LIST_CAP];
     // 1024-byte alignment of the swizzled tiles, by an offset so that the pointers stay in the shared address space (LDS / STS)
     uint8_t* const smem = smem_raw + ((1024u - (hjd_smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, grp = t >> 7, tg = t & 127u;
     uint8_t* const sM = smem;                                                   // the IDCT matrix, shared by the groups
-    uint8_t* const sV = smem + (1u + grp) * HJD_TC_TILE_BYTES;                  // this group's coefficient tile
-    uint2* const s_tile = (uint2*)(smem + (1u + HJD_TC_GROUPS) * HJD_TC_TILE_BYTES);   // [4][8 * T]: Y (left), Y (right), Cb, Cr; row r of thread t at [r * T + t]
+    uint8_t* const sV = smem + (1u + 2u * grp) * HJD_TC_TILE_BYTES;             // this group's two coefficient tiles (steps alternate)
+    uint2* const s_tile = (uint2*)(smem + (1u + 2u * HJD_TC_GROUPS) * HJD_TC_TILE_BYTES);   // [4][8 * T]: Y (left), Y (right), Cb, Cr; row r of thread t at [r * T + t]
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(hjd_smem_u32(&s_tmem)), "r"(128u * HJD_TC_GROUPS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(hjd_smem_u32(&s_tmem)), "r"(HJD_TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (t < HJD_TC_GROUPS) { hjd_mbar_init(hjd_smem_u32(&s_bar[t]), 1); s_nsteps[t] = 0; }
+    if (t < HJD_TC_GROUPS) { hjd_mbar_init(hjd_smem_u32(&s_bar[t]), 1); s_nsteps[t] = 0; s_arrive[t] = 0; }
     if (t == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (t < 64) s_cos[t] = c_cos[t];
     if (t < HJD_TC_THREADS / 32) s_cnt[t] = 0;
-#pragma unroll
-    for (uint32_t i = 0; i < HJD_TC_TILE_BYTES / 16 / HJD_TC_THREADS; i++) ((uint4*)sM)[i * HJD_TC_THREADS + t] = g_idct_mat[i * HJD_TC_THREADS + t];
+    for (uint32_t i = t; i < HJD_TC_TILE_BYTES / 16; i += HJD_TC_THREADS) ((uint4*)sM)[i] = g_idct_mat[i];
     hjd_proxy_fence();                                            // the matrix tile was written through the generic proxy
     hjd_tc_fence_before();
     __syncthreads();                                              // barriers, TMEM address, matrix
@@ -218,11 +219,12 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
 
     const uint32_t tmem = s_tmem;
     const uint32_t bar = hjd_smem_u32(&s_bar[grp]);
-    const uint64_t vdesc = hjd_smem_desc_sw128(hjd_smem_u32(sV)), mdesc = hjd_smem_desc_sw128(hjd_smem_u32(sM));
+    const uint32_t arrive_s = hjd_smem_u32(&s_arrive[grp]);
+    const uint64_t vdesc0 = hjd_smem_desc_sw128(hjd_smem_u32(sV)), mdesc = hjd_smem_desc_sw128(hjd_smem_u32(sM));
     const uint32_t tacc = tmem + 128u * grp;                      // this group's accumulator: 128 lanes x 128 columns
     const uint32_t taddr = tacc + (((warp & 3u) * 32u) << 16);    // a warp reads the 32 lanes of its quarter
-    uint8_t* const vrow = sV + tg * 128u;
-    const uint32_t vrow_s = hjd_smem_u32(vrow);
+    uint8_t* const vrow0 = sV + tg * 128u;                        // this thread's row in tile 0; tile 1 is HJD_TC_TILE_BYTES further
+    const uint32_t vrow0_s = hjd_smem_u32(vrow0);
     constexpr uint32_t kPitch = HJD_TC_THREADS * 8;
     constexpr uint32_t kTile = 8 * kPitch;
     uint8_t* const tile0 = (uint8_t*)&s_tile[t];                  // tile s of this thread: tile0 + s * kTile, row r at + r * kPitch
@@ -278,15 +280,21 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
         }
         const uint32_t n_pre = gray ? 0u : 2u;
         const uint32_t n_mine = valid ? n_pre + ny : 0u;
-        // The coefficients travel global -> shared memory asynchronously, straight into this thread's row of the V tile (raw
-        // int16, already at the swizzled chunk positions), one step ahead: requested as soon as the MMA that read the row has
-        // completed, converted in place at the top of the next step.  No registers and no second buffer are held meanwhile.
+        // The coefficients travel global -> shared memory asynchronously, straight into this thread's row of a V tile (raw int16,
+        // already at the swizzled chunk positions), two steps ahead: block j + 2 is requested into the tile of block j as soon as
+        // MMA j has completed, and converted in place one step later, while MMA j + 1 runs.  No registers are held meanwhile.
         // (A lane without a block requests nothing and converts whatever its row holds, see below.)
-        if (n_mine) {
-            const uint8_t* const src = (const uint8_t*)(cp + (gray ? 0u : ny) * 8);
+        auto request = [&](uint32_t step) {
+            if (step < n_mine) {
+                const uint32_t rbi = step < n_pre ? ny + step : step - n_pre;
+                const uint8_t* const src = (const uint8_t*)(cp + rbi * 8);
+                const uint32_t row = vrow0_s + (step & 1u) * HJD_TC_TILE_BYTES;
 #pragma unroll
-            for (uint32_t i = 0; i < 8; i++) hjd_cp_async16(vrow_s + ((i ^ (tg & 7u)) << 4), src + 16 * i);
-        }
+                for (uint32_t i = 0; i < 8; i++) hjd_cp_async16(row + ((i ^ (tg & 7u)) << 4), src + 16 * i);
+            }
+        };
+        request(0);
+        request(1);
         {
             const int wmax = __reduce_max_sync(0xffffffffu, (int)n_mine);
             if (tg == 0) s_nsteps[grp] = 0;
@@ -296,35 +304,57 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
         }
         const int n_steps = s_nsteps[grp];                            // of this group: its barrier and its MMAs are its own
 
-        // one loop: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order; after the last Y block of a
-        // block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB
+        // One loop, software-pipelined: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order; after the last
+        // Y block of a block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB.  Iteration `it`:
+        //   barrier -> MMA(it) issued -> conversion of block it + 1 into the other V tile (the MMA runs meanwhile) -> MMA(it) done
+        //   -> request of block it + 2 into the tile just read -> samples, exact re-evaluation, colour of block it.
+        // Iteration -1 only converts block 0.
+        float win = 0.f, n_win = 0.f;         // re-evaluation window on the 0.25*sum scale (0: no sample can be flagged), of block it / it + 1
+        uint32_t fl = 0, n_fl = 0;            // bit 0: outside the fast tier's preconditions (all 64 samples exact); bit 1: DC-only
+        uint32_t dcw = 0, n_dcw = 0;          // the sample of a DC-only block, four times
 #pragma unroll 1
-        for (int it = 0; it < n_steps; it++) {
-            const bool act = (uint32_t)it < n_mine;
-            const bool chroma = (uint32_t)it < n_pre;
-            const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
-            const uint32_t bx = chroma ? 0u : bi & (hf - 1u), by = chroma ? 0u : bi >> hs;      // sampling factors are 1 or 2
-            const uint32_t slot = chroma ? 2u + it : (bx ? 1u : 0u);
-            const uint32_t comp = chroma ? 1u + it : 0u;
-
-            // ---- coefficients -> de-quantised FP16 row of the V tile; A, preconditions -------------------------
-            float win;                 // re-evaluation window on the 0.25*sum scale; 0: no sample can be flagged
-            bool all_exact = false;    // the block is outside the fast tier's preconditions
-            bool dc_only = false;
-            float dc_bp = 0.f;         // fl(C(0)C(0) * DC), the only term of a DC-only block
-            {
+        for (int it = -1; it < n_steps; it++) {
+            if (it >= 0) {
+                // No barrier: a warp that has converted its rows of block it and read its part of D of block it - 1 checks in and
+                // moves on to the next conversion; the LAST of the group's four warps to check in issues the MMA.  Nobody waits for
+                // a slower warp before it has to (the completion of MMA(it), further down).
+                __syncwarp();
+                if (lane == 0) {
+                    uint32_t old;
+                    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(arrive_s) : "memory");
+                    if (old == 3u) {
+                        asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" :: "r"(arrive_s), "r"(0u) : "memory");   // nobody checks in again before this MMA completes
+                        hjd_tc_fence_after();
+                        const uint64_t vdesc = vdesc0 + (uint64_t)(((uint32_t)it & 1u) * (HJD_TC_TILE_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < 4; k++) hjd_umma_f16(tacc, vdesc + 2 * k, mdesc + 2 * k, HJD_IDESC_F16_M128_N128, k > 0);
+                        hjd_umma_commit(bar);
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- coefficients of block it + 1 -> de-quantised FP16 row of its V tile; A, preconditions ----------------
+            if (it + 1 < n_steps) {
+                const uint32_t pit = (uint32_t)(it + 1);
+                const bool pact = pit < n_mine;
+                const uint32_t pcomp = pit < n_pre ? 1u + pit : 0u;
+                uint8_t* const prow = vrow0 + (pit & 1u) * HJD_TC_TILE_BYTES;
+                bool all_exact = false, dc_only = false;
+                float dc_bp = 0.f;         // fl(C(0)C(0) * DC), the only term of a DC-only block
+                float win_next_tmp = 0.f;
+                {
                 // Lanes without a block this step (MCU beyond the image, fewer blocks per MCU than the group's longest) convert
                 // whatever their row holds like everybody else (any bit pattern converts to finite values): the rows of V are
                 // independent (row t -> TMEM lane t), so what such a lane computes is never looked at; only its flags and stores
                 // are switched off.  (They must not all fetch one dummy address either: 67 M requests for one L2 line cost
                 // config 5 seven milliseconds.)
                 uint4 c[8], q[8];
-                const HjdQuantSet* const qsrc = act ? qs : qsets;
+                const HjdQuantSet* const qsrc = pact ? qs : qsets;
 #pragma unroll
-                for (int i = 0; i < 4; i++) hjd_ldg256_nc((const uint4*)qsrc->qh[comp] + 2 * i, q[2 * i], q[2 * i + 1]);
-                hjd_cp_async_wait();
+                for (int i = 0; i < 4; i++) hjd_ldg256_nc((const uint4*)qsrc->qh[pcomp] + 2 * i, q[2 * i], q[2 * i + 1]);
+                hjd_cp_async_wait();                                   // everything this thread has requested (block pit) has landed
 #pragma unroll
-                for (int i = 0; i < 8; i++) c[i] = *(const uint4*)(vrow + ((i ^ (tg & 7u)) << 4));
+                for (int i = 0; i < 8; i++) c[i] = *(const uint4*)(prow + ((i ^ (tg & 7u)) << 4));
                 uint32_t* cw = (uint32_t*)c;
                 const uint32_t* qw = (const uint32_t*)q;
                 // DC: un-differenced, up to +-1024 / q, beyond the range of the bit trick below: one conversion per block.
@@ -358,7 +388,7 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                     cw[i] = hjd_h2_as_u32(v);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) *(uint4*)(vrow + ((i ^ (tg & 7u)) << 4)) = c[i];
+                for (int i = 0; i < 8; i++) *(uint4*)(prow + ((i ^ (tg & 7u)) << 4)) = c[i];
                 const __half2 as = __hadd2(a2[0], a2[1]);
                 const float a_ac = __low2float(as) + __high2float(as);
                 const float a_dc = 0.5f * fabsf(dc_f);
@@ -369,26 +399,24 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                 const bool dc_wide = (uint32_t)(c0 + 2047) > 4094u || !(vm < 2048.f);     // the DC itself outside the exact range
                 all_exact = (!dc_only && (((chk | ac1_chk) & 0xFC00FC00u) != 0u || !(a_tot < 4000.f))) || dc_wide;
                 if (dc_wide) dc_only = false;
-                win = (dc_only || !act || all_exact) ? 0.f : a_tot * (HJD_TC_WINDOW_UNITS * 5.9604644775390625e-08f);
+                win_next_tmp = (dc_only || !pact || all_exact) ? 0.f : a_tot * (HJD_TC_WINDOW_UNITS * 5.9604644775390625e-08f);
             }
-            hjd_proxy_fence();                                        // generic-proxy writes of the tile -> visible to the tensor core
-            hjd_group_barrier(1u + grp);                              // everybody's row is written; everybody has read the previous D
-            if (tg == 0) {
-                hjd_tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 4; k++) hjd_umma_f16(tacc, vdesc + 2 * k, mdesc + 2 * k, HJD_IDESC_F16_M128_N128, k > 0);
-                hjd_umma_commit(bar);
+                hjd_proxy_fence();                                    // generic-proxy writes of the tile -> visible to the tensor core
+                n_win = win_next_tmp; n_fl = (all_exact ? 1u : 0u) | (dc_only ? 2u : 0u);
+                n_dcw = (uint32_t)hjd_finish_sample(dc_bp) * 0x01010101u;
             }
+            if (it < 0) { win = n_win; fl = n_fl; dcw = n_dcw; continue; }
+
+            const bool act = (uint32_t)it < n_mine;
+            const bool chroma = (uint32_t)it < n_pre;
+            const uint32_t bi = chroma ? ny + it : it - n_pre;        // block index inside the MCU
+            const uint32_t bx = chroma ? 0u : bi & (hf - 1u), by = chroma ? 0u : bi >> hs;      // sampling factors are 1 or 2
+            const uint32_t slot = chroma ? 2u + it : (bx ? 1u : 0u);
+            const bool all_exact = (fl & 1u) != 0u, dc_only = (fl & 2u) != 0u;
             hjd_mbar_wait(bar, phase);
             phase ^= 1u;
             hjd_tc_fence_after();
-            if ((uint32_t)it + 1u < n_mine) {                         // the MMA has read the tile: the next block's coefficients may land in it
-                const uint32_t nit = (uint32_t)it + 1u;
-                const uint32_t nbi = nit < n_pre ? ny + nit : nit - n_pre;
-                const uint8_t* const src = (const uint8_t*)(cp + nbi * 8);
-#pragma unroll
-                for (uint32_t i = 0; i < 8; i++) hjd_cp_async16(vrow_s + ((i ^ (tg & 7u)) << 4), src + 16 * i);
-            }
+            request((uint32_t)it + 2u);                               // MMA(it) has read its tile: block it + 2 may land in it
 
             // ---- D -> samples.  h = D_hi + 2^-24 * D_lo is within `win` of the reference's 0.25 * sum, and the reference's sample is
             // sat_u8(trunc(0.25 * sum) + 128) = sat_s8(trunc(.)) ^ 0x80 (|h| <= A / 4 < 1000: neither short wrap of loadjpg.cpp:136-137 can
@@ -396,7 +424,7 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
             // Everything else -- an integer inside the window, not a saturated one, not zero -- is re-evaluated exactly.
             uint32_t near_lo = 0, near_hi = 0;                        // bit (8y + x)
             uint8_t* const dst = tile0 + slot * kTile;
-            const uint32_t dc_word = (uint32_t)hjd_finish_sample(dc_bp) * 0x01010101u;
+            const uint32_t dc_word = dcw;
             const float2 wpos = make_float2(win, win), wneg = make_float2(-win, -win);
 #pragma unroll
             for (int yp = 0; yp < 4; yp++) {
@@ -474,6 +502,8 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                 if (!__any_sync(0xffffffffu, more)) break;
             }
 
+            win = n_win; fl = n_fl; dcw = n_dcw;                      // block it + 1 becomes the current one
+
             // ---- upsample + colour conversion of the finished block row ---------------------------------------------
             if (batch_end && npix != 0) {
                 const uint8_t* tY0 = tile0, * tY1 = tile0 + kTile, * tCb = tile0 + 2 * kTile, * tCr = tile0 + 3 * kTile;
@@ -530,5 +560,5 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
     }
     hjd_tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u * HJD_TC_GROUPS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(HJD_TC_TMEM_COLS) : "memory");
 }
