@@ -490,7 +490,7 @@ def run_ours(args, rank, local_rank, world):
     files, file_ids = load_images(n_req, rank, world, args.config, args.scaling, with_ids=True)
     n = len(files)
     arena = hjd.PinnedArena(files, device=local_rank)       # pinned pages from the NUMA node next to this GPU, if any
-    dec = hjd.BatchDecoder(local_rank, int(os.environ.get("HJD_BENCH_FLAGS", "0")))     # experiments only: e.g. 64 = HJD_FLAG_CUDA_CORE_IDCT
+    dec = hjd.BatchDecoder(local_rank, int(os.environ.get("HJD_BENCH_FLAGS", "0")))     # experiments only: e.g. 128 = HJD_FLAG_TENSOR_CORE_IDCT
     dec.upload_arena(arena)
     dec.sync()
     pixels, scan_bytes = dec.pixels, dec.scan_bytes

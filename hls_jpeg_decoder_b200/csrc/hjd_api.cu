@@ -844,7 +844,8 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaSt
         if (c.blocks) {
             CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                   (uint8_t*)b->d_rgb.p, (const uint32_t*)b->d_mcucta.p + c.img0, n,
-                                  b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, (b->flags & HJD_FLAG_BMP_OUT) != 0, !(b->flags & HJD_FLAG_CUDA_CORE_IDCT), st));
+                                  b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, (b->flags & HJD_FLAG_BMP_OUT) != 0,
+                                  (b->flags & HJD_FLAG_TENSOR_CORE_IDCT) ? HJD_MCU_TENSOR_CORE : HJD_MCU_CUDA_CORE, st));
             b->launches += 1;
         }
         if (ev) CU(cudaEventRecord(ev[3], st));

@@ -1144,10 +1144,10 @@ static int g_tc_ctas[64];      // resident CTAs of the tensor-core kernel per de
 
 cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
-                               uint32_t max_mcus, bool bmp, bool tensor_core, cudaStream_t st)
+                               uint32_t max_mcus, bool bmp, int variant, cudaStream_t st)
 {
     if (n_images <= 0 || n_mcus == 0 || max_mcus == 0) return cudaSuccess;
-    if (tensor_core) {
+    if (variant == HJD_MCU_TENSOR_CORE) {
         // units of 128 MCUs, walked by the groups of one resident CTA per SM.  Images of similar size: unit = (image, 128 MCUs of it),
         // no look-up; clearly skewed or tiny-image batches: units over all MCUs of the batch, the image found by binary search
         // (an idle thread slot is cheap, a search in front of every unit is not: the same rule as for the CUDA-core kernel below).

@@ -45,7 +45,9 @@ cudaError_t hjd_launch_color(const uint8_t* planes, const HjdImageDesc* imgs, ui
 // n_mcus = mcu_prefix[n_images] - mcu_prefix[0]; max_mcus = MCUs of the largest image.  Batches of
 // similar-sized images get an (image, CTA) grid, mixed or tiny sizes a flat grid over all MCUs (see the kernel).
 // bmp: write the reference's BMP file layout (header at rgb_off + 10, bottom-up B G R rows from rgb_off + 64).
-// tensor_core: the IDCT's fast tier as tcgen05.mma (mcu_tc.cuh) instead of FP32 FMA chains; same bytes out.
+// variant: where the IDCT's fast tier runs and who re-evaluates the flagged samples; same bytes out.
+#define HJD_MCU_CUDA_CORE    0   // FP32 FMA chains on the CUDA cores, every thread re-evaluates its own flagged samples (default)
+#define HJD_MCU_TENSOR_CORE  1   // tcgen05.mma (mcu_tc.cuh), exact re-evaluations batched per warp
 cudaError_t hjd_launch_mcu_rgb(const int16_t* coef, const HjdImageDesc* imgs, const HjdQuantSet* qsets,
                                uint8_t* rgb, const uint32_t* mcu_prefix, int n_images, uint32_t n_mcus,
-                               uint32_t max_mcus, bool bmp, bool tensor_core, cudaStream_t st);
+                               uint32_t max_mcus, bool bmp, int variant, cudaStream_t st);
