@@ -444,8 +444,11 @@ def test_absurd_dequantisation_wraps_like_the_reference(hjd, port):
     base = [encode_jpeg(cases.noise_rgb(96, 80, 71), 100, "4:4:4"),
             encode_jpeg(cases.noise_rgb(112, 64, 72), 100, "4:2:0", restart_blocks=4)]
     files = [_patch_dqt(f, v) for f in base for v in (255, 64, 17)]
-    with hjd.BatchDecoder(0, hjd.FLAG_KEEP_PLANES) as d1, hjd.BatchDecoder(0) as d2:
-        for d in (d1, d2):
+    # the tensor-core kernel takes its exact tier for all 64 samples of such blocks (quantised coefficients beyond +-511,
+    # products beyond +-2047, A >= 4000): the preconditions of its fast tier, csrc/mcu_tc.cuh
+    with hjd.BatchDecoder(0, hjd.FLAG_KEEP_PLANES) as d1, hjd.BatchDecoder(0) as d2, \
+            hjd.BatchDecoder(0, hjd.FLAG_TENSOR_CORE_IDCT) as d3:
+        for d in (d1, d2, d3):
             d.upload(files)
             d.decode()
             assert (d.status() == 0).all(), d.status()
@@ -456,6 +459,7 @@ def test_absurd_dequantisation_wraps_like_the_reference(hjd, port):
                 assert np.array_equal(a, b), i
             assert np.array_equal(d1.rgb(i), o["rgb"]), i
             assert np.array_equal(d2.rgb(i), o["rgb"]), i
+            assert np.array_equal(d3.rgb(i), o["rgb"]), i
 
 
 def _patch_component_ids(jpg: bytes, ids):

@@ -63,8 +63,8 @@ def main():
         files = list(ex.map(make_job, [(i, seed, max_w, max_h) for i in range(n)], chunksize=4 if max_w > 400 else 32))
         want = list(ex.map(oracle, files, chunksize=8))
     bad = 0
-    variants = (("default", 0), ("planes", hjd.FLAG_KEEP_PLANES), 
-                ("no-selfsync", hjd.FLAG_NO_SELFSYNC))
+    variants = (("default", 0), ("planes", hjd.FLAG_KEEP_PLANES),
+                ("no-selfsync", hjd.FLAG_NO_SELFSYNC), ("tensor-core", hjd.FLAG_TENSOR_CORE_IDCT))
     for name, flags in variants:
         with hjd.BatchDecoder(0, flags) as d:
             d.upload(files)
