@@ -83,10 +83,10 @@ __device__ __forceinline__ uint64_t hjd_smem_desc_sw128(uint32_t addr)
 
 #define HJD_TC_TILE_BYTES   16384u
 #define HJD_TC_LIST_CAP     64
-#define HJD_TC_GROUPS       3                          // 128-thread groups per CTA: one V tile, one accumulator, one barrier each; the matrix is shared
+#define HJD_TC_GROUPS       4                          // 128-thread groups per CTA: one V tile, one accumulator, one barrier each; the matrix is shared
 #define HJD_TC_THREADS      (128 * HJD_TC_GROUPS)
-// slack for the 1024-byte alignment + M + two V tiles per group + four 8x8 tiles per thread
-#define HJD_TC_SMEM_BYTES   (1024u + (1u + 2u * HJD_TC_GROUPS) * HJD_TC_TILE_BYTES + 4u * 8u * HJD_TC_THREADS * 8u)
+// slack for the 1024-byte alignment + M + one V tile per group + four 8x8 tiles per thread
+#define HJD_TC_SMEM_BYTES   (1024u + (1u + HJD_TC_GROUPS) * HJD_TC_TILE_BYTES + 4u * 8u * HJD_TC_THREADS * 8u)
 #define HJD_TC_TMEM_COLS    512u                       // allocation: a power of two >= 128 * groups
 #ifndef HJD_TC_WINDOW_UNITS
 #define HJD_TC_WINDOW_UNITS 20.0f
@@ -200,8 +200,8 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
     uint8_t* const smem = smem_raw + ((1024u - (hjd_smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, grp = t >> 7, tg = t & 127u;
     uint8_t* const sM = smem;                                                   // the IDCT matrix, shared by the groups
-    uint8_t* const sV = smem + (1u + 2u * grp) * HJD_TC_TILE_BYTES;             // this group's two coefficient tiles (steps alternate)
-    uint2* const s_tile = (uint2*)(smem + (1u + 2u * HJD_TC_GROUPS) * HJD_TC_TILE_BYTES);   // [4][8 * T]: Y (left), Y (right), Cb, Cr; row r of thread t at [r * T + t]
+    uint8_t* const sV = smem + (1u + grp) * HJD_TC_TILE_BYTES;                  // this group's coefficient tile
+    uint2* const s_tile = (uint2*)(smem + (1u + HJD_TC_GROUPS) * HJD_TC_TILE_BYTES);   // [4][8 * T]: Y (left), Y (right), Cb, Cr; row r of thread t at [r * T + t]
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(hjd_smem_u32(&s_tmem)), "r"(HJD_TC_TMEM_COLS) : "memory");
@@ -280,17 +280,13 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
         }
         const uint32_t n_pre = gray ? 0u : 2u;
         const uint32_t n_mine = valid ? n_pre + ny : 0u;
-        // The coefficients travel global -> shared memory asynchronously, straight into this thread's row of a V tile (raw int16,
-        // already at the swizzled chunk positions), two steps ahead: block j + 2 is requested into the tile of block j as soon as
-        // MMA j has completed, and converted in place one step later, while MMA j + 1 runs.  No registers are held meanwhile.
-        // (A lane without a block requests nothing and converts whatever its row holds, see below.)
+        // One V tile per group: block it + 1 is loaded and converted in REGISTERS while MMA(it) reads the tile, and stored into
+        // it once that MMA has completed.  Its 128-byte line is requested into the L2 two steps ahead (the slab is 6 GB: a
+        // cold load would wait for HBM); a lane without a block requests nothing and converts what its row holds.
         auto request = [&](uint32_t step) {
             if (step < n_mine) {
                 const uint32_t rbi = step < n_pre ? ny + step : step - n_pre;
-                const uint8_t* const src = (const uint8_t*)(cp + rbi * 8);
-                const uint32_t row = vrow0_s + (step & 1u) * HJD_TC_TILE_BYTES;
-#pragma unroll
-                for (uint32_t i = 0; i < 8; i++) hjd_cp_async16(row + ((i ^ (tg & 7u)) << 4), src + 16 * i);
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + rbi * 8));
             }
         };
         request(0);
@@ -325,7 +321,7 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                     if (old == 3u) {
                         asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" :: "r"(arrive_s), "r"(0u) : "memory");   // nobody checks in again before this MMA completes
                         hjd_tc_fence_after();
-                        const uint64_t vdesc = vdesc0 + (uint64_t)(((uint32_t)it & 1u) * (HJD_TC_TILE_BYTES >> 4));
+                        const uint64_t vdesc = vdesc0;
 #pragma unroll
                         for (int k = 0; k < 4; k++) hjd_umma_f16(tacc, vdesc + 2 * k, mdesc + 2 * k, HJD_IDESC_F16_M128_N128, k > 0);
                         hjd_umma_commit(bar);
@@ -333,12 +329,13 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                 }
                 __syncwarp();
             }
-            // ---- coefficients of block it + 1 -> de-quantised FP16 row of its V tile; A, preconditions ----------------
+            // ---- coefficients of block it + 1 -> de-quantised FP16 row of the V tile; A, preconditions ----------------
+            bool waited = false;
             if (it + 1 < n_steps) {
                 const uint32_t pit = (uint32_t)(it + 1);
                 const bool pact = pit < n_mine;
                 const uint32_t pcomp = pit < n_pre ? 1u + pit : 0u;
-                uint8_t* const prow = vrow0 + (pit & 1u) * HJD_TC_TILE_BYTES;
+                uint8_t* const prow = vrow0;
                 bool all_exact = false, dc_only = false;
                 float dc_bp = 0.f;         // fl(C(0)C(0) * DC), the only term of a DC-only block
                 float win_next_tmp = 0.f;
@@ -352,9 +349,14 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                 const HjdQuantSet* const qsrc = pact ? qs : qsets;
 #pragma unroll
                 for (int i = 0; i < 4; i++) hjd_ldg256_nc((const uint4*)qsrc->qh[pcomp] + 2 * i, q[2 * i], q[2 * i + 1]);
-                hjd_cp_async_wait();                                   // everything this thread has requested (block pit) has landed
+                if (pact) {
+                    const uint32_t pbi = pit < n_pre ? ny + pit : pit - n_pre;
 #pragma unroll
-                for (int i = 0; i < 8; i++) c[i] = *(const uint4*)(prow + ((i ^ (tg & 7u)) << 4));
+                    for (int i = 0; i < 4; i++) hjd_ldg256(cp + pbi * 8 + 2 * i, c[2 * i], c[2 * i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) c[i] = *(const uint4*)(prow + ((i ^ (tg & 7u)) << 4));
+                }
                 uint32_t* cw = (uint32_t*)c;
                 const uint32_t* qw = (const uint32_t*)q;
                 // DC: un-differenced, up to +-1024 / q, beyond the range of the bit trick below: one conversion per block.
@@ -387,6 +389,11 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
                     a2[i & 1] = __hfma2(av, hjd_u32_as_h2(hjd_cc_pair_bits(i)), a2[i & 1]);
                     cw[i] = hjd_h2_as_u32(v);
                 }
+                if (it >= 0) {                                        // MMA(it) is reading the tile: wait for it (normally long done)
+                    hjd_mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    waited = true;
+                }
 #pragma unroll
                 for (int i = 0; i < 8; i++) *(uint4*)(prow + ((i ^ (tg & 7u)) << 4)) = c[i];
                 const __half2 as = __hadd2(a2[0], a2[1]);
@@ -413,10 +420,9 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
             const uint32_t bx = chroma ? 0u : bi & (hf - 1u), by = chroma ? 0u : bi >> hs;      // sampling factors are 1 or 2
             const uint32_t slot = chroma ? 2u + it : (bx ? 1u : 0u);
             const bool all_exact = (fl & 1u) != 0u, dc_only = (fl & 2u) != 0u;
-            hjd_mbar_wait(bar, phase);
-            phase ^= 1u;
+            if (!waited) { hjd_mbar_wait(bar, phase); phase ^= 1u; }
             hjd_tc_fence_after();
-            request((uint32_t)it + 2u);                               // MMA(it) has read its tile: block it + 2 may land in it
+            request((uint32_t)it + 2u);
 
             // ---- D -> samples.  h = D_hi + 2^-24 * D_lo is within `win` of the reference's 0.25 * sum, and the reference's sample is
             // sat_u8(trunc(0.25 * sum) + 128) = sat_s8(trunc(.)) ^ 0x80 (|h| <= A / 4 < 1000: neither short wrap of loadjpg.cpp:136-137 can
