@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = ["probe", "MultiDecoder", "shard_range_c", "ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU", "FLAG_BMP_OUT", "FLAG_TENSOR_CORE_IDCT"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU", "FLAG_BMP_OUT", "FLAG_TENSOR_CORE_IDCT", "FLAG_CUDA_CORE_IDCT"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HJD_LIB_PATH") or os.path.join(_HERE, "libhjd.so")   # override: tuning builds only
@@ -36,7 +36,8 @@ FLAG_HOST_SCAN = 2
 FLAG_NO_SELFSYNC = 8
 FLAG_FUSED_MCU = 16
 FLAG_BMP_OUT = 32
-FLAG_TENSOR_CORE_IDCT = 128  # fused kernel with the IDCT's fast tier as tcgen05.mma
+FLAG_TENSOR_CORE_IDCT = 128  # always the fused kernel with the IDCT's fast tier as tcgen05.mma
+FLAG_CUDA_CORE_IDCT = 64     # always the fused kernel with the fast tier as FP32 FMA chains (default: chosen per chunk)
 
 IMG_WARN_BAD_CODE, IMG_WARN_COEF_RANGE, IMG_WARN_OVERRUN, IMG_WARN_RESTART = 1, 2, 4, 8
 

@@ -813,6 +813,19 @@ static int run_selfsync(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaSt
     return HJD_OK;
 }
 
+// Which fused kernel decodes a chunk's MCUs.  The tensor-core kernel (csrc/mcu_tc.cuh) is the faster one where its 128-MCU
+// units are full and an MCU has several blocks to pipeline: large colour images (config 2: 3.39 ms against 3.63 ms, and the
+// same time at every quality where the CUDA-core kernel's depends on the coefficients: 3.42 against 3.83 ms at q95; config 4:
+// 0.221 against 0.242 ms).  Batches of small images are faster on the CUDA-core kernel (8192 thumbnails: 0.92 ms against
+// 2.3 ms: a unit's set-up and pipeline fill are not amortised over one or two steps).
+static int mcu_variant(unsigned flags, uint64_t blocks, uint32_t n_mcus, uint32_t n_images)
+{
+    if (flags & HJD_FLAG_TENSOR_CORE_IDCT) return HJD_MCU_TENSOR_CORE;
+    if (flags & HJD_FLAG_CUDA_CORE_IDCT) return HJD_MCU_CUDA_CORE;
+    // at least three blocks per MCU, at least eight full units per image, at least one unit for every group of every SM's CTA
+    return (blocks >= 3ull * n_mcus && (uint64_t)n_mcus >= 1024ull * n_images && n_mcus >= 148u * 4u * 128u) ? HJD_MCU_TENSOR_CORE : HJD_MCU_CUDA_CORE;
+}
+
 // Kernels of one chunk on one stream.  ev != nullptr: record stage boundaries (serial mode only).
 static int launch_chunk(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaStream_t st, cudaEvent_t* ev)
 {
@@ -842,10 +855,11 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaSt
     if (!(b->flags & HJD_FLAG_KEEP_PLANES)) {
         // default: kernels 2+3 fused per MCU, planes never reach HBM
         if (c.blocks) {
+            const uint32_t n_mcus_chunk = b->mcu_cta[c.img1] - b->mcu_cta[c.img0];
             CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                   (uint8_t*)b->d_rgb.p, (const uint32_t*)b->d_mcucta.p + c.img0, n,
                                   b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, (b->flags & HJD_FLAG_BMP_OUT) != 0,
-                                  (b->flags & HJD_FLAG_TENSOR_CORE_IDCT) ? HJD_MCU_TENSOR_CORE : HJD_MCU_CUDA_CORE, st));
+                                  mcu_variant(b->flags, c.blocks, n_mcus_chunk, (uint32_t)n), st));
             b->launches += 1;
         }
         if (ev) CU(cudaEventRecord(ev[3], st));

@@ -24,11 +24,13 @@
 //   whatever its internal alignment and rounding are (measured: tools/exp_umma_idct.cu, 0 mismatches against 64-bit
 //   integer sums over 9.7 M sums incl. adversarial blocks).  The same holds for M_lo.  Then
 //       h = fma(D_lo, 2^-24, D_hi)
-//   differs from the real-number value of 0.25 * sum by at most 0.5 unit (fixed-point error of M: 2^-25 * sum|v|,
-//   and sum|v| <= 2A) + 0.25 unit (the FMA's rounding), one unit being 2^-24 * A with A = sum |C(u)C(v) v|.  The
-//   reference's own float evaluation (three roundings per product, 63 additions) is within (3 + 63) / 4 = 16.5
-//   units of it.  Samples closer than 20 units to an integer are re-evaluated exactly; A is accumulated in FP16
-//   (relative error below 1.7 %, C(0) rounded up) and inflated by 2 %.
+//   differs from the real-number value of 0.25 * sum by at most 1 unit (fixed-point error of M: 2^-25 * sum|v|, and
+//   sum|v| <= 2A) + 0.25 unit (the FMA's rounding), one unit being 2^-24 * A with A = sum |C(u)C(v) v|.  The reference's
+//   own float evaluation (three roundings per product, 63 additions) is within (3 + 63) / 4 = 16.5 units of it, and the
+//   two candidates h - win, h + win of the truncation test cost another 0.25 unit: 18 units in all.  The window is 20
+//   units; A is accumulated in FP16 (relative error below 1.6 %, C(0) rounded up) and inflated by 2 %.
+//   Measured (tools/exp_umma_idct.cu, 4.8 M samples incl. adversarial blocks): at most 0.79 units from the real value,
+//   1.34 units from the reference's float result.
 //   Blocks outside the fast tier's preconditions (a quantised coefficient beyond +-511, a de-quantised one beyond
 //   +-2047, A >= 4000 -- none of which a picture produces at any quality below ~97) take the exact evaluation for
 //   all 64 samples.  DC-only blocks are one multiplication (cos(0) == 1: every sample is trunc(0.25 * fl(C00 * v))).

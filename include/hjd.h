@@ -66,8 +66,9 @@ extern "C" {
                                        54-byte header, bottom-up B G R rows padded to 4 bytes) instead of top-down RGB24: written by
                                        the colour kernel's epilogue, so a file writer only has to fwrite it.  The file of image i
                                        is hjd_batch_bmp_bytes(i) bytes from rgb_offset + 10 of the slab (pixel array 64-byte aligned). */
-#define HJD_FLAG_TENSOR_CORE_IDCT 128u /* fused kernel with the IDCT's fast tier as tcgen05.mma on the 5th-generation tensor cores (csrc/mcu_tc.cuh): same bytes out;
-                                         measured 4.15 ms against 3.64 ms for the CUDA-core kernel on config 2, so not the default */
+#define HJD_FLAG_TENSOR_CORE_IDCT 128u /* always the fused kernel with the IDCT's fast tier as tcgen05.mma on the tensor cores (csrc/mcu_tc.cuh) */
+#define HJD_FLAG_CUDA_CORE_IDCT   64u  /* always the fused kernel with the fast tier as FP32 FMA chains on the CUDA cores (csrc/kernels.cu);
+                                          default: chosen per chunk -- tensor cores for large colour images, CUDA cores for batches of small ones (same bytes out) */
 #define HJD_FLAG_NO_SELFSYNC   8u   /* restart-free scans: one thread per scan (kernel 1a) instead of kernel 1b */
 
 typedef struct hjd_batch hjd_batch;

@@ -30,12 +30,13 @@ def golden_files():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.jpg")))
 
 
-@pytest.fixture(scope="module", params=["planes", "fused_mcu", "fused_mcu_tensor_core"])
+@pytest.fixture(scope="module", params=["planes", "fused_mcu", "fused_mcu_tensor_core", "fused_mcu_cuda_core"])
 def dec(hjd, request):
-    """fused_mcu: the default product path (kernels 2+3 fused per MCU, planes in shared memory only);
-    fused_mcu_tensor_core: the same with the IDCT's fast tier as tcgen05.mma (HJD_FLAG_TENSOR_CORE_IDCT, csrc/mcu_tc.cuh);
+    """fused_mcu: the default product path (kernels 2+3 fused per MCU, planes in shared memory only; the IDCT's fast tier on
+    the tensor cores for large colour images, on the CUDA cores for small ones); fused_mcu_tensor_core / fused_mcu_cuda_core:
+    one of the two for every image (HJD_FLAG_TENSOR_CORE_IDCT, csrc/mcu_tc.cuh / HJD_FLAG_CUDA_CORE_IDCT, csrc/kernels.cu);
     planes: HJD_FLAG_KEEP_PLANES, unfused kernels 2 and 3 with the Y/Cb/Cr planes in HBM (parity tap)."""
-    d = hjd.BatchDecoder(0, {"fused_mcu": 0, "fused_mcu_tensor_core": hjd.FLAG_TENSOR_CORE_IDCT,
+    d = hjd.BatchDecoder(0, {"fused_mcu": 0, "fused_mcu_cuda_core": hjd.FLAG_CUDA_CORE_IDCT, "fused_mcu_tensor_core": hjd.FLAG_TENSOR_CORE_IDCT,
                              "planes": hjd.FLAG_KEEP_PLANES}[request.param])
     d.keeps_planes = request.param == "planes"
     yield d
