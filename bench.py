@@ -625,7 +625,10 @@ def run_ours(args, rank, local_rank, world):
                            "images_per_gpu": n, "scan_bytes_per_image": scan_bytes // max(n, 1),
                            "l2_policy": f"per-step working set (coefficient + RGB slabs, {working_set / 1e9:.2f} GB on rank 0) "
                                         "against a 126 MB L2; every step rewrites all of it",
-                           "parallelism": f"{world} independent shards ({args.scaling} scaling), no collective"},
+                           "parallelism": f"{world} independent shards ({args.scaling} scaling), no collective",
+                           "idct_kernel": {1: "tensor cores: tcgen05.mma, FP16 x FP16 -> FP32 with exact integer accumulation (csrc/mcu_tc.cuh)",
+                                           2: "CUDA cores: FP32 FMA chains (csrc/kernels.cu)",
+                                           3: "tensor cores and CUDA cores, chosen per chunk"}.get(dec.idct_variant, "none")},
                 "compressed_GB_per_s": round(job_scan * args.steps / (ms_max / 1e3) / 1e9, 2),
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1),

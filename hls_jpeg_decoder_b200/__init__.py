@@ -91,6 +91,7 @@ _SIGS = {
     "hjd_batch_set_selfsync_range": (c_int, [c_void_p, c_int]),
     "hjd_batch_num_images": (c_int, [c_void_p]),
     "hjd_batch_selfsync_rounds": (c_int, [c_void_p]),
+    "hjd_batch_idct_variant": (c_int, [c_void_p]),
     "hjd_batch_get_info": (c_int, [c_void_p, c_int, POINTER(ImageInfo)]),
     "hjd_batch_get_status": (c_int, [c_void_p, c_void_p]),
     "hjd_batch_get_timings": (c_int, [c_void_p, POINTER(Timings)]),
@@ -352,6 +353,11 @@ class BatchDecoder:
     @property
     def selfsync_rounds(self) -> int:
         return lib().hjd_batch_selfsync_rounds(self._h)
+
+    @property
+    def idct_variant(self) -> int:
+        """bit 0: chunks of the last decode went through the tensor-core fused kernel; bit 1: through the CUDA-core one"""
+        return lib().hjd_batch_idct_variant(self._h)
 
     @property
     def num_images(self) -> int:

@@ -148,6 +148,7 @@ struct hjd_batch {
     bool any_parse_error = false;
     bool uploaded = false, decoded = false;
     int launches = 0;
+    int tc_chunks = 0, cc_chunks = 0;           // chunks of the last decode whose MCUs went through the tensor-core / CUDA-core fused kernel
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_planes, d_rgb, d_status;
     DevBuf d_ss, d_sswork, d_sssegs, d_destuff, d_dlen, d_counts, d_scantmp, d_ssE0, d_ssX, d_ssnb, d_flag;
@@ -856,10 +857,12 @@ static int launch_chunk(hjd_batch* b, const Chunk& c, size_t chunk_index, cudaSt
         // default: kernels 2+3 fused per MCU, planes never reach HBM
         if (c.blocks) {
             const uint32_t n_mcus_chunk = b->mcu_cta[c.img1] - b->mcu_cta[c.img0];
+            const int variant = mcu_variant(b->flags, c.blocks, n_mcus_chunk, (uint32_t)n);
+            if (variant == HJD_MCU_TENSOR_CORE) b->tc_chunks++; else b->cc_chunks++;
             CU(hjd_launch_mcu_rgb((const int16_t*)b->d_coef.p, imgs + c.img0, (const HjdQuantSet*)b->d_qsets.p,
                                   (uint8_t*)b->d_rgb.p, (const uint32_t*)b->d_mcucta.p + c.img0, n,
                                   b->mcu_cta[c.img1] - b->mcu_cta[c.img0], c.max_mcus, (b->flags & HJD_FLAG_BMP_OUT) != 0,
-                                  mcu_variant(b->flags, c.blocks, n_mcus_chunk, (uint32_t)n), st));
+                                  variant, st));
             b->launches += 1;
         }
         if (ev) CU(cudaEventRecord(ev[3], st));
@@ -883,6 +886,7 @@ static int run_chunks(hjd_batch* b, bool h2d, uint8_t* rgb_host)
 {
     cudaStream_t main = b->stream;
     b->launches = 0;
+    b->tc_chunks = b->cc_chunks = 0;
     b->ss_ran = false;
     if (b->any_parse_error && b->rgb_bytes) CU(cudaMemsetAsync(b->d_rgb.p, 0, b->rgb_bytes, main));
     CU(cudaEventRecord(b->ev[0], main));
@@ -951,6 +955,11 @@ extern "C" int hjd_batch_sync(hjd_batch* b)
 }
 
 extern "C" int hjd_batch_num_images(const hjd_batch* b) { return b ? (int)b->imgs.size() : 0; }
+extern "C" int hjd_batch_idct_variant(const hjd_batch* b)
+{
+    if (!b || (b->flags & HJD_FLAG_KEEP_PLANES)) return 0;
+    return (b->tc_chunks ? 1 : 0) | (b->cc_chunks ? 2 : 0);
+}
 extern "C" int hjd_batch_selfsync_rounds(hjd_batch* b)
 {
     // rounds the device-side loop ran in the last decode (working rounds + the one that confirmed); syncs

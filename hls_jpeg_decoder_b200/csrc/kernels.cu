@@ -10,7 +10,9 @@
 // The MCU raster loop of JpegDecodeHW (1134-1190) becomes the grid: every restart interval,
 // 8x8 block and pixel run of every image of the batch is an independent unit of work.
 //
-// All of it is HBM-bound integer/byte work plus a small FP32 IDCT; no tensor cores on purpose.
+// Integer / byte work plus a small FP32 IDCT.  The IDCT's fast tier exists twice: as FP32 FMA chains on the CUDA cores
+// (hjd_idct_block, below) and as tcgen05.mma on the tensor cores (mcu_tc.cuh, included at the end of this file); the host
+// picks per chunk (mcu_variant, hjd_api.cu).  Both feed the same exact re-evaluation and give the reference's bytes.
 #include "kernels.cuh"
 #include "device_common.cuh"
 #include <cuda_runtime.h>

@@ -171,6 +171,9 @@ int  hjd_batch_selfsync_rounds(hjd_batch* b);                        /* syncs */
 /* Sub-sequences per warp in those rounds: 0 = pick by batch size (default), else a multiple of 32 up
  * to 256 (testing / tuning; results do not depend on it).  Takes effect at the next upload. */
 int  hjd_batch_set_selfsync_range(hjd_batch* b, int range);
+/* Which fused kernel(s) the chunks of the last decode went through: bit 0 = tensor cores (csrc/mcu_tc.cuh), bit 1 = CUDA
+ * cores; 0 = none (nothing decoded yet, or HJD_FLAG_KEEP_PLANES). */
+int  hjd_batch_idct_variant(const hjd_batch* b);
 int  hjd_batch_num_images(const hjd_batch* b);
 int  hjd_batch_get_info(const hjd_batch* b, int i, hjd_image_info* out);
 int  hjd_batch_get_status(hjd_batch* b, int32_t* status /* n */);   /* syncs */
