@@ -533,6 +533,7 @@ def run_ours(args, rank, local_rank, world):
     for k in stage:
         stage[k] = t[k]
     launches = t["launches"]
+    idct_variant = dec.idct_variant          # which fused kernel(s) the timed decodes went through (read while the batch is alive)
 
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(pixels), float(scan_bytes), float(alg_bytes), float(n), float(launches * args.steps)],
@@ -628,7 +629,7 @@ def run_ours(args, rank, local_rank, world):
                            "parallelism": f"{world} independent shards ({args.scaling} scaling), no collective",
                            "idct_kernel": {1: "tensor cores: tcgen05.mma, FP16 x FP16 -> FP32 with exact integer accumulation (csrc/mcu_tc.cuh)",
                                            2: "CUDA cores: FP32 FMA chains (csrc/kernels.cu)",
-                                           3: "tensor cores and CUDA cores, chosen per chunk"}.get(dec.idct_variant, "none")},
+                                           3: "tensor cores and CUDA cores, chosen per chunk"}.get(idct_variant, "none")},
                 "compressed_GB_per_s": round(job_scan * args.steps / (ms_max / 1e3) / 1e9, 2),
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                 "roofline": {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": round(achieved, 1),

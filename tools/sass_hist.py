@@ -4,7 +4,8 @@
 
 Columns: total instructions, then the opcodes that carry the design (packed FP32x2 FMAs, 256-bit loads,
 fused truncate+saturate+pack conversions, dot-product de-quantisation, warp votes / reductions, shared-memory
-traffic) and the tensor / TMA opcodes that are deliberately absent.
+traffic) and the tcgen05 opcodes of the tensor-core fused kernel (UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit,
+LDTM = tcgen05.ld, UTCATOMSWS = TMEM allocation, SYNCS = mbarrier); HMMA / IMMA (mma.sync) and TMA tensor loads are absent.
 """
 import collections
 import os
@@ -15,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WATCH = ["FFMA2", "FFMA", "FMUL2", "FADD2", "FADD", "FMUL", "LDG.E.256", "LDG.E.128", "LDG", "STG.E.128", "STG", "LDS", "STS",
          "F2IP", "F2I", "I2F", "I2FP", "IDP", "PRMT", "SHF", "LOP3", "VOTE", "REDUX", "SHFL", "BAR", "ATOMS", "LDC",
-         "UTMALDG", "UTCHMMA", "UTCQMMA", "HMMA", "IMMA", "LDL", "STL"]
+         "HFMA2", "HADD2", "HMUL2", "UTMALDG", "UTCHMMA", "UTCBAR", "LDTM", "SYNCS", "UTCATOMSWS", "HMMA", "IMMA", "LDL", "STL"]
 
 
 def main():
