@@ -148,6 +148,7 @@ struct hjd_batch {
     bool any_parse_error = false;
     bool uploaded = false, decoded = false;
     int launches = 0;
+    int sm_count = 148;                         // multiprocessors of this device (work-list balancing)
     int tc_chunks = 0, cc_chunks = 0;           // chunks of the last decode whose MCUs went through the tensor-core / CUDA-core fused kernel
 
     DevBuf d_arena, d_imgs, d_tsets, d_qsets, d_work, d_segs, d_mcucta, d_slices, d_slicecnt, d_istart, d_coef, d_planes, d_rgb, d_status;
@@ -212,6 +213,7 @@ extern "C" hjd_batch* hjd_batch_create(int device, unsigned flags)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = hjd_kernels_init_device();            // function attributes are per device
     if (e == cudaSuccess) e = hjd_selfsync_init_device(&b->max_sync_ctas);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
         float cos_tab[64], c0, c00;
         compute_idct_constants(cos_tab, &c0, &c00);
@@ -511,6 +513,23 @@ static int upload_common(hjd_batch* b, bool chunked)
             for (int i = c.img0; i < c.img1; i++) if (b->imgs[i].n_intervals) order.push_back(i);
             std::stable_sort(order.begin(), order.end(),
                              [&](int x, int y) { return b->imgs[x].table_set < b->imgs[y].table_set; });
+            // Intervals per CTA.  A big chunk fills its CTAs (HJD_ENT_THREADS).  A chunk of only a few waves -- one 1024-image
+            // batch cut over 8 GPUs is 0.86 of a wave -- is cut into a whole number of waves of equally loaded CTAs instead:
+            // with 510 full CTAs on 592 slots the SMs that got four of them set the time; 592 CTAs of 221 intervals finish
+            // in 0.86 of it.  (Below half a wave the CTAs stay full: fewer table loads, and nothing to balance.)
+            uint32_t cap = HJD_ENT_THREADS;
+            {
+                uint64_t total = 0;
+                for (int i : order) total += b->imgs[i].n_intervals;
+                const uint64_t slots = (uint64_t)b->sm_count * HJD_ENT_MINBLOCKS;
+                const uint64_t full = (total + HJD_ENT_THREADS - 1) / HJD_ENT_THREADS;
+                if (2 * full >= slots && full <= 4 * slots) {
+                    const uint64_t n_ctas = (full + slots - 1) / slots * slots;
+                    cap = (uint32_t)((total + n_ctas - 1) / n_ctas);
+                    if (cap > HJD_ENT_THREADS) cap = HJD_ENT_THREADS;
+                    if (cap < 32) cap = 32;
+                }
+            }
             HjdEntropyWork w{0, 0, 0, 0};
             auto flush = [&]() {
                 if (w.n_intervals) b->work.push_back(w);
@@ -522,9 +541,9 @@ static int upload_common(hjd_batch* b, bool chunked)
                 if (w.n_intervals && w.table_set != d.table_set) flush();
                 uint32_t left = d.n_intervals, g = d.interval_base;
                 while (left) {
-                    if (w.n_intervals == HJD_ENT_THREADS) flush();
+                    if (w.n_intervals == cap) flush();
                     w.table_set = d.table_set;
-                    const uint32_t take = left < (HJD_ENT_THREADS - w.n_intervals) ? left : (HJD_ENT_THREADS - w.n_intervals);
+                    const uint32_t take = left < (cap - w.n_intervals) ? left : (cap - w.n_intervals);
                     b->segs.push_back(HjdEntropySeg{g, w.n_intervals, (uint32_t)i, take});
                     w.n_segs++;
                     w.n_intervals += take; g += take; left -= take;
