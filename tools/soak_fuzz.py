@@ -2,7 +2,7 @@
 between.  Every call must return, the good files must decode exactly as they do alone, and the
 outcome (status and output bytes) must not depend on what the slabs held before.
 
-    python tools/soak_fuzz.py [rounds] [seed]
+    python tools/soak_fuzz.py [rounds] [seed] [hjd_batch_create flags, e.g. 128 = HJD_FLAG_TENSOR_CORE_IDCT]
 """
 import os
 import sys
@@ -40,11 +40,12 @@ def damage(jpg: bytes, rng) -> bytes:
 def main():
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     import hls_jpeg_decoder_b200 as hjd
     from tools.soak_parity import make
     rng = np.random.default_rng(seed)
     good = make(0, seed, 640, 480)
-    with hjd.BatchDecoder(0) as d:
+    with hjd.BatchDecoder(0, flags) as d:
         d.upload([good])
         d.decode()
         assert d.status()[0] == 0
@@ -72,7 +73,7 @@ def main():
                 n_bad += 1
             n_rejected += int((outs[0][0] < 0).sum())
             n_warn += int((outs[0][0] > 0).sum())
-    print(f"fuzz soak: {rounds} rounds x 64 damaged files, seed {seed}: {n_rejected} rejected by the parser, "
+    print(f"fuzz soak: {rounds} rounds x 64 damaged files, seed {seed}, flags {flags}: {n_rejected} rejected by the parser, "
           f"{n_warn} decoded with warnings, {n_bad} failures")
     sys.exit(1 if n_bad else 0)
 
