@@ -227,11 +227,13 @@ def test_decode_host_end_to_end(hjd, port):
     arena.close()
 
 
-def test_chunked_overlapped_execution_matches_serial(hjd, port):
+@pytest.mark.parametrize("flags", [0, "tensor_core"])
+def test_chunked_overlapped_execution_matches_serial(hjd, port, flags):
     """Multi-stream chunked execution (forced with a tiny blocks-per-chunk target) gives the same
-    bytes as the serial path, resident and host-buffer variants."""
+    bytes as the serial path, resident and host-buffer variants -- also with the tensor-core kernel on every
+    chunk (persistent CTAs that hold all of an SM's TMEM and shared memory, launched from three streams)."""
     files = list(cases.small_cases().values())
-    with hjd.BatchDecoder(0) as d:
+    with hjd.BatchDecoder(0, hjd.FLAG_TENSOR_CORE_IDCT if flags else 0) as d:
         d.set_overlap(0)
         d.upload(files)
         d.decode()
