@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = ["probe", "MultiDecoder", "shard_range_c", "ConvertJpgFile", "ConvertJpgFiles", "DecodeJpgFileData", "JpegGetImageSize", "WriteBMP24", "encode_bmp24",
            "BatchDecoder", "HjdError", "lib", "build", "LIB_PATH",
-           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU", "FLAG_BMP_OUT", "FLAG_TENSOR_CORE_IDCT", "FLAG_CUDA_CORE_IDCT"]
+           "FLAG_KEEP_PLANES", "FLAG_HOST_SCAN", "FLAG_NO_SELFSYNC", "FLAG_FUSED_MCU", "FLAG_BMP_OUT", "FLAG_TENSOR_CORE_IDCT", "FLAG_CUDA_CORE_IDCT", "idct_matrix", "idct_tables"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HJD_LIB_PATH") or os.path.join(_HERE, "libhjd.so")   # override: tuning builds only
@@ -122,6 +122,7 @@ _SIGS = {
     "hjd_device_numa_node": (c_int, [c_int]),
     "hjd_link_probe": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_int, POINTER(c_float), POINTER(c_float)]),
     "hjd_get_idct_tables": (None, [c_void_p, c_void_p]),
+    "hjd_get_idct_matrix": (None, [c_void_p]),
     "hjd_decode_jpg_file_data_alloc": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_void_p), POINTER(c_uint), POINTER(c_uint)]),
     "hjd_set_default_device": (c_int, [c_int]),
     "hjd_convert_jpg_files_multi": (c_int, [POINTER(c_char_p), POINTER(c_char_p), c_int, POINTER(c_int), c_int, c_int, c_int, POINTER(c_int)]),
@@ -519,6 +520,24 @@ def link_probe(device: int, host_in_ptr: int, h2d_bytes: int, host_out_ptr: int,
 
 def rgb_slab_bytes(arena: PinnedArena) -> int:
     return int(lib().hjd_rgb_slab_bytes(arena.ptr, arena.offsets, arena.sizes, arena.n))
+
+
+def idct_matrix():
+    """(M_hi, M_lo): the two integer matrices [zig-zag position k][sample 8y+x] of the tensor-core kernel, read back from the
+    FP16 tile image hjd_get_idct_matrix builds (un-swizzled here): M = (M_hi * 2^11 + M_lo) * 2^-24 up to 2^-25."""
+    img = np.zeros(8192, dtype=np.uint16)
+    lib().hjd_get_idct_matrix(img.ctypes.data)
+    h = img.view(np.float16).astype(np.float64)
+    hi = np.zeros((64, 64)); lo = np.zeros((64, 64))
+    for row in range(128):
+        for k in range(64):
+            off = (row >> 3) * 1024 + (row & 7) * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2
+            v = h[off // 2]
+            if row < 64:
+                hi[k, row] = v * 8192.0
+            else:
+                lo[k, row - 64] = v
+    return hi, lo
 
 
 def idct_tables():

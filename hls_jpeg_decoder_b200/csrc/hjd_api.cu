@@ -184,6 +184,13 @@ extern "C" void hjd_get_idct_tables(float cos_tab[64], float cc[64])
         for (int v = 0; v < 8; v++) cc[u * 8 + v] = (u == 0 && v == 0) ? c00 : ((u == 0 || v == 0) ? c0 : 1.0f);
 }
 
+extern "C" void hjd_get_idct_matrix(uint16_t img[8192])
+{
+    float cos_tab[64], c0, c00;
+    compute_idct_constants(cos_tab, &c0, &c00);
+    hjd_build_idct_matrix(cos_tab, c0, c00, img);
+}
+
 extern "C" int hjd_version(void) { return HJD_VERSION; }
 extern "C" const char* hjd_last_error(void) { return g_err.c_str(); }
 

@@ -1119,9 +1119,8 @@ hjd_k_mcu_rgb(const int16_t* __restrict__ coef, const HjdImageDesc* __restrict__
 // real-number product of the reference's float constants, split into M_hi * 2^-13 and M_lo (integers, exact in FP16)
 // and laid out as the K-major, 128-byte-swizzled shared-memory tile tcgen05.mma reads: row n (0..63: M_hi of sample
 // n = 8y+x; 64..127: M_lo), 64 FP16 per row in zig-zag order, 16-byte chunk j of row n at chunk j ^ (n & 7).
-static cudaError_t hjd_set_idct_matrix(const float cos_tab[64], float cc0, float cc00)
+void hjd_build_idct_matrix(const float cos_tab[64], float cc0, float cc00, uint16_t img[8192])
 {
-    static uint16_t img[HJD_TC_TILE_BYTES / 2];
     for (int k = 0; k < 64; k++) {
         const int nat = hjd_zz(k), u = nat & 7, v = nat >> 3;
         const double cc = nat == 0 ? (double)cc00 : ((u == 0 || v == 0) ? (double)cc0 : 1.0);
@@ -1139,6 +1138,12 @@ static cudaError_t hjd_set_idct_matrix(const float cos_tab[64], float cc0, float
                 }
             }
     }
+}
+
+static cudaError_t hjd_set_idct_matrix(const float cos_tab[64], float cc0, float cc00)
+{
+    static uint16_t img[HJD_TC_TILE_BYTES / 2];
+    hjd_build_idct_matrix(cos_tab, cc0, cc00, img);
     return cudaMemcpyToSymbol(g_idct_mat, img, sizeof img);
 }
 

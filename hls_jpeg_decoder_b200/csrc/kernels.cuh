@@ -20,6 +20,11 @@ cudaError_t hjd_kernels_init_device(void);
 // Upload the IDCT constants (host libm values, loadjpg.cpp:96-102,120).
 cudaError_t hjd_set_idct_constants(const float cos_tab[64], float cc0, float cc00);
 
+// The tensor-core kernel's IDCT matrix as the 16 KB FP16 tile image it keeps in shared memory (host computation; see mcu_tc.cuh):
+// row n of 128 (0..63: M_hi * 2^-13 of sample n = 8y+x; 64..127: M_lo), 64 FP16 per row in zig-zag order, 16-byte chunk j of
+// row n stored at chunk j ^ (n & 7) (128-byte swizzle), rows in 1024-byte groups of eight.
+void hjd_build_idct_matrix(const float cos_tab[64], float cc0, float cc00, uint16_t img[8192]);
+
 // Kernel 0: RSTn marker scan -> interval_start[] (one CTA per image), images [first_image, first_image + n);
 // scans longer than HJD_SCAN_SLICE_MIN are done by the n_slices slice CTAs instead (count, then number).
 cudaError_t hjd_launch_marker_scan(const uint8_t* arena, const HjdImageDesc* imgs, uint32_t* interval_start,

@@ -251,6 +251,12 @@ uint32_t hjd_huff_lookup_probe(const uint8_t bits[16], const uint8_t* vals, int 
 /* The float constants the kernels use (computed on the host with the libm expressions of
  * loadjpg.cpp:96-102,120): cos_tab[p*8+k] = cosf(((2p+1)*k*3.14f)/16), cc[u*8+v] = C(u)*C(v). */
 void hjd_get_idct_tables(float cos_tab[64], float cc[64]);
+/* The IDCT matrix of the tensor-core kernel as the 16 KB FP16 tile image it multiplies by (csrc/mcu_tc.cuh): with
+ * M[k][8y+x] = 0.25 * cc * cos[x][u] * cos[y][v] for zig-zag position k = (u, v) (the real-number product of the constants
+ * above), row n of 128 holds M_hi * 2^-13 (n = 8y+x) or M_lo (n = 64 + 8y+x), integers with M = (M_hi * 2^11 + M_lo) * 2^-24
+ * up to 2^-25; 64 FP16 per row in zig-zag order, 16-byte chunk j of row n stored at chunk j ^ (n & 7), rows in 1024-byte
+ * groups of eight (the K-major, 128-byte-swizzled operand layout of tcgen05.mma).  Host computation, no GPU needed. */
+void hjd_get_idct_matrix(uint16_t img[8192]);
 
 #ifdef __cplusplus
 }
