@@ -41,6 +41,10 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#ifndef HJD_TC_WAIT_NS
+#define HJD_TC_WAIT_NS 100    // sleep between two looks at an mbarrier that has not completed yet
+#endif
+
 // ---- tcgen05 / mbarrier PTX -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t hjd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void hjd_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
@@ -49,7 +53,12 @@ __device__ __forceinline__ void hjd_mbar_wait(uint32_t bar, uint32_t parity)
     uint32_t ok, spins = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 26)) __trap();      // a lost MMA must end the kernel, not hang the device
+        if (!ok) {
+            // not yet: sleep instead of spinning (a failed attempt returns after ~100 cycles; fifteen of them per wait were
+            // 9 % of all the instructions this kernel issued, in slots the other warps of the SM could have used)
+            __nanosleep(HJD_TC_WAIT_NS);
+            if (++spins > (1u << 24)) __trap();         // a lost MMA must end the kernel, not hang the device
+        }
     } while (!ok);
 }
 __device__ __forceinline__ void hjd_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
