@@ -224,11 +224,13 @@ def test_short_block_idct_variant_on_every_block_length(hjd, port):
                             assert np.array_equal(a, b), names[i]
 
 
-def test_multi_device_handle_matches_single_device(hjd, port):
+@pytest.mark.parametrize("tensor_core", [False, True])
+def test_multi_device_handle_matches_single_device(hjd, port, tensor_core):
     """hjd_multi_*: the batch cut into contiguous ranges balanced by compressed bytes, one handle + one host
     thread per device.  With one visible GPU two handles share it (the sharding, offsets and threading are
     the same); with more, every device takes part.  Every image must be exactly the single-handle result --
-    including a six-table image that lands on the second handle."""
+    including a six-table image that lands on the second handle.  tensor_core: every handle uses the tensor-core
+    fused kernel (persistent CTAs that take a whole SM each, launched concurrently from the handles' host threads)."""
     n_dev = hjd.lib().hjd_device_count()
     six, src = six_table_image(port)
     base = list(cases.small_cases().values())
@@ -240,7 +242,7 @@ def test_multi_device_handle_matches_single_device(hjd, port):
         ref_offs, st = d.decode_host(arena, ref.ctypes.data, need)
     assert (st == 0).all()
     for devices in ([0, 0], [0, 0, 0], list(range(n_dev)) if n_dev > 1 else [0]):
-        with hjd.MultiDecoder(devices) as m:
+        with hjd.MultiDecoder(devices, hjd.FLAG_TENSOR_CORE_IDCT if tensor_core else 0) as m:
             cap = m.out_slab_bytes(arena)
             assert cap >= need
             out = np.zeros(cap, dtype=np.uint8)
