@@ -9,7 +9,7 @@
 // Truncation is discontinuous, so the decoder works in two tiers: a fast evaluation with a PROVEN error bound,
 // and a re-evaluation in the reference's own order of operations of the few samples that land within that
 // bound of an integer.  hjd_idct_block (kernels.cu) runs the fast tier as FP32 FMA chains, 16 per sample, and is
-// bound by instruction issue.  Here the fast tier is one tcgen05.mma sequence per 128 blocks:
+// bound by the FMA pipe (64 % busy; the passes and the de-quantisation are two thirds of its cycles).  Here the fast tier is one tcgen05.mma sequence per 128 blocks:
 //
 //     D[128 blocks x 128] (TMEM, FP32)  =  V[128 x 64] (FP16, shared memory)  x  [M_hi | M_lo]^T (FP16, shared memory)
 //
@@ -234,7 +234,7 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
     const uint64_t vdesc0 = hjd_smem_desc_sw128(hjd_smem_u32(sV)), mdesc = hjd_smem_desc_sw128(hjd_smem_u32(sM));
     const uint32_t tacc = tmem + 128u * grp;                      // this group's accumulator: 128 lanes x 128 columns
     const uint32_t taddr = tacc + (((warp & 3u) * 32u) << 16);    // a warp reads the 32 lanes of its quarter
-    uint8_t* const vrow0 = sV + tg * 128u;                        // this thread's row in tile 0; tile 1 is HJD_TC_TILE_BYTES further
+    uint8_t* const vrow0 = sV + tg * 128u;                        // this thread's row of the group's V tile
     const uint32_t vrow0_s = hjd_smem_u32(vrow0);
     constexpr uint32_t kPitch = HJD_TC_THREADS * 8;
     constexpr uint32_t kTile = 8 * kPitch;
@@ -311,10 +311,11 @@ hjd_k_mcu_rgb_tc(const int16_t* __restrict__ coef, const HjdImageDesc* __restric
         }
         const int n_steps = s_nsteps[grp];                            // of this group: its barrier and its MMAs are its own
 
-        // One loop, software-pipelined: iterations 0,1 = Cb, Cr (colour images), then the Y blocks in decode order; after the last
+        // One loop, software-pipelined: steps 0,1 = Cb, Cr (colour images), then the Y blocks in decode order; after the last
         // Y block of a block row, that row of the MCU (8 or 16 pixels wide) goes out as RGB.  Iteration `it`:
-        //   barrier -> MMA(it) issued -> conversion of block it + 1 into the other V tile (the MMA runs meanwhile) -> MMA(it) done
-        //   -> request of block it + 2 into the tile just read -> samples, exact re-evaluation, colour of block it.
+        //   check-in (the last warp of the group issues MMA(it)) -> block it + 1 loaded and converted in registers (the MMA runs
+        //   meanwhile) -> MMA(it) done -> block it + 1 stored into the V tile -> block it + 2 requested into the L2
+        //   -> samples, exact re-evaluations, colour of block it.
         // Iteration -1 only converts block 0.
         float win = 0.f, n_win = 0.f;         // re-evaluation window on the 0.25*sum scale (0: no sample can be flagged), of block it / it + 1
         uint32_t fl = 0, n_fl = 0;            // bit 0: outside the fast tier's preconditions (all 64 samples exact); bit 1: DC-only
